@@ -1,0 +1,86 @@
+"""CPU tests: pin the oracle restatement against the reference's own outputs
+(committed golden vectors made by tests/golden/make_golden.py from
+/root/reference/ops.py:92-140) and check its internal consistency."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import nets, ref_ops
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "wct_np_*.npz")))
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[7:-4] for p in GOLDEN])
+def test_wct_np_restatement_matches_reference_golden(path):
+    g = np.load(path)
+    out, info = ref_ops.wct_np(g["content"], g["style"], float(g["alpha"]), return_info=True)
+    assert out.dtype == np.float32  # ops.py:140
+    assert info["k_c"] == int(g["k_c"]) and info["k_s"] == int(g["k_s"])
+    # same arithmetic, same LAPACK: the fp32 restatement reproduces the reference run to fp32 noise
+    assert np.abs(out - g["out_ref_fp32"]).max() <= 2e-4
+    out64 = ref_ops.wct_np(g["content"].astype(np.float64), g["style"].astype(np.float64), float(g["alpha"]))
+    assert np.abs(out64 - g["out_ref_fp64"]).max() <= 1e-6
+    assert ref_ops.spectral_gap_ok(g["wc"]) and ref_ops.spectral_gap_ok(g["ws"])
+
+
+def test_live_reference_import_if_present():
+    ref = ref_ops.load_reference_ops()
+    if ref is None:
+        pytest.skip("/root/reference not present (GPU box)")
+    g = np.load(GOLDEN[0])
+    out = ref.wct_np(g["content"], g["style"], float(g["alpha"]))
+    assert np.array_equal(out, g["out_ref_fp32"])
+
+
+def test_np_vs_tf_semantics_differ_only_as_documented():
+    # SURVEY 8a "np-vs-tf deltas": at alpha=1 the blend term vanishes; the remaining
+    # difference is eps placement (1e-8 on cov vs 1e-5 on eigenvalues)
+    g = np.load(GOLDEN[0])
+    c, s = g["content"].astype(np.float64), g["style"].astype(np.float64)
+    a = ref_ops.wct_generic(c, s, 1.0, eps_cov=0.0, eps_eig=0.0, readd_content_mean=False)
+    b = ref_ops.wct_generic(c, s, 1.0, eps_cov=0.0, eps_eig=0.0, readd_content_mean=True)
+    assert np.abs(a - b).max() < 1e-12
+    t = ref_ops.wct_tf(c, s, 0.5)
+    n = ref_ops.wct_generic(c, s, 0.5, eps_cov=1e-8, eps_eig=0.0, readd_content_mean=False)
+    mc = c.reshape(-1, c.shape[-1]).mean(0)
+    assert np.allclose(t - n, 0.5 * mc, atol=1e-9)
+
+
+def test_adain_matches_definition():
+    rng = np.random.default_rng(0)
+    c = rng.random((1, 6, 5, 8)); s = rng.random((1, 4, 7, 8)) * 3 + 1
+    y = ref_ops.adain(c, s, 1.0, epsilon=0.0)
+    assert np.allclose(y.mean((1, 2)), s.mean((1, 2)))
+    assert np.allclose(y.var((1, 2)), s.var((1, 2)))
+    y2 = ref_ops.adain(c, s, 0.25)
+    y1 = ref_ops.adain(c, s, 1.0)
+    assert np.allclose(y2, 0.25 * y1 + 0.75 * c)
+
+
+def test_decoder_layer_names_match_reference_table():
+    # model.py:283-298: relu5_1 -> layers 0..15 + output 16 (convs and upsamples both counted)
+    l5 = nets.decoder_layers("relu5_1")
+    assert [n for _, n, _, _ in l5] == ["relu5_1_%d" % i for i in range(17)]
+    assert [t for t, _, _, _ in l5].count("up") == 4
+    assert l5[-1][2] == 3 and l5[-1][3] is False
+    assert [n for _, n, _, _ in nets.decoder_layers("relu1_1")] == ["relu1_1_0", "relu1_1_1"]
+
+
+def test_encoder_shapes_and_pool_same():
+    from wct_tf_b200.weights import make_synthetic_weights
+    w = make_synthetic_weights(0)
+    x = np.random.default_rng(0).random((1, 22, 18, 3)).astype(np.float32)
+    f = nets.encode(x, w, ["relu1_1", "relu2_1", "relu3_1", "relu4_1", "relu5_1"])
+    assert f["relu1_1"].shape == (1, 22, 18, 64)
+    assert f["relu2_1"].shape == (1, 11, 9, 128)
+    assert f["relu3_1"].shape == (1, 6, 5, 256)   # ceil: MaxPooling2D(padding='same')
+    assert f["relu4_1"].shape == (1, 3, 3, 512)
+    assert f["relu5_1"].shape == (1, 2, 2, 512)
+    y = nets.decode(f["relu3_1"], w, "relu3_1")
+    assert y.shape == (1, 24, 20, 3)

@@ -1,0 +1,70 @@
+"""Weight containers for the WCT engine, in the REFERENCE's layouts.
+
+The reference loads
+  * the shared encoder from ``vgg_normalised.t7`` (vgg_normalised.py:16-38): conv
+    weights (O,I,kH,kW) float32 + bias (O,), transposed to (kH,kW,I,O) at
+    vgg_normalised.py:33;
+  * one TF checkpoint per decoder (wct.py:47-56): Keras Conv2D kernels
+    (3,3,Cin,Cout) + bias (Cout,), layers named ``{relu}_{count}`` (model.py:288).
+
+Neither file exists offline, so benchmarks and parity tests use seeded
+synthetic weights in exactly those layouts (``make_synthetic_weights``).
+
+A weights dict is
+  {"vgg":      [ {"name", "weight" (O,I,kH,kW), "bias" (O,)} ... in module order ],
+   "decoders": { relu: [ {"name", "kernel" (3,3,Cin,Cout), "bias" (Cout,)} ... ] } }
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .model import VGG_CONVS, decoder_plan, RELU_TARGETS_ALL
+
+# BGR channel means of the caffe VGG the normalised .t7 was converted from
+# (vgg_normalised.py:26 comment: "multiply by 255 and subtract BGR mean as bias").
+_BGR_MEAN = np.array([103.939, 116.779, 123.68], dtype=np.float64)
+
+
+def make_synthetic_weights(seed=42, relu_targets=RELU_TARGETS_ALL, act_rms=1.4,
+                           bias_gain=0.3, dec_gain=0.22):
+    """Seeded synthetic weights in the reference layouts.
+
+    He-normal 3x3 filters made zero-sum per output filter (no common-mode drive,
+    so no channel dies) plus a positive bias ``bias_gain*act_rms``: every relu map
+    stays O(1) at every depth (the 'normalised VGG' convention) and the feature
+    covariances are well conditioned (no eigenvalue near the hard 1e-5 cut of
+    ops.py:112 -- see SURVEY 8c; tests/golden/make_golden.py asserts the gap).
+    conv0 is the documented 1x1 preprocess conv; each decoder ends in a
+    3-filter conv landing around 0.5 +- ``dec_gain``.  Deterministic in ``seed``."""
+    rng = np.random.default_rng(seed)
+    vgg = []
+    # conv0 "preprocess": x*255, RGB->BGR, minus BGR mean (vgg_normalised.py:25-26)
+    w0 = np.zeros((3, 3, 1, 1), dtype=np.float32)
+    for o in range(3):
+        w0[o, 2 - o, 0, 0] = 255.0
+    vgg.append(dict(name="preprocess", weight=w0, bias=(-_BGR_MEAN).astype(np.float32)))
+    for name, cin, cout in VGG_CONVS:
+        std = np.sqrt(2.0 / (9 * cin))
+        if name == "conv1_1":
+            std *= act_rms / 80.0  # input ~ 255*U(0,1) - mean: rms ~ 80
+        w = rng.normal(0.0, std, size=(cout, cin, 3, 3))
+        if name != "conv1_1":
+            w -= w.mean(axis=(1, 2, 3), keepdims=True)
+        b = np.full(cout, bias_gain * act_rms) + rng.normal(0.0, 0.01, size=cout)
+        vgg.append(dict(name=name, weight=w.astype(np.float32), bias=b.astype(np.float32)))
+    decoders = {}
+    for relu in relu_targets:
+        layers = []
+        for op in decoder_plan(relu):
+            if op.kind != "conv":
+                continue
+            if op.act:
+                k = rng.normal(0.0, np.sqrt(2.0 / (9 * op.cin)), size=(3, 3, op.cin, op.cout))
+                b = np.full(op.cout, bias_gain * act_rms) + rng.normal(0.0, 0.01, size=op.cout)
+            else:  # final 3-channel conv: land around [0,1]
+                k = rng.normal(0.0, dec_gain / (act_rms * np.sqrt(9 * op.cin)), size=(3, 3, op.cin, op.cout))
+                b = np.full(op.cout, 0.5)
+            k -= k.mean(axis=(0, 1, 2), keepdims=True)
+            layers.append(dict(name=op.name, kernel=k.astype(np.float32), bias=b.astype(np.float32)))
+        decoders[relu] = layers
+    return dict(vgg=vgg, decoders=decoders)
