@@ -1,0 +1,141 @@
+/*
+ * libwctb200 -- C-ABI of the B200-native WCT inference hot path.
+ *
+ * The reference (eridgd/WCT-TF) has no native boundary: its operator surface is
+ * Python (`WCT.predict` wct.py:70, `WCTModel` model.py:33, `wct_np/wct_tf/adain`
+ * ops.py:24,92,282) executed inside one TF `sess.run` (wct.py:97).  This header
+ * is the boundary a maintainer binds with ctypes; every
+ * entry point names the reference code it replaces.
+ *
+ * Conventions (all functions):
+ *   - return 0 on success, <0 on error (WCTB200_E*); `wctb200_last_error()` gives a
+ *     thread-local message; nothing throws;
+ *   - plain pointers and sizes only; every buffer is a CUDA DEVICE pointer owned by
+ *     the caller (e.g. `torch.Tensor.data_ptr()`), kept alive until `stream` is synced;
+ *   - asynchronous on `stream` (a `cudaStream_t` passed as void*; 0 = default stream);
+ *     the caller selects the device (`cudaSetDevice`) before the call;
+ *   - no CPU fallback: without an sm_100 device the kernels fail with WCTB200_ECUDA.
+ *
+ * Activation format "SPF16" (split-pair fp16, reflect-padded NHWC):
+ *   one allocation of `wctb200_act_bytes(N,H,W,C)` bytes holding two fp16 planes
+ *   [plane 0 = hi | plane 1 = lo], each [N][H+2][W+2][C]; the fp32 value of an
+ *   element is hi+lo (22 significant bits).  The 1-pixel halo already holds the
+ *   REFLECT padding of ops.py:12-15 (mirror without edge repeat), written by the
+ *   producer, so a 3x3 'valid' conv over the padded plane equals Conv2DReflect
+ *   (ops.py:17-19).  C must be a multiple of 8; H,W >= 2.
+ */
+#ifndef WCTB200_H
+#define WCTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define WCTB200_API __attribute__((visibility("default")))
+#else
+#define WCTB200_API
+#endif
+
+#define WCTB200_ABI_VERSION 1
+
+#define WCTB200_OK       0
+#define WCTB200_EINVAL  -1   /* bad argument / unsupported shape */
+#define WCTB200_ECUDA   -2   /* CUDA runtime / driver error (incl. no sm_100 device) */
+#define WCTB200_EWS     -3   /* workspace too small */
+#define WCTB200_EDEVICE -4   /* a kernel flagged an internal error (pipeline timeout) */
+
+/* conv / transform flags */
+#define WCTB200_RELU     1   /* ReLU epilogue                     (vgg_normalised.py:40, model.py:291) */
+#define WCTB200_CLIP01   2   /* clip to [0,1] (tail conv only)    (model.py:17,86) */
+
+WCTB200_API int         wctb200_abi_version(void);
+WCTB200_API const char* wctb200_last_error(void);
+/* Synchronises `stream` and returns WCTB200_EDEVICE if any kernel since the last
+ * call recorded an internal error (mbarrier timeout in the tcgen05 pipeline). */
+WCTB200_API int         wctb200_check_device(void* stream);
+
+/* ---- SPF16 activations ---------------------------------------------------- */
+WCTB200_API size_t wctb200_act_bytes(int N, int H, int W, int C);
+/* fp32 NHWC -> SPF16 (interior + reflect halo).  Test / interop helper. */
+WCTB200_API int wctb200_act_from_f32(const float* nhwc, int N, int H, int W, int C, void* act, void* stream);
+/* SPF16 -> fp32 NHWC (interior only). */
+WCTB200_API int wctb200_act_to_f32(const void* act, int N, int H, int W, int C, float* nhwc, void* stream);
+
+/* ---- image pre/post: WCT.preprocess / WCT.postprocess (wct.py:60-68) -------- */
+/* out[i] = img[i] / 255 */
+WCTB200_API int wctb200_image_u8_to_f32(const uint8_t* img, size_t count, float* out, void* stream);
+/* out[i] = (uint8) (clip(img[i],0,1) * 255)   -- truncation, like np.uint8 */
+WCTB200_API int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t* out, void* stream);
+
+/* ---- encoder / decoder layers ---------------------------------------------- */
+/* Weight preparation (one-time, device side):
+ * w_hwio fp32 [3][3][Cin][Cout] (Keras kernel layout, vgg_normalised.py:33 /
+ * model.py:291) -> split-fp16 GEMM operand [2 planes][Cout][9*Cin], k = tap*Cin + cin.
+ * `taps` is 9 (3x3) or 1 (a [Cin][Cout] matrix). */
+WCTB200_API size_t wctb200_conv_weight_bytes(int taps, int Cin, int Cout);
+WCTB200_API int wctb200_prep_conv_weights(const float* w_hwio, int taps, int Cin, int Cout, void* w_split, void* stream);
+
+/* Conv2DReflect 3x3 (+bias, optional ReLU) on tensor cores (tcgen05, split-fp16 x3):
+ * replaces `Lambda(pad_reflect) -> Conv2D(valid)` of vgg_normalised.py:28-40 and
+ * model.py:291.  Cin, Cout multiples of 64.  in/out: SPF16 [N,H,W,Cin] -> [N,H,W,Cout]. */
+WCTB200_API int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin,
+                    const void* w_split, const float* bias, int Cout, int flags,
+                    void* act_out, void* stream);
+/* Same contract on CUDA cores in plain fp32 (validation kernel, fp32 weights [3][3][Cin][Cout]). */
+WCTB200_API int wctb200_conv3x3_ref(const void* act_in, int N, int H, int W, int Cin,
+                        const float* w_hwio, const float* bias, int Cout, int flags,
+                        void* act_out, void* stream);
+/* Encoder head: the 1x1 'preprocess' conv (vgg_normalised.py:25-26) folded into
+ * conv1_1 3->64 + ReLU.  img fp32 NHWC [N,H,W,3] in [0,1]; w fp32 [27][64] (k = tap*3+cin),
+ * b fp32 [64]; out SPF16 [N,H,W,64]. */
+WCTB200_API int wctb200_conv_head(const float* img, int N, int H, int W, const float* w, const float* b,
+                      void* act_out, void* stream);
+/* Decoder tail: Conv2DReflect Cin->3, no activation (model.py:297-298), optional
+ * clip to [0,1] (model.py:86).  w fp32 [9*Cin][3], b fp32 [3]; out fp32 NHWC [N,H,W,3]. */
+WCTB200_API int wctb200_conv_tail(const void* act_in, int N, int H, int W, int Cin, const float* w, const float* b,
+                      int flags, float* img_out, void* stream);
+/* MaxPooling2D(2x2, stride 2, padding='same') (vgg_normalised.py:41-42): out [N,ceil(H/2),ceil(W/2),C]. */
+WCTB200_API int wctb200_maxpool2(const void* act_in, int N, int H, int W, int C, void* act_out, void* stream);
+/* UpSampling2D nearest x2 (model.py:293): out [N,2H,2W,C]. */
+WCTB200_API int wctb200_upsample2(const void* act_in, int N, int H, int W, int C, void* act_out, void* stream);
+
+/* ---- feature transforms ------------------------------------------------------ */
+/* Whiten-colour transform of one relu level for a batch: replaces wct_tf (ops.py:24-90,
+ * what the graph runs) and wct_np (ops.py:92-140, the named oracle) -- semantics flags:
+ *   eps_cov            added to the covariance diagonal           (wct_tf 1e-8 | wct_np 0)
+ *   eps_eig            added to the kept eigenvalues              (wct_tf 0    | wct_np 1e-5)
+ *   thresh             keep eigenvalues > thresh                  (1e-5, ops.py:68,112)
+ *   readd_content_mean blend with fc+mc (ops.py:83) or fc (ops.py:133)
+ * content SPF16 [Nc,Hc,Wc,C]; style SPF16 [Ns,Hs,Ws,C] with Ns == Nc (frame i uses
+ * style i) or Ns == 1 (shared).  out SPF16 [Nc,Hc,Wc,C].  k_out (device int32
+ * [2*(Nc+Ns)], may be NULL): k_c per content then k_s per style, then sweep counts.
+ * C in {64,128,256,512}.  ws: device scratch of wctb200_wct_workspace_bytes(). */
+WCTB200_API size_t wctb200_wct_workspace_bytes(int C, int Nc, int Ns);
+WCTB200_API int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc,
+                      const void* style, int Ns, int Hs, int Ws, int C,
+                      float alpha, float eps_cov, float eps_eig, float thresh, int readd_content_mean,
+                      void* out, int32_t* k_out, void* ws, size_t ws_bytes, void* stream);
+/* AdaIN (ops.py:282-294): biased per-channel moments of content and style,
+ * y = (x-mc)*rsqrt(vc+eps)*sqrt(vs)+ms, out = alpha*y + (1-alpha)*x. */
+WCTB200_API int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc,
+                        const void* style, int Ns, int Hs, int Ws, int C,
+                        float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Stand-alone pieces of the transform, exposed for parity tests and profiling:
+ * symmetric eigen-decomposition of `count` CxC fp32 matrices by one-sided Jacobi.
+ * a: [count][C][C] symmetric (overwritten: column i becomes sigma_i * u_i),
+ * sigma: [count][C] = |lambda_i|, sweeps: [count] (may be NULL). */
+WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream);
+
+/* Tuning hook, NOT part of the stable ABI: force the conv output-channel tile
+ * (64/128/256; 0 = built-in heuristic).  Used by bench/profiling scripts. */
+WCTB200_API int wctb200_debug_set_conv_bn(int bn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WCTB200_H */

@@ -1,0 +1,126 @@
+"""GPU parity of the whole hot path (WCT.predict, wct.py:70-106) against the CPU oracle.
+
+Two statements (DESIGN.md "Parity"):
+  * teacher-forced: every level of the engine's own run is re-computed by the fp64 oracle
+    FROM THE ENGINE'S INPUT TO THAT LEVEL; each level output must agree to <= 1e-3;
+  * free-running: the final image vs the oracle's own 5-level run, reported next to the
+    oracle's fp32-vs-fp64 distance (the chained levels amplify rounding noise ~1e3x with
+    random weights, so this bound is stated relative to that noise floor).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, ref_ops
+from wct_tf_b200.engine import Engine
+from wct_tf_b200.weights import make_synthetic_weights
+from wct_tf_b200.wct import WCT
+
+pytestmark = pytest.mark.gpu
+ALL = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return make_synthetic_weights(42)
+
+
+def _imgs(n, s, seed):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, (n, s, s, 3), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("sem,adain,targets,size", [
+    ("np", False, ALL, 128),
+    ("tf", False, ALL, 128),
+    ("tf", True, ALL, 96),
+    ("np", False, ["relu3_1", "relu1_1", "relu2_1"], 72),     # any order / subset (README.md:46)
+    ("tf", False, ["relu1_1"], 64),
+])
+def test_teacher_forced_levels(weights, sem, adain, targets, size):
+    eng = Engine(weights, targets, semantics=sem)
+    content = _imgs(1, size, 100)
+    style = _imgs(1, size + 16, 7)
+    cap = {}
+    out = eng.stylize(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), alpha=0.8, adain=adain,
+                      want_info=True, capture=cap)
+    eng.check_device()
+    sfe = nets.encode(nets.preprocess(style).astype(np.float64), weights, targets, np.float64)
+    worst = 0.0
+    for i, relu in enumerate(targets):
+        x = cap["level_input"][i].cpu().numpy().astype(np.float64)
+        if i == 0:
+            assert np.abs(x - content / 255.0).max() < 1e-7
+        else:
+            assert x.min() >= 0 and x.max() <= 1                     # model.py:86 clip between levels
+        cf = nets.encode(x, weights, [relu], np.float64)[relu]
+        got_cf = eng.act_to_f32(cap["content_feat"][i]).cpu().numpy()
+        e_enc = np.abs(got_cf - cf).max()
+        if adain:
+            f = ref_ops.adain(cf, sfe[relu], 0.8)
+        else:
+            fn = ref_ops.wct_tf if sem == "tf" else ref_ops.wct_np
+            f, info = fn(cf, sfe[relu], 0.8, return_info=True)
+            k = eng.last_info[i].cpu().numpy()
+            assert ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"]), "ill-posed vector"
+            assert (k[0], k[1]) == (info["k_c"], info["k_s"])
+        got_f = eng.act_to_f32(cap["transformed"][i]).cpu().numpy()
+        e_wct = np.abs(got_f - f).max()
+        y = nets.decode(np.asarray(f, dtype=np.float64), weights, relu, np.float64)
+        if i < len(targets) - 1:
+            y = np.clip(y, 0, 1)
+        e_out = np.abs(cap["level_output"][i].cpu().numpy() - y).max()
+        print("%s: encoder %.2e  transform %.2e  level output %.2e" % (relu, e_enc, e_wct, e_out))
+        worst = max(worst, e_enc, e_wct, e_out)
+    assert worst <= 1e-3
+    assert out.shape[0] == 1 and out.shape[3] == 3
+
+
+def test_free_running_five_levels_vs_oracle(weights):
+    size = 128
+    content, style = _imgs(1, size, 1000), _imgs(1, size, 7)
+    o64, info = nets.pipeline(content[0], style[0], weights, ALL, alpha=0.8, semantics="np", dtype=np.float64, return_info=True)
+    o32 = nets.pipeline(content[0], style[0], weights, ALL, alpha=0.8, semantics="np", dtype=np.float32)
+    for inf in info:
+        assert ref_ops.spectral_gap_ok(inf["wc"]) and ref_ops.spectral_gap_ok(inf["ws"])
+    eng = Engine(weights, ALL, semantics="np")
+    out = eng.stylize(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), alpha=0.8, want_info=True)
+    eng.check_device()
+    got = out.cpu().numpy()
+    noise = np.abs(o32 - o64).max()
+    err = np.abs(got - o64).max()
+    print("free-running 5-level: engine-vs-fp64 oracle %.3e ; oracle fp32-vs-fp64 %.3e" % (err, noise))
+    for lvl, inf in zip(eng.last_info, info):
+        k = lvl.cpu().numpy()
+        assert (k[0], k[1]) == (inf["k_c"], inf["k_s"])
+    assert err <= max(1e-3, 4 * noise)
+
+
+def test_batch_equals_single_frames_and_u8_postprocess(weights):
+    eng = Engine(weights, ALL, semantics="tf")
+    contents = _imgs(3, 64, 5)
+    styles = _imgs(3, 64, 9)
+    outs = eng.stylize(torch.from_numpy(contents).cuda(), torch.from_numpy(styles).cuda(), alpha=0.7).cpu().numpy()
+    for i in range(3):
+        o = eng.stylize(torch.from_numpy(contents[i:i + 1]).cuda(), torch.from_numpy(styles[i:i + 1]).cuda(), alpha=0.7)
+        assert np.abs(o.cpu().numpy()[0] - outs[i]).max() <= 2e-4   # same kernels; Jacobi sweep order may differ with batch
+    shared = eng.stylize(torch.from_numpy(contents).cuda(), torch.from_numpy(styles[:1]).cuda(), alpha=0.7).cpu().numpy()
+    assert np.abs(shared[0] - outs[0]).max() <= 2e-4
+    u8 = eng.to_u8(torch.from_numpy(outs).cuda()).cpu().numpy()
+    assert np.array_equal(u8, nets.postprocess(outs))                 # wct.py:66-68
+    eng.check_device()
+
+
+def test_wct_predict_surface(weights):
+    wct = WCT(checkpoints=None, relu_targets=["relu2_1", "relu1_1"], vgg_path=None, device="/gpu:0", weights=weights)
+    c, s = _imgs(1, 48, 1)[0], _imgs(1, 40, 2)[0]
+    out = wct.predict(c, s, alpha=0.6)
+    assert out.dtype == np.uint8 and out.shape == (48, 48, 3)
+    ref = nets.pipeline(c, s, weights, ["relu2_1", "relu1_1"], alpha=0.6, semantics="tf", dtype=np.float64)
+    diff = np.abs(out.astype(int) - nets.postprocess(ref[0]).astype(int))
+    assert diff.max() <= 1                                            # 1e-3 float error may flip a u8 LSB
+    with pytest.raises(NotImplementedError):
+        wct.predict(c, s, swap5=True)
+    out2 = wct.predict(c, s, alpha=0.6, adain=True)
+    ref2 = nets.pipeline(c, s, weights, ["relu2_1", "relu1_1"], alpha=0.6, adain=True, dtype=np.float64)
+    assert np.abs(out2.astype(int) - nets.postprocess(ref2[0]).astype(int)).max() <= 1

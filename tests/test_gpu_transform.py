@@ -1,0 +1,127 @@
+"""GPU parity: Jacobi eigensolver, WCT level (vs the reference's own wct_np golden
+vectors and vs the wct_tf restatement), AdaIN -- all through the C-ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops
+from wct_tf_b200 import _capi
+from tests import gpu_util as U
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "wct_np_*.npz")))
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512])
+def test_jacobi_eigh_matches_lapack(n):
+    rng = np.random.default_rng(n)
+    count = 3
+    mats = []
+    for i in range(count):
+        f = np.maximum(rng.standard_normal((3 * n, n)) @ (rng.standard_normal((n, n)) / np.sqrt(n)) + 0.3, 0)
+        if i == 1:
+            f[:, rng.choice(n, n // 8, replace=False)] = 0.0      # dead channels -> exact zero eigenvalues
+        f -= f.mean(0)
+        mats.append((f.T @ f / (f.shape[0] - 1)).astype(np.float32))
+    a = np.stack(mats)
+    d = U.dev(a)
+    sigma = torch.empty((count, n), dtype=torch.float32, device="cuda")
+    sweeps = torch.zeros(count, dtype=torch.int32, device="cuda")
+    _capi.check(U.lib().wctb200_jacobi_eigh(d.data_ptr(), n, count, sigma.data_ptr(), sweeps.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    g = d.cpu().numpy().astype(np.float64)       # [count][col][row]: column i = sigma_i u_i
+    sg = sigma.cpu().numpy().astype(np.float64)
+    print("sweeps", sweeps.cpu().numpy())
+    assert (sweeps.cpu().numpy() < 40).all(), "Jacobi did not converge"
+    for i in range(count):
+        w = np.linalg.eigvalsh(a[i].astype(np.float64))[::-1]
+        got = np.sort(sg[i])[::-1]
+        assert np.abs(got - np.abs(w)).max() <= 2e-5 * np.abs(w).max(), (i, np.abs(got - np.abs(w)).max())
+        # reconstruct A = sum_i u_i u_i^T sigma_i = G diag(1/sigma) G^T over the non-null columns
+        keep = sg[i] > 1e-6 * sg[i].max()
+        gi = g[i][keep]                       # rows = columns of G
+        rec = (gi.T / sg[i][keep]) @ gi
+        assert np.abs(rec - a[i]).max() <= 5e-5 * np.abs(a[i]).max()
+        u = gi / sg[i][keep][:, None]
+        assert np.abs(u @ u.T - np.eye(u.shape[0])).max() <= 5e-5
+
+
+def _run_wct(content, style, alpha, sem):
+    nc, hc, wc, c = content.shape
+    ns, hs, ws_, _ = style.shape
+    cin = U.act_from_numpy(content)
+    sin = U.act_from_numpy(style)
+    out = U.act_alloc(nc, hc, wc, c)
+    ws = torch.empty(U.lib().wctb200_wct_workspace_bytes(c, nc, ns), dtype=torch.uint8, device="cuda")
+    kbuf = torch.zeros(2 * (nc + ns), dtype=torch.int32, device="cuda")
+    p = dict(tf=(1e-8, 0.0, 1), np=(0.0, 1e-5, 0))[sem]
+    _capi.check(U.lib().wctb200_wct_level(cin.data_ptr(), nc, hc, wc, sin.data_ptr(), ns, hs, ws_, c, float(alpha),
+                                          p[0], p[1], 1e-5, p[2], out.data_ptr(), kbuf.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), U.stream()))
+    U.check_device()
+    got = U.act_to_numpy(out, nc, hc, wc, c)
+    padded = U.act_raw_padded(out, nc, hc, wc, c)
+    assert np.isfinite(padded).all()
+    assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
+    return got, kbuf.cpu().numpy()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[7:-4] for p in GOLDEN])
+def test_wct_level_vs_reference_wct_np_golden(path):
+    """north_star: stylised features within 1e-3 max-abs of the reference's wct_np."""
+    g = np.load(path)
+    got, k = _run_wct(g["content"], g["style"], float(g["alpha"]), "np")
+    assert k[0] == int(g["k_c"]) and k[1] == int(g["k_s"]), (k, int(g["k_c"]), int(g["k_s"]))
+    e32 = np.abs(got - g["out_ref_fp32"]).max()
+    e64 = np.abs(got - g["out_ref_fp64"]).max()
+    noise = np.abs(g["out_ref_fp32"] - g["out_ref_fp64"]).max()
+    print("max-abs vs reference wct_np fp32 %.2e, vs its fp64 run %.2e (reference fp32-vs-fp64 %.2e), sweeps %s"
+          % (e32, e64, noise, k[2:]))
+    assert e32 <= 1e-3 and e64 <= 1e-3
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.6])
+def test_wct_level_tf_semantics_batched_shared_style(alpha):
+    """wct_tf (ops.py:24-90): eps*I on the covariance, no eigenvalue eps, blend with fc+mc.
+    Batch of 3 content frames sharing one style == 3 independent calls of the oracle."""
+    g = np.load(GOLDEN[2])
+    rng = np.random.default_rng(0)
+    base = g["content"][0]
+    contents = np.stack([base, np.roll(base, 3, axis=0) * 0.9 + 0.05, base[::-1].copy()]).astype(np.float32)
+    style = g["style"]
+    got, k = _run_wct(contents, style, alpha, "tf")
+    for i in range(3):
+        ref, info = ref_ops.wct_tf(contents[i:i + 1].astype(np.float64), style.astype(np.float64), alpha, return_info=True)
+        assert ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"])
+        assert k[i] == info["k_c"] and k[3] == info["k_s"]
+        assert np.abs(got[i:i + 1] - ref).max() <= 1e-3, np.abs(got[i:i + 1] - ref).max()
+
+
+def test_wct_level_per_frame_styles():
+    g = np.load(GOLDEN[0])
+    c2 = np.concatenate([g["content"], g["content"][:, ::-1]]).astype(np.float32)
+    s2 = np.concatenate([g["style"], g["style"][:, :, ::-1] * 1.3]).astype(np.float32)
+    got, k = _run_wct(c2, s2, 0.8, "np")
+    for i in range(2):
+        ref = ref_ops.wct_np(c2[i:i + 1].astype(np.float64), s2[i:i + 1].astype(np.float64), 0.8)
+        assert np.abs(got[i:i + 1] - ref).max() <= 1e-3
+
+
+@pytest.mark.parametrize("c", [64, 512])
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_adain_level(c, alpha):
+    rng = np.random.default_rng(c)
+    content = np.maximum(rng.normal(0.5, 1, (2, 9, 11, c)), 0).astype(np.float32)
+    style = np.maximum(rng.normal(0.2, 2, (1, 7, 13, c)), 0).astype(np.float32)
+    cin, sin = U.act_from_numpy(content), U.act_from_numpy(style)
+    out = U.act_alloc(2, 9, 11, c)
+    ws = torch.empty(U.lib().wctb200_wct_workspace_bytes(c, 2, 1), dtype=torch.uint8, device="cuda")
+    _capi.check(U.lib().wctb200_adain_level(cin.data_ptr(), 2, 9, 11, sin.data_ptr(), 1, 7, 13, c, alpha, 1e-5,
+                                            out.data_ptr(), ws.data_ptr(), ws.numel(), U.stream()))
+    got = U.act_to_numpy(out, 2, 9, 11, c)
+    for i in range(2):
+        ref = ref_ops.adain(U.split_repr(content[i:i + 1]), U.split_repr(style), alpha)
+        assert np.abs(got[i:i + 1] - ref).max() <= 2e-5 * (1 + np.abs(ref).max())

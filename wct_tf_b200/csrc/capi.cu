@@ -1,0 +1,187 @@
+// extern "C" surface of libwctb200 (declared in include/wctb200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace wctb {
+
+static thread_local char t_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return WCTB200_ECUDA;
+}
+
+__device__ unsigned int g_device_error = 0;
+
+unsigned int* device_error_word() {
+    static unsigned int* ptr[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!ptr[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, g_device_error) == cudaSuccess) ptr[dev] = static_cast<unsigned int*>(p);
+    }
+    return ptr[dev];
+}
+
+// launchers (layers.cu / wct.cu)
+int launch_u8_to_f32(const uint8_t*, size_t, float*, cudaStream_t);
+int launch_f32_to_u8(const float*, size_t, uint8_t*, cudaStream_t);
+int launch_act_from_f32(const float*, ActGeom, __half*, cudaStream_t);
+int launch_act_to_f32(const __half*, ActGeom, float*, cudaStream_t);
+int launch_prep_weights(const float*, int, int, int, __half*, cudaStream_t);
+int launch_conv3x3_ref(const __half*, ActGeom, const float*, const float*, int, int, __half*, cudaStream_t);
+int launch_conv_head(const float*, int, int, int, const float*, const float*, __half*, cudaStream_t);
+int launch_conv_tail(const __half*, ActGeom, const float*, const float*, int, float*, cudaStream_t);
+int launch_maxpool2(const __half*, ActGeom, __half*, cudaStream_t);
+int launch_upsample2(const __half*, ActGeom, __half*, cudaStream_t);
+size_t wct_workspace_bytes(int, int, int);
+int launch_wct_level(const __half*, int, int, int, const __half*, int, int, int, int, float, float, float, float, int,
+                     __half*, int32_t*, void*, size_t, cudaStream_t);
+int launch_adain_level(const __half*, int, int, int, const __half*, int, int, int, int, float, float, __half*, void*,
+                       size_t, cudaStream_t);
+int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
+int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
+extern int g_conv_bn_override;
+
+static bool geom_ok(int N, int H, int W, int C) { return N >= 1 && H >= 2 && W >= 2 && C >= 8 && C % 8 == 0; }
+
+}  // namespace wctb
+
+using namespace wctb;
+
+#define ST(s) static_cast<cudaStream_t>(s)
+#define HP(p) static_cast<__half*>(p)
+#define HCP(p) static_cast<const __half*>(p)
+
+extern "C" {
+
+int wctb200_abi_version(void) { return WCTB200_ABI_VERSION; }
+const char* wctb200_last_error(void) { return t_err; }
+
+int wctb200_check_device(void* stream) {
+    WCTB_CUDA(cudaStreamSynchronize(ST(stream)));
+    unsigned int* w = device_error_word();
+    if (!w) {
+        set_error("device error word unavailable (no CUDA device?)");
+        return WCTB200_ECUDA;
+    }
+    unsigned int v = 0;
+    WCTB_CUDA(cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v != 0) {
+        unsigned int zero = 0;
+        cudaMemcpy(w, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+        set_error("device-side pipeline time-out, code 0x%x (0x1xx producer wait, 0x2xx MMA wait, 0x3xx epilogue wait)", v);
+        return WCTB200_EDEVICE;
+    }
+    return 0;
+}
+
+size_t wctb200_act_bytes(int N, int H, int W, int C) {
+    if (!geom_ok(N, H, W, C)) return 0;
+    ActGeom g(N, H, W, C);
+    return (size_t)g.plane * 2 * sizeof(__half);
+}
+
+int wctb200_act_from_f32(const float* nhwc, int N, int H, int W, int C, void* act, void* stream) {
+    WCTB_REQUIRE(geom_ok(N, H, W, C) && nhwc && act, "act_from_f32: bad arguments");
+    return launch_act_from_f32(nhwc, ActGeom(N, H, W, C), HP(act), ST(stream));
+}
+int wctb200_act_to_f32(const void* act, int N, int H, int W, int C, float* nhwc, void* stream) {
+    WCTB_REQUIRE(geom_ok(N, H, W, C) && nhwc && act, "act_to_f32: bad arguments");
+    return launch_act_to_f32(HCP(act), ActGeom(N, H, W, C), nhwc, ST(stream));
+}
+
+int wctb200_image_u8_to_f32(const uint8_t* img, size_t count, float* out, void* stream) {
+    WCTB_REQUIRE(img && out, "image_u8_to_f32: null pointer");
+    if (count == 0) return 0;
+    return launch_u8_to_f32(img, count, out, ST(stream));
+}
+int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t* out, void* stream) {
+    WCTB_REQUIRE(img && out, "image_f32_to_u8: null pointer");
+    if (count == 0) return 0;
+    return launch_f32_to_u8(img, count, out, ST(stream));
+}
+
+size_t wctb200_conv_weight_bytes(int taps, int Cin, int Cout) {
+    if (taps < 1 || Cin < 1 || Cout < 1) return 0;
+    return (size_t)2 * taps * Cin * Cout * sizeof(__half);
+}
+int wctb200_prep_conv_weights(const float* w_hwio, int taps, int Cin, int Cout, void* w_split, void* stream) {
+    WCTB_REQUIRE(w_hwio && w_split && (taps == 9 || taps == 1) && Cin >= 1 && Cout >= 1, "prep_conv_weights: bad arguments");
+    return launch_prep_weights(w_hwio, taps, Cin, Cout, HP(w_split), ST(stream));
+}
+
+int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin, const void* w_split, const float* bias, int Cout,
+                    int flags, void* act_out, void* stream) {
+    WCTB_REQUIRE(act_in && w_split && act_out, "conv3x3: null pointer");
+    return launch_conv3x3_tc(HCP(act_in), N, H, W, Cin, HCP(w_split), 9, 1, bias, Cout, flags, HP(act_out), ST(stream));
+}
+int wctb200_conv3x3_ref(const void* act_in, int N, int H, int W, int Cin, const float* w_hwio, const float* bias, int Cout,
+                        int flags, void* act_out, void* stream) {
+    WCTB_REQUIRE(act_in && w_hwio && act_out && geom_ok(N, H, W, Cin) && Cout >= 1, "conv3x3_ref: bad arguments");
+    return launch_conv3x3_ref(HCP(act_in), ActGeom(N, H, W, Cin), w_hwio, bias, Cout, flags, HP(act_out), ST(stream));
+}
+int wctb200_conv_head(const float* img, int N, int H, int W, const float* w, const float* b, void* act_out, void* stream) {
+    WCTB_REQUIRE(img && w && b && act_out && N >= 1 && H >= 2 && W >= 2, "conv_head: bad arguments");
+    return launch_conv_head(img, N, H, W, w, b, HP(act_out), ST(stream));
+}
+int wctb200_conv_tail(const void* act_in, int N, int H, int W, int Cin, const float* w, const float* b, int flags,
+                      float* img_out, void* stream) {
+    WCTB_REQUIRE(act_in && w && b && img_out && geom_ok(N, H, W, Cin) && Cin <= 1024, "conv_tail: bad arguments");
+    return launch_conv_tail(HCP(act_in), ActGeom(N, H, W, Cin), w, b, flags, img_out, ST(stream));
+}
+int wctb200_maxpool2(const void* act_in, int N, int H, int W, int C, void* act_out, void* stream) {
+    WCTB_REQUIRE(act_in && act_out && geom_ok(N, H, W, C) && (H + 1) / 2 >= 2 && (W + 1) / 2 >= 2, "maxpool2: bad arguments (output must be >= 2x2)");
+    return launch_maxpool2(HCP(act_in), ActGeom(N, H, W, C), HP(act_out), ST(stream));
+}
+int wctb200_upsample2(const void* act_in, int N, int H, int W, int C, void* act_out, void* stream) {
+    WCTB_REQUIRE(act_in && act_out && geom_ok(N, H, W, C), "upsample2: bad arguments");
+    return launch_upsample2(HCP(act_in), ActGeom(N, H, W, C), HP(act_out), ST(stream));
+}
+
+size_t wctb200_wct_workspace_bytes(int C, int Nc, int Ns) {
+    if (C < 8 || Nc < 1 || Ns < 1) return 0;
+    return wct_workspace_bytes(C, Nc, Ns);
+}
+int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc, const void* style, int Ns, int Hs, int Ws, int C,
+                      float alpha, float eps_cov, float eps_eig, float thresh, int readd_content_mean, void* out,
+                      int32_t* k_out, void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(content && style && out && ws, "wct_level: null pointer");
+    return launch_wct_level(HCP(content), Nc, Hc, Wc, HCP(style), Ns, Hs, Ws, C, alpha, eps_cov, eps_eig, thresh,
+                            readd_content_mean, HP(out), k_out, ws, ws_bytes, ST(stream));
+}
+int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc, const void* style, int Ns, int Hs, int Ws, int C,
+                        float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(content && style && out && ws, "adain_level: null pointer");
+    return launch_adain_level(HCP(content), Nc, Hc, Wc, HCP(style), Ns, Hs, Ws, C, alpha, eps, HP(out), ws, ws_bytes,
+                              ST(stream));
+}
+
+int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream) {
+    WCTB_REQUIRE(a && sigma && count >= 1, "jacobi_eigh: bad arguments");
+    // convergence scratch: 16 floats per matrix
+    float* conv = nullptr;
+    WCTB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&conv), (size_t)count * 16 * sizeof(float), ST(stream)));
+    int rc = launch_jacobi(a, C, count, conv, sweeps, ST(stream));
+    if (!rc) rc = launch_eig_post(a, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
+    cudaFreeAsync(conv, ST(stream));
+    return rc;
+}
+
+// tuning hook (not part of the stable ABI): force the conv N tile (0 = heuristic)
+int wctb200_debug_set_conv_bn(int bn) {
+    g_conv_bn_override = bn;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+// Shared device/host helpers for libwctb200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/wctb200.h"
+
+namespace wctb {
+
+// ---------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+// device error word (set by kernels on pipeline time-outs)
+unsigned int* device_error_word();
+
+#define WCTB_CUDA(call)                                        \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return ::wctb::cuda_fail(_e, #call); \
+    } while (0)
+
+#define WCTB_CHECK_LAUNCH(name)                                \
+    do {                                                       \
+        cudaError_t _e = cudaGetLastError();                   \
+        if (_e != cudaSuccess) return ::wctb::cuda_fail(_e, name); \
+    } while (0)
+
+#define WCTB_REQUIRE(cond, ...)                                \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            ::wctb::set_error(__VA_ARGS__);                    \
+            return WCTB200_EINVAL;                             \
+        }                                                      \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// SPF16 geometry
+// ---------------------------------------------------------------------------
+struct ActGeom {
+    int N, H, W, C;
+    int Hp, Wp;          // H+2, W+2
+    long long P;         // N*Hp*Wp padded positions
+    long long plane;     // P*C elements per plane
+    __host__ __device__ ActGeom() {}
+    __host__ __device__ ActGeom(int n, int h, int w, int c)
+        : N(n), H(h), W(w), C(c), Hp(h + 2), Wp(w + 2) {
+        P = (long long)N * Hp * Wp;
+        plane = P * C;
+    }
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// split-pair fp16
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);   // keep hi finite
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ float merge_f32(__half hi, __half lo) { return __half2float(hi) + __half2float(lo); }
+
+// 8 channels = one 16-byte vector per plane
+struct alignas(16) Half8 { __half2 v[4]; };
+
+__device__ __forceinline__ void split8(const float* x, Half8& hi, Half8& lo) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __half h0, l0, h1, l1;
+        split_f32(x[2 * i], h0, l0);
+        split_f32(x[2 * i + 1], h1, l1);
+        hi.v[i] = __halves2half2(h0, h1);
+        lo.v[i] = __halves2half2(l0, l1);
+    }
+}
+__device__ __forceinline__ void merge8(const Half8& hi, const Half8& lo, float* x) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 a = __half22float2(hi.v[i]);
+        float2 b = __half22float2(lo.v[i]);
+        x[2 * i] = a.x + b.x;
+        x[2 * i + 1] = a.y + b.y;
+    }
+}
+
+// Destinations of interior pixel (y,x) in the reflect-padded plane (ops.py:12-15):
+// the pixel itself at (y+1,x+1) plus the halo cells that mirror it.
+// rows[] / cols[] receive padded coordinates; returns counts.
+__device__ __forceinline__ int halo_rows(int y, int H, int* rows) {
+    int n = 0;
+    rows[n++] = y + 1;
+    if (y == 1) rows[n++] = 0;
+    if (y == H - 2) rows[n++] = H + 1;
+    return n;
+}
+
+// store one 8-channel group (hi+lo) of pixel (n,y,x) to every padded cell that holds it
+__device__ __forceinline__ void store8_with_halo(__half* __restrict__ act, const ActGeom& g, int n, int y, int x,
+                                                 int c0, const Half8& hi, const Half8& lo) {
+    int rows[3], cols[3];
+    int nr = halo_rows(y, g.H, rows);
+    int nc = halo_rows(x, g.W, cols);
+    for (int a = 0; a < nr; ++a)
+        for (int b = 0; b < nc; ++b) {
+            long long pos = ((long long)n * g.Hp + rows[a]) * g.Wp + cols[b];
+            long long off = pos * g.C + c0;
+            *reinterpret_cast<Half8*>(act + off) = hi;
+            *reinterpret_cast<Half8*>(act + g.plane + off) = lo;
+        }
+}
+
+__device__ __forceinline__ void load8(const __half* __restrict__ act, const ActGeom& g, long long pos, int c0,
+                                      float* x) {
+    long long off = pos * g.C + c0;
+    Half8 hi = *reinterpret_cast<const Half8*>(act + off);
+    Half8 lo = *reinterpret_cast<const Half8*>(act + g.plane + off);
+    merge8(hi, lo, x);
+}
+
+// ---------------------------------------------------------------------------
+// PTX wrappers: mbarrier / TMA / tcgen05 (sm_100a)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must not hang the GPU.  After ~2 s the CTA-wide abort
+// flag is raised (all later waits fall through) and the global error word is set.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag,
+                                          unsigned int* err_word, unsigned int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned int it = 1;; ++it) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((it & 63u) == 0u) {
+            if (*abort_flag) return;
+            if (*reinterpret_cast<volatile unsigned int*>(err_word)) { *abort_flag = 1; return; }
+            if (globaltimer_ns() - t0 > 2000000000ull) break;
+        }
+    }
+    *abort_flag = 1;
+    atomicExch(err_word, code);
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread retire
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (tile rows are 128 bytes =
+// 64 fp16 of K; 8-row groups 1024 B apart).  Bit layout: cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address  [0,14)
+    d |= (uint64_t)1 << 16;                       // LBO (unused for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;             // SBO = 1024 B   [32,46)
+    d |= (uint64_t)1 << 46;                       // descriptor version = 1 (sm_100)
+    d |= (uint64_t)2 << 61;                       // layout type = SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, K-major A and B, M x N tile.
+// Bit layout: cute::UMMA::InstrDescriptor.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4)                      // c_format = F32
+           | (0u << 7) | (0u << 10)       // a_format = b_format = F16
+           | (0u << 15) | (0u << 16)      // a_major = b_major = K
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------
+// kernel launchers implemented in the .cu files (host API used by capi.cu)
+// ---------------------------------------------------------------------------
+int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __half* w_split, int taps, int nsets,
+                      const float* bias, int Cout, int flags, __half* out, cudaStream_t st);
+
+}  // namespace wctb

@@ -1,0 +1,342 @@
+// Memory-bound layers of the encoder/decoder and the SPF16 conversion helpers.
+// All kernels are HBM-bound streaming kernels: 16-byte vector loads/stores, one
+// 8-channel group per thread, grid sized from the element count.
+#include "common.cuh"
+
+namespace wctb {
+
+// ---------------------------------------------------------------------------
+// image pre/post   (wct.py:60-68)
+// ---------------------------------------------------------------------------
+__global__ void k_u8_to_f32(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (float)in[i] / 255.f;   // image / 255.  (wct.py:64)
+}
+__global__ void k_f32_to_u8(const float* __restrict__ in, size_t n, uint8_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        float v = fminf(fmaxf(in[i], 0.f), 1.f) * 255.f;        // np.clip(x,0,1)*255 (wct.py:68)
+        out[i] = (uint8_t)v;                                     // np.uint8 truncates
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 NHWC <-> SPF16
+// ---------------------------------------------------------------------------
+__global__ void k_act_from_f32(const float* __restrict__ in, ActGeom g, __half* __restrict__ act) {
+    const int cg = g.C / 8;
+    const long long total = (long long)g.N * g.H * g.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        long long pix = i / cg;
+        const int x = (int)(pix % g.W); pix /= g.W;
+        const int y = (int)(pix % g.H);
+        const int n = (int)(pix / g.H);
+        const float* src = in + (((long long)n * g.H + y) * g.W + x) * g.C + c0;
+        float v[8];
+        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(src);
+        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(src + 4);
+        Half8 hi, lo;
+        split8(v, hi, lo);
+        store8_with_halo(act, g, n, y, x, c0, hi, lo);
+    }
+}
+__global__ void k_act_to_f32(const __half* __restrict__ act, ActGeom g, float* __restrict__ out) {
+    const int cg = g.C / 8;
+    const long long total = (long long)g.N * g.H * g.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        long long pix = i / cg;
+        const int x = (int)(pix % g.W); pix /= g.W;
+        const int y = (int)(pix % g.H);
+        const int n = (int)(pix / g.H);
+        const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
+        float v[8];
+        load8(act, g, pos, c0, v);
+        float* dst = out + (((long long)n * g.H + y) * g.W + x) * g.C + c0;
+        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<float4*>(v);
+        *reinterpret_cast<float4*>(dst + 4) = *reinterpret_cast<float4*>(v + 4);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// weights: fp32 [taps][Cin][Cout] -> split fp16 [2][Cout][taps*Cin]
+// ---------------------------------------------------------------------------
+__global__ void k_prep_weights(const float* __restrict__ w, int taps, int Cin, int Cout, __half* __restrict__ ws) {
+    const long long K = (long long)taps * Cin;
+    const long long total = K * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i / K);
+        const long long k = i - (long long)co * K;      // k = tap*Cin + cin
+        const float v = w[k * Cout + co];
+        __half hi, lo;
+        split_f32(v, hi, lo);
+        ws[i] = hi;
+        ws[total + i] = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// validation conv: plain fp32 FFMA, one thread per (pixel, cout)
+// ---------------------------------------------------------------------------
+__global__ void k_conv3x3_ref(const __half* __restrict__ in, ActGeom gi, const float* __restrict__ w,
+                              const float* __restrict__ bias, int Cout, int flags, __half* __restrict__ out) {
+    const ActGeom go(gi.N, gi.H, gi.W, Cout);
+    const long long total = (long long)gi.N * gi.H * gi.W * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        long long pix = i / Cout;
+        const int x = (int)(pix % gi.W); pix /= gi.W;
+        const int y = (int)(pix % gi.H);
+        const int n = (int)(pix / gi.H);
+        float acc = bias ? bias[co] : 0.f;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const long long pos = ((long long)n * gi.Hp + y + ky) * gi.Wp + x + kx;
+                const __half* ph = in + pos * gi.C;
+                const __half* pl = ph + gi.plane;
+                const float* wp = w + (long long)(ky * 3 + kx) * gi.C * Cout + co;
+                for (int ci = 0; ci < gi.C; ++ci) acc = fmaf(merge_f32(ph[ci], pl[ci]), wp[(long long)ci * Cout], acc);
+            }
+        if (flags & WCTB200_RELU) acc = fmaxf(acc, 0.f);
+        __half hi, lo;
+        split_f32(acc, hi, lo);
+        int rows[3], cols[3];
+        const int nr = halo_rows(y, go.H, rows), nc = halo_rows(x, go.W, cols);
+        for (int a = 0; a < nr; ++a)
+            for (int b = 0; b < nc; ++b) {
+                const long long off = (((long long)n * go.Hp + rows[a]) * go.Wp + cols[b]) * Cout + co;
+                out[off] = hi;
+                out[go.plane + off] = lo;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// encoder head: (1x1 preprocess conv folded into) conv1_1 3->64 + ReLU
+//   vgg_normalised.py:25-40.  One thread = one pixel x 8 output channels.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void __launch_bounds__(256)
+k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
+            const float* __restrict__ b, __half* __restrict__ out) {
+    __shared__ float sw[27 * 64];
+    __shared__ float sb[64];
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const ActGeom go(N, H, W, 64);
+    const long long total = (long long)N * H * W * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i & 7) * 8;
+        long long pix = i >> 3;
+        const int x = (int)(pix % W); pix /= W;
+        const int y = (int)(pix % H);
+        const int n = (int)(pix / H);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = reflect_idx(y + ky - 1, H);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = reflect_idx(x + kx - 1, W);
+                const float* px = img + (((long long)n * H + yy) * W + xx) * 3;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = __ldg(px + ci);
+                    const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * 64 + c0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        Half8 hi, lo;
+        split8(acc, hi, lo);
+        store8_with_halo(out, go, n, y, x, c0, hi, lo);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// decoder tail: Conv2DReflect Cin->3, no activation (model.py:297-298) [+ clip, model.py:86]
+//   8 lanes cooperate on one pixel (each owns Cin/8 channels... in 8-wide groups), shuffle-reduce.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_conv_tail(const __half* __restrict__ in, ActGeom gi, const float* __restrict__ w, const float* __restrict__ b,
+            int flags, float* __restrict__ img) {
+    extern __shared__ float swt[];   // [9*Cin][3]
+    const int K = 9 * gi.C;
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) swt[i] = w[i];
+    __syncthreads();
+    const int cgs = gi.C / 8;                      // 8-channel groups per pixel
+    const long long npix = (long long)gi.N * gi.H * gi.W;
+    const int sub = threadIdx.x & 7;               // 8 lanes per pixel, 4 pixels per warp
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop bound (the shuffles below need the whole warp)
+    for (long long wbase = (((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane) >> 3; wbase < npix;
+         wbase += ((long long)gridDim.x * blockDim.x) >> 3) {
+        const long long pix = wbase + (lane >> 3);
+        const bool ok = pix < npix;
+        long long t = ok ? pix : 0;
+        const int x = (int)(t % gi.W); t /= gi.W;
+        const int y = (int)(t % gi.H);
+        const int n = (int)(t / gi.H);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (ok) {
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    const long long pos = ((long long)n * gi.Hp + y + ky) * gi.Wp + x + kx;
+                    for (int cgi = sub; cgi < cgs; cgi += 8) {
+                        float v[8];
+                        load8(in, gi, pos, cgi * 8, v);
+                        const float* wr = swt + ((ky * 3 + kx) * gi.C + cgi * 8) * 3;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            a0 = fmaf(v[j], wr[j * 3 + 0], a0);
+                            a1 = fmaf(v[j], wr[j * 3 + 1], a1);
+                            a2 = fmaf(v[j], wr[j * 3 + 2], a2);
+                        }
+                    }
+                }
+        }
+#pragma unroll
+        for (int o = 4; o >= 1; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (ok && sub == 0) {
+            a0 += b[0]; a1 += b[1]; a2 += b[2];
+            if (flags & WCTB200_CLIP01) {
+                a0 = fminf(fmaxf(a0, 0.f), 1.f);
+                a1 = fminf(fmaxf(a1, 0.f), 1.f);
+                a2 = fminf(fmaxf(a2, 0.f), 1.f);
+            }
+            float* d = img + pix * 3;
+            d[0] = a0; d[1] = a1; d[2] = a2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// MaxPooling2D 2x2/2 'same' (vgg_normalised.py:41-42) and UpSampling2D x2 (model.py:293)
+// ---------------------------------------------------------------------------
+__global__ void k_maxpool2(const __half* __restrict__ in, ActGeom gi, __half* __restrict__ out) {
+    const ActGeom go(gi.N, (gi.H + 1) / 2, (gi.W + 1) / 2, gi.C);
+    const int cg = gi.C / 8;
+    const long long total = (long long)go.N * go.H * go.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        long long pix = i / cg;
+        const int x = (int)(pix % go.W); pix /= go.W;
+        const int y = (int)(pix % go.H);
+        const int n = (int)(pix / go.H);
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -3.0e38f;
+        for (int dy = 0; dy < 2; ++dy) {
+            const int yy = 2 * y + dy;
+            if (yy >= gi.H) continue;               // 'same': window clipped at the bottom/right edge
+            for (int dx = 0; dx < 2; ++dx) {
+                const int xx = 2 * x + dx;
+                if (xx >= gi.W) continue;
+                float v[8];
+                load8(in, gi, ((long long)n * gi.Hp + yy + 1) * gi.Wp + xx + 1, c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+            }
+        }
+        Half8 hi, lo;
+        split8(m, hi, lo);
+        store8_with_halo(out, go, n, y, x, c0, hi, lo);
+    }
+}
+
+__global__ void k_upsample2(const __half* __restrict__ in, ActGeom gi, __half* __restrict__ out) {
+    const ActGeom go(gi.N, gi.H * 2, gi.W * 2, gi.C);
+    const int cg = gi.C / 8;
+    const long long total = (long long)go.N * go.H * go.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        long long pix = i / cg;
+        const int x = (int)(pix % go.W); pix /= go.W;
+        const int y = (int)(pix % go.H);
+        const int n = (int)(pix / go.H);
+        const long long off = (((long long)n * gi.Hp + (y >> 1) + 1) * gi.Wp + (x >> 1) + 1) * gi.C + c0;
+        const Half8 hi = *reinterpret_cast<const Half8*>(in + off);
+        const Half8 lo = *reinterpret_cast<const Half8*>(in + gi.plane + off);
+        store8_with_halo(out, go, n, y, x, c0, hi, lo);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static inline int grid_for(long long total, int block) {
+    long long b = (total + block - 1) / block;
+    const long long cap = 148ll * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int launch_u8_to_f32(const uint8_t* in, size_t n, float* out, cudaStream_t st) {
+    k_u8_to_f32<<<grid_for((long long)n, 256), 256, 0, st>>>(in, n, out);
+    WCTB_CHECK_LAUNCH("k_u8_to_f32");
+    return 0;
+}
+int launch_f32_to_u8(const float* in, size_t n, uint8_t* out, cudaStream_t st) {
+    k_f32_to_u8<<<grid_for((long long)n, 256), 256, 0, st>>>(in, n, out);
+    WCTB_CHECK_LAUNCH("k_f32_to_u8");
+    return 0;
+}
+int launch_act_from_f32(const float* in, ActGeom g, __half* act, cudaStream_t st) {
+    k_act_from_f32<<<grid_for((long long)g.N * g.H * g.W * (g.C / 8), 256), 256, 0, st>>>(in, g, act);
+    WCTB_CHECK_LAUNCH("k_act_from_f32");
+    return 0;
+}
+int launch_act_to_f32(const __half* act, ActGeom g, float* out, cudaStream_t st) {
+    k_act_to_f32<<<grid_for((long long)g.N * g.H * g.W * (g.C / 8), 256), 256, 0, st>>>(act, g, out);
+    WCTB_CHECK_LAUNCH("k_act_to_f32");
+    return 0;
+}
+int launch_prep_weights(const float* w, int taps, int Cin, int Cout, __half* ws, cudaStream_t st) {
+    k_prep_weights<<<grid_for((long long)taps * Cin * Cout, 256), 256, 0, st>>>(w, taps, Cin, Cout, ws);
+    WCTB_CHECK_LAUNCH("k_prep_weights");
+    return 0;
+}
+int launch_conv3x3_ref(const __half* in, ActGeom gi, const float* w, const float* bias, int Cout, int flags,
+                       __half* out, cudaStream_t st) {
+    k_conv3x3_ref<<<grid_for((long long)gi.N * gi.H * gi.W * Cout, 256), 256, 0, st>>>(in, gi, w, bias, Cout, flags, out);
+    WCTB_CHECK_LAUNCH("k_conv3x3_ref");
+    return 0;
+}
+int launch_conv_head(const float* img, int N, int H, int W, const float* w, const float* b, __half* out, cudaStream_t st) {
+    k_conv_head<<<grid_for((long long)N * H * W * 8, 256), 256, 0, st>>>(img, N, H, W, w, b, out);
+    WCTB_CHECK_LAUNCH("k_conv_head");
+    return 0;
+}
+int launch_conv_tail(const __half* in, ActGeom gi, const float* w, const float* b, int flags, float* img, cudaStream_t st) {
+    const size_t smem = (size_t)9 * gi.C * 3 * sizeof(float);
+    k_conv_tail<<<grid_for((long long)gi.N * gi.H * gi.W * 8, 256), 256, smem, st>>>(in, gi, w, b, flags, img);
+    WCTB_CHECK_LAUNCH("k_conv_tail");
+    return 0;
+}
+int launch_maxpool2(const __half* in, ActGeom gi, __half* out, cudaStream_t st) {
+    const long long total = (long long)gi.N * ((gi.H + 1) / 2) * ((gi.W + 1) / 2) * (gi.C / 8);
+    k_maxpool2<<<grid_for(total, 256), 256, 0, st>>>(in, gi, out);
+    WCTB_CHECK_LAUNCH("k_maxpool2");
+    return 0;
+}
+int launch_upsample2(const __half* in, ActGeom gi, __half* out, cudaStream_t st) {
+    const long long total = (long long)gi.N * gi.H * 2 * gi.W * 2 * (gi.C / 8);
+    k_upsample2<<<grid_for(total, 256), 256, 0, st>>>(in, gi, out);
+    WCTB_CHECK_LAUNCH("k_upsample2");
+    return 0;
+}
+
+}  // namespace wctb

@@ -1,0 +1,698 @@
+// Whiten-colour transform (ops.py:24-140) and AdaIN (ops.py:282-294) for one relu level,
+// batched over frames.
+//
+// Stage A  channel sums / covariance        HBM-bound streaming kernels (fp32 FFMA, fp64 combine)
+// Stage B  C x C symmetric eigendecomposition: one-sided (Hestenes) Jacobi, one pair per warp,
+//          columns staged in shared memory, a thread-block CLUSTER of C/64 CTAs per matrix
+// Stage C  W_c = E_c D_c^-1/2 E_c^T, C_s = E_s D_s^1/2 E_s^T, T = C_s W_c, M = aT + (1-a)I, bias
+// Stage D  out = M x + bias : the 1-tap mode of the tcgen05 conv kernel (conv_tc.cu) with a
+//          per-frame weight set, so the apply GEMM runs on the tensor cores.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace wctb {
+
+// ---------------------------------------------------------------------------
+// Stage A.1: per-channel sums (and sums of squares) over the interior pixels
+//   grid (chunks, problems); 256 threads; thread = (row lane, 8-channel group)
+// ---------------------------------------------------------------------------
+template <bool SQ>
+__global__ void __launch_bounds__(256)
+k_chan_sums(const __half* __restrict__ act, ActGeom g, int chunk_pix, double* __restrict__ sum, double* __restrict__ sumsq) {
+    __shared__ float red[256 * 8];
+    __shared__ float red2[SQ ? 256 * 8 : 8];
+    const int cgs = g.C / 8;
+    const int rows = 256 / cgs;                 // pixel rows handled per iteration (C <= 2048)
+    const int grp = threadIdx.x % cgs;
+    const int rl = threadIdx.x / cgs;
+    const int n = blockIdx.y;
+    const long long HW = (long long)g.H * g.W;
+    const long long q0 = (long long)blockIdx.x * chunk_pix;
+    const long long q1 = min(q0 + chunk_pix, HW);
+    float s[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; s2[j] = 0.f; }
+    if (rl < rows) {
+        for (long long q = q0 + rl; q < q1; q += rows) {
+            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+            float v[8];
+            load8(act, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, grp * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += v[j];
+                if (SQ) s2[j] = fmaf(v[j], v[j], s2[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x * 8 + j] = s[j];
+        if (SQ) red2[threadIdx.x * 8 + j] = s2[j];
+    }
+    __syncthreads();
+    // thread t < C reduces channel t over the row lanes
+    for (int c = threadIdx.x; c < g.C; c += 256) {
+        const int gq = c / 8, j = c % 8;
+        float a = 0.f, a2 = 0.f;
+        for (int r = 0; r < rows; ++r) {
+            a += red[(r * cgs + gq) * 8 + j];
+            if (SQ) a2 += red2[(r * cgs + gq) * 8 + j];
+        }
+        atomicAdd(&sum[(long long)n * g.C + c], (double)a);
+        if (SQ) atomicAdd(&sumsq[(long long)n * g.C + c], (double)a2);
+    }
+}
+
+__global__ void k_mean_finalize(const double* __restrict__ sum, const double* __restrict__ sumsq, long long HW, int total,
+                                float* __restrict__ mean, float* __restrict__ var) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double m = sum[i] / (double)HW;
+    mean[i] = (float)m;
+    if (var) var[i] = (float)fmax(sumsq[i] / (double)HW - m * m, 0.0);   // biased variance (tf.nn.moments)
+}
+
+// ---------------------------------------------------------------------------
+// Stage A.2: covariance partial sums  cov[i][j] += sum_p (x_pi - m_i)(x_pj - m_j)
+//   grid (upper-tri 64x64 block pairs, pixel chunks, problems); 256 threads, 4x4 per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cov_partial(const __half* __restrict__ act, ActGeom g, const float* __restrict__ mean, int chunk_pix,
+              double* __restrict__ cov) {
+    __shared__ __align__(16) float Xi[32][64];
+    __shared__ __align__(16) float Xj[32][64];
+    const int nb = g.C / 64;
+    // decode upper-triangular pair index
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+    const int bj = bi + rem;
+    const bool diag = (bi == bj);
+    const int n = blockIdx.z;
+    const long long HW = (long long)g.H * g.W;
+    const long long q0 = (long long)blockIdx.y * chunk_pix;
+    const long long q1 = min(q0 + chunk_pix, HW);
+    const float* mn = mean + (long long)n * g.C;
+
+    const int lp = threadIdx.x >> 3;           // pixel within the 32-pixel step
+    const int lg = threadIdx.x & 7;            // 8-channel group within the 64-channel block
+    float mi[8], mj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mi[j] = mn[bi * 64 + lg * 8 + j];
+        mj[j] = mn[bj * 64 + lg * 8 + j];
+    }
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    for (long long qs = q0; qs < q1; qs += 32) {
+        const long long q = qs + lp;
+        float vi[8], vj[8];
+        if (q < q1) {
+            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+            const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
+            load8(act, g, pos, bi * 64 + lg * 8, vi);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vi[j] -= mi[j];
+            if (!diag) {
+                load8(act, g, pos, bj * 64 + lg * 8, vj);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) vj[j] -= mj[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { vi[j] = 0.f; vj[j] = 0.f; }
+        }
+        __syncthreads();   // previous step's reads done
+        *reinterpret_cast<float4*>(&Xi[lp][lg * 8]) = *reinterpret_cast<float4*>(vi);
+        *reinterpret_cast<float4*>(&Xi[lp][lg * 8 + 4]) = *reinterpret_cast<float4*>(vi + 4);
+        if (!diag) {
+            *reinterpret_cast<float4*>(&Xj[lp][lg * 8]) = *reinterpret_cast<float4*>(vj);
+            *reinterpret_cast<float4*>(&Xj[lp][lg * 8 + 4]) = *reinterpret_cast<float4*>(vj + 4);
+        }
+        __syncthreads();
+        const float (*XB)[64] = diag ? Xi : Xj;
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&Xi[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&XB[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+    }
+    double* cv = cov + (long long)n * g.C * g.C;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            atomicAdd(&cv[(long long)(bi * 64 + ty * 4 + r) * g.C + bj * 64 + tx * 4 + c], (double)acc[r][c]);
+}
+
+// cov64 (upper blocks) -> full symmetric fp32 matrix, /(HW-1), + eps_cov*I   (ops.py:45,50,108,121)
+__global__ void k_cov_finalize(const double* __restrict__ cov, int C, long long HW, float eps_cov, int count,
+                               float* __restrict__ G) {
+    const long long total = (long long)count * C * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % C);
+        const int i = (int)((t / C) % C);
+        const long long n = t / ((long long)C * C);
+        const double* cv = cov + n * C * C;
+        const double v = (i / 64 <= j / 64) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
+        float r = (float)(v / (double)(HW - 1));
+        if (i == j) r += eps_cov;
+        G[t] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stage B: one-sided Jacobi.  Matrix n x n (n = 64*P), columns contiguous
+//   (symmetric input, so row-major == column-major).  A cluster of P CTAs owns one
+//   matrix; the 2P column blocks (32 columns each) are paired by a round-robin
+//   tournament; a CTA stages its two blocks in shared memory, orthogonalises
+//   all 32x32 cross pairs (one pair per warp, 32 warps), writes them back, and
+//   the cluster barriers.  On convergence column i = sigma_i * u_i.
+// ---------------------------------------------------------------------------
+template <int NN>
+struct JacobiCfg {
+    static constexpr int P = NN / 64;
+    static constexpr int VEC = NN >= 128 ? 4 : 2;        // floats per lane per load
+    static constexpr int NV = NN / (32 * VEC);           // vector loads per lane per column
+    static constexpr int SMEM_BYTES = 64 * NN * 4 + 64;
+};
+
+template <int NN>
+__device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __restrict__ cy, int lane, float tol) {
+    using Cfg = JacobiCfg<NN>;
+    float x[Cfg::NV * Cfg::VEC], y[Cfg::NV * Cfg::VEC];
+#pragma unroll
+    for (int v = 0; v < Cfg::NV; ++v) {
+        const int off = (v * 32 + lane) * Cfg::VEC;
+        if (Cfg::VEC == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(cx + off);
+            const float4 b = *reinterpret_cast<const float4*>(cy + off);
+            x[v * 4] = a.x; x[v * 4 + 1] = a.y; x[v * 4 + 2] = a.z; x[v * 4 + 3] = a.w;
+            y[v * 4] = b.x; y[v * 4 + 1] = b.y; y[v * 4 + 2] = b.z; y[v * 4 + 3] = b.w;
+        } else {
+            const float2 a = *reinterpret_cast<const float2*>(cx + off);
+            const float2 b = *reinterpret_cast<const float2*>(cy + off);
+            x[v * 2] = a.x; x[v * 2 + 1] = a.y;
+            y[v * 2] = b.x; y[v * 2 + 1] = b.y;
+        }
+    }
+    float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+    for (int i = 0; i < Cfg::NV * Cfg::VEC; ++i) {
+        al = fmaf(x[i], x[i], al);
+        be = fmaf(y[i], y[i], be);
+        ga = fmaf(x[i], y[i], ga);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        be += __shfl_xor_sync(0xffffffffu, be, o);
+        ga += __shfl_xor_sync(0xffffffffu, ga, o);
+    }
+    const float nrm = sqrtf(al) * sqrtf(be);
+    if (!(nrm > 0.f)) return 0.f;
+    const float ratio = fabsf(ga) / nrm;
+    if (ratio <= tol) return ratio;
+    // rotation that makes the two columns orthogonal (Hestenes)
+    const float zeta = (be - al) / (2.f * ga);
+    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+    const float c = rsqrtf(1.f + t * t);
+    const float s = c * t;
+#pragma unroll
+    for (int v = 0; v < Cfg::NV; ++v) {
+        const int off = (v * 32 + lane) * Cfg::VEC;
+        float nx[Cfg::VEC], ny[Cfg::VEC];
+#pragma unroll
+        for (int e = 0; e < Cfg::VEC; ++e) {
+            const float xv = x[v * Cfg::VEC + e], yv = y[v * Cfg::VEC + e];
+            nx[e] = c * xv - s * yv;
+            ny[e] = s * xv + c * yv;
+        }
+        if (Cfg::VEC == 4) {
+            *reinterpret_cast<float4*>(cx + off) = make_float4(nx[0], nx[1], nx[2], nx[3]);
+            *reinterpret_cast<float4*>(cy + off) = make_float4(ny[0], ny[1], ny[2], ny[3]);
+        } else {
+            *reinterpret_cast<float2*>(cx + off) = make_float2(nx[0], nx[1]);
+            *reinterpret_cast<float2*>(cy + off) = make_float2(ny[0], ny[1]);
+        }
+    }
+    return ratio;
+}
+
+template <int NN>
+__global__ void __launch_bounds__(1024, 1)
+k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol) {
+    using Cfg = JacobiCfg<NN>;
+    constexpr int P = Cfg::P;
+    constexpr int NB = 2 * P;          // column blocks of 32
+    constexpr int M = NB - 1;          // tournament rounds per sweep
+    extern __shared__ __align__(16) float cols[];          // [64][NN]
+    __shared__ unsigned int s_max;
+
+    const int rank = blockIdx.x;       // cluster rank (cluster spans blockIdx.x = 0..P-1)
+    const int prob = blockIdx.y;
+    float* G = Gall + (long long)prob * NN * NN;
+    float* cw = conv_ws + (long long)prob * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cg::cluster_group cluster = cg::this_cluster();
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (threadIdx.x == 0) s_max = 0u;
+        float wmax = 0.f;
+        for (int r = 0; r < (P == 1 ? 1 : M); ++r) {
+            int bt, bb;
+            if (P == 1) { bt = 0; bb = 1; }
+            else if (rank == 0) { bt = NB - 1; bb = r; }
+            else { bt = (r + rank) % M; bb = (r - rank + M) % M; }
+            // ---- stage the two column blocks (P==1: only once, they never move) ----
+            if (P > 1 || sweep == 0) {
+                const float4* s0 = reinterpret_cast<const float4*>(G + (long long)bt * 32 * NN);
+                const float4* s1 = reinterpret_cast<const float4*>(G + (long long)bb * 32 * NN);
+                float4* d = reinterpret_cast<float4*>(cols);
+                for (int i = threadIdx.x; i < 32 * NN / 4; i += 1024) {
+                    d[i] = __ldcg(s0 + i);                 // L2 (peers of the cluster wrote these columns)
+                    d[32 * NN / 4 + i] = __ldcg(s1 + i);
+                }
+            }
+            __syncthreads();
+            // ---- pairs inside each block: once per sweep (round 0); top block on warps 0-15, bottom on 16-31
+            if (r == 0) {
+                const int half = warp >> 4, w = warp & 15;
+                float* base = cols + half * 32 * NN;
+                for (int s = 0; s < 31; ++s) {
+                    int a, b;
+                    if (w == 0) { a = 31; b = s; }
+                    else { a = (s + w) % 31; b = (s - w + 31) % 31; }
+                    wmax = fmaxf(wmax, jacobi_pair<NN>(base + a * NN, base + b * NN, lane, tol));
+                    __syncthreads();
+                }
+            }
+            // ---- cross pairs: step s pairs top[w] with bottom[(w+s)%32]
+            for (int s = 0; s < 32; ++s) {
+                wmax = fmaxf(wmax, jacobi_pair<NN>(cols + warp * NN, cols + (32 + ((warp + s) & 31)) * NN, lane, tol));
+                __syncthreads();
+            }
+            if (P > 1) {
+                float4* d0 = reinterpret_cast<float4*>(G + (long long)bt * 32 * NN);
+                float4* d1 = reinterpret_cast<float4*>(G + (long long)bb * 32 * NN);
+                const float4* sc = reinterpret_cast<const float4*>(cols);
+                for (int i = threadIdx.x; i < 32 * NN / 4; i += 1024) {
+                    d0[i] = sc[i];
+                    d1[i] = sc[32 * NN / 4 + i];
+                }
+                __threadfence();
+                cluster.sync();   // release/acquire: next round reads what the peers just wrote
+            }
+        }
+        // ---- convergence: largest |x.y| / (|x||y|) seen in this sweep, agreed across the cluster
+        if (lane == 0) atomicMax(&s_max, __float_as_uint(wmax));
+        __syncthreads();
+        float gmax = __uint_as_float(s_max);
+        if (P > 1) {
+            if (threadIdx.x == 0) {
+                reinterpret_cast<volatile float*>(cw)[rank] = gmax;
+                __threadfence();
+            }
+            cluster.sync();
+            gmax = 0.f;
+            for (int i = 0; i < P; ++i) gmax = fmaxf(gmax, reinterpret_cast<volatile float*>(cw)[i]);
+            cluster.sync();   // everyone has read before the next sweep overwrites
+        }
+        __syncthreads();
+        if (gmax <= tol) { ++sweep; break; }
+    }
+    if (P == 1) {
+        float4* d = reinterpret_cast<float4*>(G);
+        const float4* sc = reinterpret_cast<const float4*>(cols);
+        for (int i = threadIdx.x; i < 64 * NN / 4; i += 1024) d[i] = sc[i];
+    }
+    if (rank == 0 && threadIdx.x == 0 && sweeps_out) sweeps_out[prob] = sweep;
+}
+
+// sigma_i = |column i|; per-problem kept count; scaling d_i of the rank-k reconstruction
+//   mode 0 (content, whitening): d = (sigma+eps_eig)^-1/2 / sigma^2
+//   mode 1 (style, colouring)  : d = (sigma+eps_eig)^+1/2 / sigma^2
+//   so that  E_k f(S_k) E_k^T = G diag(d) G^T  with G's columns = sigma_i u_i.
+__global__ void k_eig_post(const float* __restrict__ Gall, int C, float thresh, float eps_eig, int n_content,
+                           float* __restrict__ sigma, float* __restrict__ dvec, int* __restrict__ kcount) {
+    const int prob = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (col >= C) return;
+    const float* g = Gall + ((long long)prob * C + col) * C;
+    float ss = 0.f;
+    for (int i = lane; i < C; i += 32) ss = fmaf(g[i], g[i], ss);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+        const float sg = sqrtf(ss);
+        sigma[(long long)prob * C + col] = sg;
+        float d = 0.f;
+        if (sg > thresh) {                                       // ops.py:68-69,112,125
+            const float f = (prob < n_content) ? rsqrtf(sg + eps_eig) : sqrtf(sg + eps_eig);
+            d = f / ss;
+            if (kcount) atomicAdd(&kcount[prob], 1);
+        }
+        if (dvec) dvec[(long long)prob * C + col] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Stage C: small dense products  Cm[i][j] = sum_k A[k][i] * d[k] * B[k][j]   (all n x n, k-major)
+//   grid (n/64, n/64, batch); 256 threads, 4x4 per thread
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_outer_gemm(const float* __restrict__ A, long long sa, const float* __restrict__ B, long long sb,
+             const float* __restrict__ d, long long sd, float* __restrict__ Cm, long long sc, int n) {
+    __shared__ __align__(16) float As[16][64];
+    __shared__ __align__(16) float Bs[16][64];
+    const int z = blockIdx.z;
+    const float* a = A + (long long)z * sa;
+    const float* b = B + (long long)z * sb;
+    const float* dd = d ? d + (long long)z * sd : nullptr;
+    const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int lk = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;   // loader: 16 k-rows x 64 cols
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+    for (int k0 = 0; k0 < n; k0 += 16) {
+        float4 av = *reinterpret_cast<const float4*>(a + (long long)(k0 + lk) * n + i0 + lc);
+        const float4 bv = *reinterpret_cast<const float4*>(b + (long long)(k0 + lk) * n + j0 + lc);
+        if (dd) {
+            const float s = dd[k0 + lk];
+            av.x *= s; av.y *= s; av.z *= s; av.w *= s;
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&As[lk][lc]) = av;
+        *reinterpret_cast<float4*>(&Bs[lk][lc]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 x = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 y = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float xv[4] = {x.x, x.y, x.z, x.w};
+            const float yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(xv[r], yv[c], acc[r][c]);
+        }
+    }
+    float* cm = Cm + (long long)z * sc;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        *reinterpret_cast<float4*>(cm + (long long)(i0 + ty * 4 + r) * n + j0 + tx * 4) =
+            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+}
+
+// M = alpha*T + (1-alpha)*I  -> split-fp16 GEMM operand [frame][2][C][C] (row = output channel)
+// bias = alpha*ms - M*mc + (1-alpha)*readd*mc                       (ops.py:80-83 / 131-133)
+//   one warp per (frame, output channel)
+__global__ void k_finalize_transform(const float* __restrict__ T, int C, int Nc, int Ns, float alpha, int readd,
+                                     const float* __restrict__ mean_c, const float* __restrict__ mean_s,
+                                     __half* __restrict__ Msplit, float* __restrict__ bias) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int z = blockIdx.y;
+    if (row >= C) return;
+    const float* t = T + ((long long)z * C + row) * C;
+    const float* mc = mean_c + (long long)z * C;
+    const float* ms = mean_s + (long long)(Ns == 1 ? 0 : z) * C;
+    __half* mh = Msplit + (((long long)z * 2 + 0) * C + row) * C;
+    __half* ml = Msplit + (((long long)z * 2 + 1) * C + row) * C;
+    float dot = 0.f;
+    for (int j = lane; j < C; j += 32) {
+        const float m = alpha * t[j] + (j == row ? 1.f - alpha : 0.f);
+        __half hi, lo;
+        split_f32(m, hi, lo);
+        mh[j] = hi;
+        ml[j] = lo;
+        dot = fmaf(m, mc[j], dot);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) bias[(long long)z * C + row] = alpha * ms[row] - dot + (readd ? (1.f - alpha) * mc[row] : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// AdaIN (ops.py:282-294): per-(frame,channel) affine map
+// ---------------------------------------------------------------------------
+__global__ void k_adain_coeffs(const float* __restrict__ mean_c, const float* __restrict__ var_c,
+                               const float* __restrict__ mean_s, const float* __restrict__ var_s, int C, int Nc, int Ns,
+                               float alpha, float eps, float* __restrict__ scale, float* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Nc * C) return;
+    const int z = i / C, c = i % C;
+    const int si = (Ns == 1 ? 0 : z) * C + c;
+    const float inv = rsqrtf(var_c[i] + eps) * sqrtf(var_s[si]);   // batch_normalization(scale=sqrt(style_var))
+    // y = (x - mc)*inv + ms ; out = alpha*y + (1-alpha)*x
+    scale[i] = alpha * inv + (1.f - alpha);
+    shift[i] = alpha * (mean_s[si] - mean_c[i] * inv);
+}
+__global__ void k_affine_apply(const __half* __restrict__ in, ActGeom g, const float* __restrict__ scale,
+                               const float* __restrict__ shift, __half* __restrict__ out) {
+    const int cgs = g.C / 8;
+    const long long total = (long long)g.N * g.H * g.W * cgs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cgs) * 8;
+        long long pix = i / cgs;
+        const int x = (int)(pix % g.W); pix /= g.W;
+        const int y = (int)(pix % g.H);
+        const int n = (int)(pix / g.H);
+        float v[8];
+        load8(in, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, c0, v);
+        const float* sc = scale + (long long)n * g.C + c0;
+        const float* sh = shift + (long long)n * g.C + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        Half8 hi, lo;
+        split8(v, hi, lo);
+        store8_with_halo(out, g, n, y, x, c0, hi, lo);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WctWs {
+    size_t sum, sumsq, mean, var, cov, G, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
+};
+static WctWs wct_layout(int C, int Nc, int Ns) {
+    WctWs w;
+    const size_t np = (size_t)Nc + Ns;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    w.sum = take(np * C * 8);
+    w.sumsq = take(np * C * 8);
+    w.cov = take(np * C * C * 8);      // contiguous with sum/sumsq: one memset clears all three
+    w.mean = take(np * C * 4);
+    w.var = take(np * C * 4);
+    w.G = take(np * C * C * 4);
+    w.sigma = take(np * C * 4);
+    w.dvec = take(np * C * 4);
+    w.Wc = take((size_t)Nc * C * C * 4);
+    w.Cs = take((size_t)Ns * C * C * 4);
+    w.T = take((size_t)Nc * C * C * 4);
+    w.Msplit = take((size_t)Nc * 2 * C * C * 2);
+    w.bias = take((size_t)Nc * C * 4);
+    w.conv = take(np * 16 * 4);
+    w.kcount = take(np * 2 * 4);
+    w.scale = take((size_t)Nc * C * 4);
+    w.shift = take((size_t)Nc * C * 4);
+    w.total = o;
+    return w;
+}
+size_t wct_workspace_bytes(int C, int Nc, int Ns) { return wct_layout(C, Nc, Ns).total; }
+
+static int pick_chunk(long long HW) { return HW >= 65536 ? 512 : 256; }
+
+template <bool SQ>
+static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq, cudaStream_t st) {
+    const long long HW = (long long)g.H * g.W;
+    const int chunk = 1024;
+    dim3 grid((unsigned)cdiv(HW, chunk), (unsigned)g.N);
+    k_chan_sums<SQ><<<grid, 256, 0, st>>>(act, g, chunk, sum, sumsq);
+    WCTB_CHECK_LAUNCH("k_chan_sums");
+    return 0;
+}
+
+int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
+    const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
+    const int max_sweeps = 40;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(C / 64), (unsigned)count, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)(C / 64);
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+#define WCTB_JACOBI_CASE(NN)                                                                                         \
+    case NN: {                                                                                                       \
+        static bool done = false;                                                                                    \
+        if (!done) {                                                                                                 \
+            WCTB_CUDA(cudaFuncSetAttribute(k_jacobi<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
+                                           JacobiCfg<NN>::SMEM_BYTES));                                              \
+            done = true;                                                                                             \
+        }                                                                                                            \
+        cfg.dynamicSmemBytes = JacobiCfg<NN>::SMEM_BYTES;                                                            \
+        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol));                      \
+        break;                                                                                                       \
+    }
+    switch (C) {
+        WCTB_JACOBI_CASE(64)
+        WCTB_JACOBI_CASE(128)
+        WCTB_JACOBI_CASE(256)
+        WCTB_JACOBI_CASE(512)
+        default:
+            set_error("jacobi: C=%d not in {64,128,256,512}", C);
+            return WCTB200_EINVAL;
+    }
+#undef WCTB_JACOBI_CASE
+    return 0;
+}
+
+int launch_eig_post(const float* G, int C, int count, float thresh, float eps_eig, int n_content, float* sigma,
+                    float* dvec, int* kcount, cudaStream_t st) {
+    dim3 grid((unsigned)cdiv(C, 8), (unsigned)count);
+    k_eig_post<<<grid, 256, 0, st>>>(G, C, thresh, eps_eig, n_content, sigma, dvec, kcount);
+    WCTB_CHECK_LAUNCH("k_eig_post");
+    return 0;
+}
+
+static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float eps_cov,
+                         cudaStream_t st) {
+    const long long HW = (long long)g.H * g.W;
+    int rc = launch_sums<false>(act, g, sum, nullptr, st);
+    if (rc) return rc;
+    k_mean_finalize<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(sum, nullptr, HW, g.N * g.C, mean, nullptr);
+    WCTB_CHECK_LAUNCH("k_mean_finalize");
+    const int nb = g.C / 64;
+    const int chunk = pick_chunk(HW);
+    dim3 grid((unsigned)(nb * (nb + 1) / 2), (unsigned)cdiv(HW, chunk), (unsigned)g.N);
+    k_cov_partial<<<grid, 256, 0, st>>>(act, g, mean, chunk, cov);
+    WCTB_CHECK_LAUNCH("k_cov_partial");
+    k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
+        cov, g.C, HW, eps_cov, g.N, G);
+    WCTB_CHECK_LAUNCH("k_cov_finalize");
+    return 0;
+}
+
+int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
+                     float alpha, float eps_cov, float eps_eig, float thresh, int readd, __half* out, int32_t* k_out,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
+    WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "wct_level: C=%d not in {64,128,256,512}", C);
+    WCTB_REQUIRE(Ns == 1 || Ns == Nc, "wct_level: Ns must be 1 or Nc");
+    WCTB_REQUIRE(Hc >= 2 && Wc >= 2 && Hs >= 2 && Ws >= 2 && (long long)Hc * Wc >= 2 && (long long)Hs * Ws >= 2, "wct_level: bad geometry");
+    const WctWs L = wct_layout(C, Nc, Ns);
+    if (ws_bytes < L.total) {
+        set_error("wct_level: workspace %zu < %zu bytes", ws_bytes, L.total);
+        return WCTB200_EWS;
+    }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    const int np = Nc + Ns;
+    double* sum = reinterpret_cast<double*>(w + L.sum);
+    double* cov = reinterpret_cast<double*>(w + L.cov);
+    float* mean = reinterpret_cast<float*>(w + L.mean);
+    float* G = reinterpret_cast<float*>(w + L.G);
+    float* sigma = reinterpret_cast<float*>(w + L.sigma);
+    float* dvec = reinterpret_cast<float*>(w + L.dvec);
+    float* Wcm = reinterpret_cast<float*>(w + L.Wc);
+    float* Csm = reinterpret_cast<float*>(w + L.Cs);
+    float* T = reinterpret_cast<float*>(w + L.T);
+    __half* Msplit = reinterpret_cast<__half*>(w + L.Msplit);
+    float* bias = reinterpret_cast<float*>(w + L.bias);
+    float* conv = reinterpret_cast<float*>(w + L.conv);
+    int* kc = reinterpret_cast<int*>(w + L.kcount);
+    const long long CC = (long long)C * C;
+
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));          // sum, sumsq, cov
+    WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)np * 2 * 4, st));
+    ActGeom gc(Nc, Hc, Wc, C), gs(Ns, Hs, Ws, C);
+    int rc = stats_and_cov(content, gc, sum, cov, mean, G, eps_cov, st);
+    if (rc) return rc;
+    rc = stats_and_cov(style, gs, sum + (long long)Nc * C, cov + Nc * CC, mean + (long long)Nc * C, G + Nc * CC, eps_cov, st);
+    if (rc) return rc;
+    rc = launch_jacobi(G, C, np, conv, kc + np, st);
+    if (rc) return rc;
+    rc = launch_eig_post(G, C, np, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    if (rc) return rc;
+    // W_c (whitening) per content frame, C_s (colouring) per style
+    dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)np);
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C);   // Wc and Cs are contiguous in ws (Wc then Cs)
+    WCTB_CHECK_LAUNCH("k_outer_gemm(W)");
+    dim3 gt((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Nc);
+    k_outer_gemm<<<gt, 256, 0, st>>>(Csm, Ns == 1 ? 0 : CC, Wcm, CC, nullptr, 0, T, CC, C);   // T = C_s W_c (C_s symmetric)
+    WCTB_CHECK_LAUNCH("k_outer_gemm(T)");
+    dim3 gf((unsigned)cdiv(C, 8), (unsigned)Nc);
+    k_finalize_transform<<<gf, 256, 0, st>>>(T, C, Nc, Ns, alpha, readd, mean, mean + (long long)Nc * C, Msplit, bias);
+    WCTB_CHECK_LAUNCH("k_finalize_transform");
+    // out = M x + bias on the tensor cores (1-tap conv, per-frame weight set)
+    rc = launch_conv3x3_tc(content, Nc, Hc, Wc, C, Msplit, 1, Nc, bias, C, 0, out, st);
+    if (rc) return rc;
+    if (k_out) WCTB_CUDA(cudaMemcpyAsync(k_out, kc, (size_t)np * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
+                       float alpha, float eps, __half* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WCTB_REQUIRE(C % 8 == 0 && C <= 2048, "adain_level: C=%d must be a multiple of 8 (<= 2048)", C);
+    WCTB_REQUIRE(Ns == 1 || Ns == Nc, "adain_level: Ns must be 1 or Nc");
+    const WctWs L = wct_layout(C, Nc, Ns);
+    if (ws_bytes < L.total) {
+        set_error("adain_level: workspace %zu < %zu bytes", ws_bytes, L.total);
+        return WCTB200_EWS;
+    }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    double* sum = reinterpret_cast<double*>(w + L.sum);
+    double* sumsq = reinterpret_cast<double*>(w + L.sumsq);
+    float* mean = reinterpret_cast<float*>(w + L.mean);
+    float* var = reinterpret_cast<float*>(w + L.var);
+    float* scale = reinterpret_cast<float*>(w + L.scale);
+    float* shift = reinterpret_cast<float*>(w + L.shift);
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.cov - L.sum, st));
+    ActGeom gc(Nc, Hc, Wc, C), gs(Ns, Hs, Ws, C);
+    int rc = launch_sums<true>(content, gc, sum, sumsq, st);
+    if (rc) return rc;
+    rc = launch_sums<true>(style, gs, sum + (long long)Nc * C, sumsq + (long long)Nc * C, st);
+    if (rc) return rc;
+    k_mean_finalize<<<cdiv((long long)Nc * C, 256), 256, 0, st>>>(sum, sumsq, (long long)Hc * Wc, Nc * C, mean, var);
+    WCTB_CHECK_LAUNCH("k_mean_finalize(c)");
+    k_mean_finalize<<<cdiv((long long)Ns * C, 256), 256, 0, st>>>(sum + (long long)Nc * C, sumsq + (long long)Nc * C,
+                                                                  (long long)Hs * Ws, Ns * C, mean + (long long)Nc * C,
+                                                                  var + (long long)Nc * C);
+    WCTB_CHECK_LAUNCH("k_mean_finalize(s)");
+    k_adain_coeffs<<<cdiv((long long)Nc * C, 256), 256, 0, st>>>(mean, var, mean + (long long)Nc * C, var + (long long)Nc * C, C,
+                                                                 Nc, Ns, alpha, eps, scale, shift);
+    WCTB_CHECK_LAUNCH("k_adain_coeffs");
+    const long long total = (long long)Nc * Hc * Wc * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_affine_apply<<<(unsigned)blocks, 256, 0, st>>>(content, gc, scale, shift, out);
+    WCTB_CHECK_LAUNCH("k_affine_apply");
+    return 0;
+}
+
+}  // namespace wctb

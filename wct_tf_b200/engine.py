@@ -1,0 +1,243 @@
+"""Executes the multi-level WCT plan (model.py) on one GPU through libwctb200.
+
+Host side of the hot path ``WCT.predict`` (wct.py:70-106): PyTorch is used only
+for device memory, streams and H2D/D2H copies; every arithmetic step is a
+hand-written sm_100a kernel behind the C-ABI (include/wctb200.h).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _capi
+from .model import WCTModel, RELU_CHANNELS
+
+# wct_tf (ops.py:24-90, what the graph executes) vs wct_np (ops.py:92-140, the named oracle)
+SEMANTICS = {
+    "tf": dict(eps_cov=1e-8, eps_eig=0.0, thresh=1e-5, readd=1),
+    "np": dict(eps_cov=0.0, eps_eig=1e-5, thresh=1e-5, readd=0),
+}
+
+
+class Act(object):
+    """SPF16 activation: device buffer + logical NHWC shape."""
+    __slots__ = ("buf", "N", "H", "W", "C")
+
+    def __init__(self, buf, N, H, W, C):
+        self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+class Engine(object):
+    def __init__(self, weights, relu_targets, device="cuda:0", semantics="tf"):
+        if not torch.cuda.is_available():
+            raise _capi.WctB200Error("no CUDA device: the WCT engine has no CPU fallback")
+        self.lib = _capi.load()
+        self.device = torch.device(device)
+        self.model = WCTModel(mode="test", relu_targets=relu_targets)
+        if semantics not in SEMANTICS:
+            raise ValueError("semantics must be 'tf' or 'np'")
+        self.semantics = semantics
+        self.last_info = None
+        self._ws = {}
+        with torch.cuda.device(self.device):
+            self._upload(weights)
+
+    # ------------------------------------------------------------------ weights
+    def _dev(self, a, dtype=torch.float32):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+
+    def _prep_split(self, w_hwio):
+        """fp32 (kH,kW,Cin,Cout) -> device split-fp16 GEMM operand."""
+        kh, kw, cin, cout = w_hwio.shape
+        src = self._dev(w_hwio.astype(np.float32))
+        dst = torch.empty(self.lib.wctb200_conv_weight_bytes(kh * kw, cin, cout), dtype=torch.uint8, device=self.device)
+        _capi.check(self.lib.wctb200_prep_conv_weights(src.data_ptr(), kh * kw, cin, cout, dst.data_ptr(), self._stream()))
+        return dst
+
+    def _upload(self, weights):
+        vgg = {l["name"]: l for l in weights["vgg"]}
+        # fold the 1x1 'preprocess' conv (vgg_normalised.py:25-26) into conv1_1 (exact: a per-pixel affine
+        # map commutes with reflect padding); done in float64 on the host, once.
+        w0 = np.asarray(vgg["preprocess"]["weight"], dtype=np.float64)[:, :, 0, 0]  # (O=j, I=i)
+        b0 = np.asarray(vgg["preprocess"]["bias"], dtype=np.float64)
+        w1 = np.asarray(vgg["conv1_1"]["weight"], dtype=np.float64)                 # (O, j, kH, kW)
+        b1 = np.asarray(vgg["conv1_1"]["bias"], dtype=np.float64)
+        wf = np.einsum("ojyx,ji->yxio", w1, w0)                                      # (kH,kW,i,O)
+        bf = b1 + np.einsum("ojyx,j->o", w1, b0)
+        self.head_w = self._dev(wf.reshape(27, 64).astype(np.float32))
+        self.head_b = self._dev(bf.astype(np.float32))
+        self.enc_w, self.enc_b = {}, {}
+        deepest_ops = [op for op in self.model.style_plan if op.kind == "conv" and op.name != "conv1_1"]
+        for op in deepest_ops:
+            l = vgg[op.name]
+            hwio = np.transpose(np.asarray(l["weight"], dtype=np.float32), (2, 3, 1, 0))  # vgg_normalised.py:33
+            self.enc_w[op.name] = self._prep_split(hwio)
+            self.enc_b[op.name] = self._dev(np.asarray(l["bias"], dtype=np.float32))
+        self.dec_w, self.dec_b, self.tail_w, self.tail_b = {}, {}, {}, {}
+        for lvl in self.model.levels:
+            relu = lvl.relu_target
+            if relu in self.tail_w:
+                continue
+            if relu not in weights["decoders"]:
+                raise Exception("No checkpoint found for target {}".format(relu))  # wct.py:57-58
+            layers = {l["name"]: l for l in weights["decoders"][relu]}
+            for op in self.model.decoder_plan(lvl.index):
+                if op.kind != "conv":
+                    continue
+                l = layers[op.name]
+                k = np.asarray(l["kernel"], dtype=np.float32)
+                assert k.shape == (3, 3, op.cin, op.cout), (op.name, k.shape)
+                if op.act:
+                    self.dec_w[op.name] = self._prep_split(k)
+                    self.dec_b[op.name] = self._dev(np.asarray(l["bias"], dtype=np.float32))
+                else:
+                    self.tail_w[relu] = self._dev(k.reshape(9 * op.cin, 3))
+                    self.tail_b[relu] = self._dev(np.asarray(l["bias"], dtype=np.float32))
+        torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _act(self, N, H, W, C):
+        nbytes = self.lib.wctb200_act_bytes(N, H, W, C)
+        return Act(torch.empty(nbytes, dtype=torch.uint8, device=self.device), N, H, W, C)
+
+    def _workspace(self, C, Nc, Ns):
+        key = (C, Nc, Ns)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = torch.empty(self.lib.wctb200_wct_workspace_bytes(C, Nc, Ns), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ layers
+    def encode(self, img, target, taps=()):
+        """img: float32 cuda tensor [N,H,W,3] in [0,1].  Runs the shared encoder up to
+        ``target`` (vgg_normalised.py:22-50); returns (act_at_target, {tap: act})."""
+        N, H, W, _ = img.shape
+        st = self._stream()
+        lib = self.lib
+        x = self._act(N, H, W, 64)
+        _capi.check(lib.wctb200_conv_head(img.data_ptr(), N, H, W, self.head_w.data_ptr(), self.head_b.data_ptr(), x.ptr, st))
+        kept = {}
+        if "relu1_1" in taps:
+            kept["relu1_1"] = x
+        from .model import encoder_plan
+        for op in encoder_plan(target)[1:]:
+            if op.kind == "conv":
+                y = self._act(N, x.H, x.W, op.cout)
+                _capi.check(lib.wctb200_conv3x3(x.ptr, N, x.H, x.W, op.cin, self.enc_w[op.name].data_ptr(),
+                                                self.enc_b[op.name].data_ptr(), op.cout, _capi.RELU, y.ptr, st))
+                x = y
+                relu_name = op.name.replace("conv", "relu")
+                if relu_name in taps:
+                    kept[relu_name] = x
+            else:
+                y = self._act(N, (x.H + 1) // 2, (x.W + 1) // 2, x.C)
+                _capi.check(lib.wctb200_maxpool2(x.ptr, N, x.H, x.W, x.C, y.ptr, st))
+                x = y
+        return x, kept
+
+    def decode(self, feat, level_index, clip):
+        """Run decoder ``level_index`` (model.py:279-300) -> float32 image [N,H',W',3];
+        ``clip`` applies model.py:86's clip_by_value(0,1)."""
+        st = self._stream()
+        lib = self.lib
+        relu = self.model.levels[level_index].relu_target
+        x = feat
+        N = x.N
+        for op in self.model.decoder_plan(level_index):
+            if op.kind == "up":
+                y = self._act(N, x.H * 2, x.W * 2, x.C)
+                _capi.check(lib.wctb200_upsample2(x.ptr, N, x.H, x.W, x.C, y.ptr, st))
+                x = y
+            elif op.act:
+                y = self._act(N, x.H, x.W, op.cout)
+                _capi.check(lib.wctb200_conv3x3(x.ptr, N, x.H, x.W, op.cin, self.dec_w[op.name].data_ptr(),
+                                                self.dec_b[op.name].data_ptr(), op.cout, _capi.RELU, y.ptr, st))
+                x = y
+            else:
+                img = torch.empty((N, x.H, x.W, 3), dtype=torch.float32, device=self.device)
+                _capi.check(lib.wctb200_conv_tail(x.ptr, N, x.H, x.W, op.cin, self.tail_w[relu].data_ptr(),
+                                                  self.tail_b[relu].data_ptr(), _capi.CLIP01 if clip else 0,
+                                                  img.data_ptr(), st))
+                return img
+        raise AssertionError("decoder plan without a tail conv")
+
+    def transform(self, content, style, alpha, adain, want_info=False):
+        """wct_tf / wct_np / adain on one level (model.py:144-158)."""
+        st = self._stream()
+        out = self._act(content.N, content.H, content.W, content.C)
+        ws = self._workspace(content.C, content.N, style.N)
+        if adain:
+            _capi.check(self.lib.wctb200_adain_level(content.ptr, content.N, content.H, content.W, style.ptr, style.N,
+                                                     style.H, style.W, content.C, float(alpha), 1e-5, out.ptr,
+                                                     ws.data_ptr(), ws.numel(), st))
+            return out, None
+        sem = SEMANTICS[self.semantics]
+        kbuf = torch.empty(2 * (content.N + style.N), dtype=torch.int32, device=self.device) if want_info else None
+        _capi.check(self.lib.wctb200_wct_level(content.ptr, content.N, content.H, content.W, style.ptr, style.N,
+                                               style.H, style.W, content.C, float(alpha), sem["eps_cov"],
+                                               sem["eps_eig"], sem["thresh"], sem["readd"], out.ptr,
+                                               kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st))
+        return out, kbuf
+
+    # ------------------------------------------------------------------ pipeline
+    def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None):
+        """content_u8: cuda uint8 [N,H,W,3]; style_u8: cuda uint8 [Ns,Hs,Ws,3], Ns in {1, N}.
+        Returns the float32 ``decoded_output`` [N,H',W',3] (unclipped, model.py:94).
+        ``capture`` (dict) receives every level's input image / features for parity tests."""
+        lib, st = self.lib, self._stream()
+        N = content_u8.shape[0]
+        assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
+        assert style_u8.shape[0] in (1, N)
+        content = torch.empty(content_u8.shape, dtype=torch.float32, device=self.device)
+        style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
+        _capi.check(lib.wctb200_image_u8_to_f32(content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st))
+        _capi.check(lib.wctb200_image_u8_to_f32(style_u8.data_ptr(), style_u8.numel(), style.data_ptr(), st))
+        # model.py:70-72: one style pass emitting every target
+        _, style_feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
+        infos = []
+        x = content
+        nlev = len(self.model.levels)
+        for lvl in self.model.levels:
+            cf, _ = self.encode(x, lvl.relu_target)
+            f, kbuf = self.transform(cf, style_feats[lvl.relu_target], alpha, adain, want_info)
+            infos.append(kbuf)
+            if capture is not None:
+                capture.setdefault("level_input", []).append(x)
+                capture.setdefault("content_feat", []).append(cf)
+                capture.setdefault("transformed", []).append(f)
+            # model.py:86: clip between levels; model.py:94: last output unclipped
+            x = self.decode(f, lvl.index, clip=(lvl.index < nlev - 1))
+            if capture is not None:
+                capture.setdefault("level_output", []).append(x)
+        if want_info:
+            self.last_info = infos
+        return x
+
+    def to_u8(self, img_f32):
+        """WCT.postprocess (wct.py:66-68)."""
+        out = torch.empty(img_f32.shape, dtype=torch.uint8, device=self.device)
+        _capi.check(self.lib.wctb200_image_f32_to_u8(img_f32.data_ptr(), img_f32.numel(), out.data_ptr(), self._stream()))
+        return out
+
+    def act_to_f32(self, act):
+        out = torch.empty((act.N, act.H, act.W, act.C), dtype=torch.float32, device=self.device)
+        _capi.check(self.lib.wctb200_act_to_f32(act.ptr, act.N, act.H, act.W, act.C, out.data_ptr(), self._stream()))
+        return out
+
+    def act_from_f32(self, t):
+        N, H, W, C = t.shape
+        a = self._act(N, H, W, C)
+        t = t.contiguous()
+        _capi.check(self.lib.wctb200_act_from_f32(t.data_ptr(), N, H, W, C, a.ptr, self._stream()))
+        return a
+
+    def check_device(self):
+        _capi.check(self.lib.wctb200_check_device(self._stream()))

@@ -1,0 +1,94 @@
+"""``WCT`` -- drop-in for the reference inference wrapper (wct.py:14-106).
+
+Same constructor and ``predict`` signature; the TF session is replaced by the
+sm_100a engine (engine.py -> libwctb200.so).  Differences, all explicit:
+  * ``checkpoints`` / ``vgg_path`` may be file paths (``.npz`` bundles, see
+    weights.py) OR ``weights=`` may pass an in-memory weights dict (the offline
+    build has no .t7 / TF checkpoints, so benchmarks use synthetic weights);
+  * ``device`` accepts the reference's TF strings ('/gpu:0') and torch strings;
+  * ``swap5=True`` (style-swap, ops.py:145-278) is out of scope -> NotImplementedError;
+  * ``predict_batch`` is new: a batch of frames per call (frames are independent).
+"""
+from __future__ import annotations
+
+import re
+import time
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+def _torch_device(device):
+    """'/gpu:0' (stylize.py:23) -> 'cuda:0'."""
+    if isinstance(device, str):
+        m = re.match(r"^/?(?:device:)?gpu:(\d+)$", device.strip().lower())
+        if m:
+            return "cuda:%s" % m.group(1)
+        if device.strip().lower() in ("/cpu:0", "cpu"):
+            raise ValueError("the B200 engine has no CPU path (device=%r)" % (device,))
+    return device
+
+
+class WCT(object):
+    '''Stylize images with the multi-level WCT pipeline (mirror of wct.py:14)'''
+
+    def __init__(self, checkpoints=None, relu_targets=None, vgg_path=None, device='/gpu:0',
+                 ss_patch_size=3, ss_stride=1, weights=None, semantics="tf", verbose=False):
+        if relu_targets is None:
+            raise ValueError("relu_targets is required")
+        self.ss_patch_size = ss_patch_size
+        self.ss_stride = ss_stride
+        self.verbose = verbose
+        if weights is None:
+            from .weights import load_weights
+            weights = load_weights(vgg_path, checkpoints, relu_targets)   # pairs checkpoints[i] <-> relu_targets[i] (wct.py:47)
+        self.engine = Engine(weights, relu_targets, device=_torch_device(device), semantics=semantics)
+        self.model = self.engine.model
+
+    @staticmethod
+    def preprocess(image):
+        """wct.py:60-64"""
+        if len(image.shape) == 3:
+            image = np.expand_dims(image, 0)
+        return image / 255.
+
+    @staticmethod
+    def postprocess(image):
+        """wct.py:66-68"""
+        return np.uint8(np.clip(image, 0, 1) * 255)
+
+    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False):
+        """contents: uint8 [N,H,W,3]; styles: uint8 [1|N,Hs,Ws,3] (numpy or torch, host or device).
+        Returns uint8 [N,H',W',3] numpy (and the float image if return_float)."""
+        eng = self.engine
+        dev = eng.device
+
+        def to_dev(a):
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a))
+            if a.dim() == 3:
+                a = a.unsqueeze(0)
+            if a.dtype != torch.uint8:
+                a = a.clamp(0, 255).to(torch.uint8)   # the reference feeds arrays "in [0,255]" (wct.py:74)
+            return a.to(dev, non_blocking=True).contiguous()
+
+        with torch.cuda.device(dev):
+            c = to_dev(contents)
+            s = to_dev(styles)
+            out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
+            out_u8 = eng.to_u8(out_f).cpu().numpy()
+        if return_float:
+            return out_u8, out_f.cpu().numpy()
+        return out_u8
+
+    def predict(self, content, style, alpha=1, swap5=False, ss_alpha=1, adain=False):
+        '''Stylize a single content/style pair (wct.py:70-106).'''
+        if swap5:
+            raise NotImplementedError("style-swap at relu5_1 (ops.py:145-278) is out of scope for this engine")
+        s = time.time()
+        out = self.predict_batch(np.asarray(content), np.asarray(style), alpha=alpha, adain=adain)
+        if self.verbose:
+            print("Stylized in:", time.time() - s)   # wct.py:104
+        return out[0]

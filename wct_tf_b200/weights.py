@@ -68,3 +68,53 @@ def make_synthetic_weights(seed=42, relu_targets=RELU_TARGETS_ALL, act_rms=1.4,
             layers.append(dict(name=op.name, kernel=k.astype(np.float32), bias=b.astype(np.float32)))
         decoders[relu] = layers
     return dict(vgg=vgg, decoders=decoders)
+
+
+def save_weights(path, weights):
+    """Write a weights dict as one ``.npz`` bundle (the engine's own offline format)."""
+    flat = {}
+    for l in weights["vgg"]:
+        flat["vgg/%s/weight" % l["name"]] = l["weight"]
+        flat["vgg/%s/bias" % l["name"]] = l["bias"]
+    for relu, layers in weights["decoders"].items():
+        for l in layers:
+            flat["dec/%s/%s/kernel" % (relu, l["name"])] = l["kernel"]
+            flat["dec/%s/%s/bias" % (relu, l["name"])] = l["bias"]
+    np.savez(path, **flat)
+
+
+def _load_npz(path):
+    z = np.load(path)
+    vgg_names = ["preprocess"] + [n for n, _, _ in VGG_CONVS]
+    vgg = [dict(name=n, weight=z["vgg/%s/weight" % n], bias=z["vgg/%s/bias" % n])
+           for n in vgg_names if "vgg/%s/weight" % n in z.files]
+    decoders = {}
+    for key in z.files:
+        if key.startswith("dec/") and key.endswith("/kernel"):
+            _, relu, name, _ = key.split("/")
+            decoders.setdefault(relu, []).append(dict(name=name, kernel=z[key], bias=z["dec/%s/%s/bias" % (relu, name)]))
+    for relu in decoders:
+        decoders[relu].sort(key=lambda l: int(l["name"].rsplit("_", 1)[1]))
+    return dict(vgg=vgg, decoders=decoders)
+
+
+def load_weights(vgg_path, checkpoints, relu_targets):
+    """Mirror of the reference's loading protocol (wct.py:47-58): ``checkpoints[i]``
+    pairs with ``relu_targets[i]``; a target without a checkpoint raises.
+
+    Supported here: ``.npz`` bundles written by ``save_weights`` (``vgg_path`` holds the
+    encoder; each checkpoint holds at least its own decoder).  The reference's own
+    formats (Torch7 ``vgg_normalised.t7`` via torchfile.py, TF1 Saver checkpoints) are the
+    next scope row: those files do not exist offline."""
+    if vgg_path is None or checkpoints is None:
+        raise ValueError("vgg_path and checkpoints are required when no weights dict is given")
+    if not str(vgg_path).endswith(".npz"):
+        raise NotImplementedError("only .npz weight bundles are readable offline; .t7 import is scope row 8f-1")
+    vgg = _load_npz(vgg_path)["vgg"]
+    decoders = {}
+    for relu, ck in zip(relu_targets, checkpoints):     # wct.py:47 zip pairing
+        d = _load_npz(ck)["decoders"] if str(ck).endswith(".npz") else {}
+        if relu not in d:
+            raise Exception('No checkpoint found for target {} in dir {}'.format(relu, ck))  # wct.py:58
+        decoders[relu] = d[relu]
+    return dict(vgg=vgg, decoders=decoders)
