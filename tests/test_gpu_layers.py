@@ -75,7 +75,8 @@ def test_conv_head_matches_preprocess_plus_conv1_1(shape):
     wf = np.einsum("ojyx,ji->yxio", w1, w0).reshape(27, 64).astype(np.float32)
     bf = (b1 + np.einsum("ojyx,j->o", w1, b0)).astype(np.float32)
     out = U.act_alloc(n, h, w, 64)
-    _capi.check(U.lib().wctb200_conv_head(U.dev(img).data_ptr(), n, h, w, U.dev(wf).data_ptr(), U.dev(bf).data_ptr(),
+    d_img, d_wf, d_bf = U.dev(img), U.dev(wf), U.dev(bf)      # keep the device tensors alive across the async call
+    _capi.check(U.lib().wctb200_conv_head(d_img.data_ptr(), n, h, w, d_wf.data_ptr(), d_bf.data_ptr(),
                                           out.data_ptr(), U.stream()))
     got = U.act_to_numpy(out, n, h, w, 64)
     # reference order of operations: conv0 (1x1), reflect pad, conv1_1, relu (vgg_normalised.py:25-40)
@@ -115,7 +116,8 @@ def test_conv3x3_ref_kernel(case):
     x, k, b = _conv_inputs(case, 5)
     xin = U.act_from_numpy(x)
     out = U.act_alloc(n, h, w, cout)
-    _capi.check(U.lib().wctb200_conv3x3_ref(xin.data_ptr(), n, h, w, cin, U.dev(k).data_ptr(), U.dev(b).data_ptr(), cout,
+    d_k, d_b = U.dev(k), U.dev(b)
+    _capi.check(U.lib().wctb200_conv3x3_ref(xin.data_ptr(), n, h, w, cin, d_k.data_ptr(), d_b.data_ptr(), cout,
                                             _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), k, b, relu)
@@ -131,18 +133,21 @@ def test_conv3x3_tensor_core(case, bn):
     x, k, b = _conv_inputs(case, 7)
     xin = U.act_from_numpy(x)
     wsplit = torch.empty(U.lib().wctb200_conv_weight_bytes(9, cin, cout), dtype=torch.uint8, device="cuda")
-    _capi.check(U.lib().wctb200_prep_conv_weights(U.dev(k).data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
+    d_k, d_b = U.dev(k), U.dev(b)
+    _capi.check(U.lib().wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
     out = U.act_alloc(n, h, w, cout)
     U.lib().wctb200_debug_set_conv_bn(bn)
     try:
-        _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), U.dev(b).data_ptr(), cout,
+        _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,
                                             _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
         U.check_device()
     finally:
         U.lib().wctb200_debug_set_conv_bn(0)
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
-    assert_close(got, ref, name="conv_tc_%d_%d_bn%d" % (cin, cout, bn), x=x, k=k, b=b)
+    # fp32-class tolerance; the tensor core adds into its fp32 accumulator with truncation, so
+    # the error grows ~linearly with the number of K=16 steps (measured 1.2e-5 relative at K=4608)
+    assert_close(got, ref, tol=2e-5 * max(1.0, 9 * cin / 1152.0), name="conv_tc_%d_%d_bn%d" % (cin, cout, bn), x=x, k=k, b=b)
     padded = U.act_raw_padded(out, n, h, w, cout)
     assert np.isfinite(padded).all(), "halo cells left unwritten"
     assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
@@ -181,8 +186,9 @@ def test_conv_tail(shape, clip):
     b = np.array([0.5, 0.4, 0.6], dtype=np.float32)
     xin = U.act_from_numpy(x)
     img = torch.full((n, h, w, 3), float("nan"), dtype=torch.float32, device="cuda")
-    _capi.check(U.lib().wctb200_conv_tail(xin.data_ptr(), n, h, w, c, U.dev(k.reshape(9 * c, 3)).data_ptr(),
-                                          U.dev(b).data_ptr(), _capi.CLIP01 if clip else 0, img.data_ptr(), U.stream()))
+    d_k, d_b = U.dev(k.reshape(9 * c, 3)), U.dev(b)
+    _capi.check(U.lib().wctb200_conv_tail(xin.data_ptr(), n, h, w, c, d_k.data_ptr(), d_b.data_ptr(),
+                                          _capi.CLIP01 if clip else 0, img.data_ptr(), U.stream()))
     ref = conv_ref64(U.split_repr(x), k, b, False)
     if clip:
         ref = np.clip(ref, 0, 1)

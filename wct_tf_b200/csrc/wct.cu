@@ -229,7 +229,7 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
     // rotation that makes the two columns orthogonal (Hestenes)
     const float zeta = (be - al) / (2.f * ga);
     const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-    const float c = rsqrtf(1.f + t * t);
+    const float c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's 2-ulp bias would shrink |column| every rotation
     const float s = c * t;
 #pragma unroll
     for (int v = 0; v < Cfg::NV; ++v) {

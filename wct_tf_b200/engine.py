@@ -43,6 +43,8 @@ class Engine(object):
         self.semantics = semantics
         self.last_info = None
         self._ws = {}
+        self.launches = 0          # kernels launched through the C-ABI (bench.py "gpu_launches")
+        self.profile = None        # optional dict: key -> [torch.cuda.Event pairs, flops, bytes]
         with torch.cuda.device(self.device):
             self._upload(weights)
 
@@ -100,6 +102,23 @@ class Engine(object):
         torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ helpers
+    def _call(self, key, nkernels, fn, *args, flops=0.0, bytes_=0.0):
+        """Run one C-ABI call; count its kernels; optionally bracket it with CUDA events on
+        the launching stream (bench.py roofline section)."""
+        self.launches += nkernels
+        if self.profile is None:
+            _capi.check(fn(*args))
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _capi.check(fn(*args))
+        e1.record()
+        rec = self.profile.setdefault(key, dict(events=[], flops=0.0, bytes=0.0, launches=0))
+        rec["events"].append((e0, e1))
+        rec["flops"] += flops
+        rec["bytes"] += bytes_
+        rec["launches"] += nkernels
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -123,7 +142,9 @@ class Engine(object):
         st = self._stream()
         lib = self.lib
         x = self._act(N, H, W, 64)
-        _capi.check(lib.wctb200_conv_head(img.data_ptr(), N, H, W, self.head_w.data_ptr(), self.head_b.data_ptr(), x.ptr, st))
+        self._call("conv_head", 1, lib.wctb200_conv_head, img.data_ptr(), N, H, W, self.head_w.data_ptr(),
+                   self.head_b.data_ptr(), x.ptr, st, flops=2.0 * 27 * 64 * N * H * W,
+                   bytes_=N * H * W * (12.0 + 64 * 4))
         kept = {}
         if "relu1_1" in taps:
             kept["relu1_1"] = x
@@ -131,15 +152,18 @@ class Engine(object):
         for op in encoder_plan(target)[1:]:
             if op.kind == "conv":
                 y = self._act(N, x.H, x.W, op.cout)
-                _capi.check(lib.wctb200_conv3x3(x.ptr, N, x.H, x.W, op.cin, self.enc_w[op.name].data_ptr(),
-                                                self.enc_b[op.name].data_ptr(), op.cout, _capi.RELU, y.ptr, st))
+                self._call("conv3x3_tc[%dx%d@%d]" % (op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr, N, x.H, x.W,
+                           op.cin, self.enc_w[op.name].data_ptr(), self.enc_b[op.name].data_ptr(), op.cout,
+                           _capi.RELU, y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
+                           bytes_=4.0 * N * x.H * x.W * (op.cin + op.cout))
                 x = y
                 relu_name = op.name.replace("conv", "relu")
                 if relu_name in taps:
                     kept[relu_name] = x
             else:
                 y = self._act(N, (x.H + 1) // 2, (x.W + 1) // 2, x.C)
-                _capi.check(lib.wctb200_maxpool2(x.ptr, N, x.H, x.W, x.C, y.ptr, st))
+                self._call("maxpool2", 1, lib.wctb200_maxpool2, x.ptr, N, x.H, x.W, x.C, y.ptr, st,
+                           bytes_=4.0 * N * x.C * (x.H * x.W + y.H * y.W))
                 x = y
         return x, kept
 
@@ -154,18 +178,21 @@ class Engine(object):
         for op in self.model.decoder_plan(level_index):
             if op.kind == "up":
                 y = self._act(N, x.H * 2, x.W * 2, x.C)
-                _capi.check(lib.wctb200_upsample2(x.ptr, N, x.H, x.W, x.C, y.ptr, st))
+                self._call("upsample2", 1, lib.wctb200_upsample2, x.ptr, N, x.H, x.W, x.C, y.ptr, st,
+                           bytes_=4.0 * N * x.C * x.H * x.W * 5)
                 x = y
             elif op.act:
                 y = self._act(N, x.H, x.W, op.cout)
-                _capi.check(lib.wctb200_conv3x3(x.ptr, N, x.H, x.W, op.cin, self.dec_w[op.name].data_ptr(),
-                                                self.dec_b[op.name].data_ptr(), op.cout, _capi.RELU, y.ptr, st))
+                self._call("conv3x3_tc[%dx%d@%d]" % (op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr, N, x.H, x.W,
+                           op.cin, self.dec_w[op.name].data_ptr(), self.dec_b[op.name].data_ptr(), op.cout,
+                           _capi.RELU, y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
+                           bytes_=4.0 * N * x.H * x.W * (op.cin + op.cout))
                 x = y
             else:
                 img = torch.empty((N, x.H, x.W, 3), dtype=torch.float32, device=self.device)
-                _capi.check(lib.wctb200_conv_tail(x.ptr, N, x.H, x.W, op.cin, self.tail_w[relu].data_ptr(),
-                                                  self.tail_b[relu].data_ptr(), _capi.CLIP01 if clip else 0,
-                                                  img.data_ptr(), st))
+                self._call("conv_tail", 1, lib.wctb200_conv_tail, x.ptr, N, x.H, x.W, op.cin, self.tail_w[relu].data_ptr(),
+                           self.tail_b[relu].data_ptr(), _capi.CLIP01 if clip else 0, img.data_ptr(), st,
+                           flops=2.0 * 9 * op.cin * 3 * N * x.H * x.W, bytes_=N * x.H * x.W * (4.0 * op.cin + 12))
                 return img
         raise AssertionError("decoder plan without a tail conv")
 
@@ -175,16 +202,20 @@ class Engine(object):
         out = self._act(content.N, content.H, content.W, content.C)
         ws = self._workspace(content.C, content.N, style.N)
         if adain:
-            _capi.check(self.lib.wctb200_adain_level(content.ptr, content.N, content.H, content.W, style.ptr, style.N,
-                                                     style.H, style.W, content.C, float(alpha), 1e-5, out.ptr,
-                                                     ws.data_ptr(), ws.numel(), st))
+            self._call("adain_level[C%d]" % content.C, 6, self.lib.wctb200_adain_level, content.ptr, content.N, content.H,
+                       content.W, style.ptr, style.N, style.H, style.W, content.C, float(alpha), 1e-5, out.ptr,
+                       ws.data_ptr(), ws.numel(), st,
+                       bytes_=4.0 * content.C * (2 * content.N * content.H * content.W + style.N * style.H * style.W))
             return out, None
         sem = SEMANTICS[self.semantics]
         kbuf = torch.empty(2 * (content.N + style.N), dtype=torch.int32, device=self.device) if want_info else None
-        _capi.check(self.lib.wctb200_wct_level(content.ptr, content.N, content.H, content.W, style.ptr, style.N,
-                                               style.H, style.W, content.C, float(alpha), sem["eps_cov"],
-                                               sem["eps_eig"], sem["thresh"], sem["readd"], out.ptr,
-                                               kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st))
+        C = content.C
+        hwc, hws = content.H * content.W, style.H * style.W
+        self._call("wct_level[C%d]" % C, 14, self.lib.wctb200_wct_level, content.ptr, content.N, content.H, content.W,
+                   style.ptr, style.N, style.H, style.W, C, float(alpha), sem["eps_cov"], sem["eps_eig"],
+                   sem["thresh"], sem["readd"], out.ptr, kbuf.data_ptr() if want_info else None, ws.data_ptr(),
+                   ws.numel(), st, flops=2.0 * C * C * (2 * content.N * hwc + style.N * hws),
+                   bytes_=4.0 * C * (2 * content.N * hwc + style.N * hws))
         return out, kbuf
 
     # ------------------------------------------------------------------ pipeline
@@ -198,8 +229,8 @@ class Engine(object):
         assert style_u8.shape[0] in (1, N)
         content = torch.empty(content_u8.shape, dtype=torch.float32, device=self.device)
         style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
-        _capi.check(lib.wctb200_image_u8_to_f32(content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st))
-        _capi.check(lib.wctb200_image_u8_to_f32(style_u8.data_ptr(), style_u8.numel(), style.data_ptr(), st))
+        self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st)
+        self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(), st)
         # model.py:70-72: one style pass emitting every target
         _, style_feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
         infos = []
@@ -224,7 +255,8 @@ class Engine(object):
     def to_u8(self, img_f32):
         """WCT.postprocess (wct.py:66-68)."""
         out = torch.empty(img_f32.shape, dtype=torch.uint8, device=self.device)
-        _capi.check(self.lib.wctb200_image_f32_to_u8(img_f32.data_ptr(), img_f32.numel(), out.data_ptr(), self._stream()))
+        self._call("f32_to_u8", 1, self.lib.wctb200_image_f32_to_u8, img_f32.data_ptr(), img_f32.numel(), out.data_ptr(),
+                   self._stream())
         return out
 
     def act_to_f32(self, act):
