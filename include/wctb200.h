@@ -134,6 +134,9 @@ WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, in
 /* Tuning hook, NOT part of the stable ABI: force the conv output-channel tile
  * (64/128/256; 0 = built-in heuristic).  Used by bench/profiling scripts. */
 WCTB200_API int wctb200_debug_set_conv_bn(int bn);
+/* 1 = one tile per CTA with all-TMEM accumulation, 2 = persistent CTAs with chunked register
+ * accumulation (default).  Returns the implementation now selected. */
+WCTB200_API int wctb200_debug_set_conv_impl(int impl);
 
 #ifdef __cplusplus
 }

@@ -124,9 +124,10 @@ def test_conv3x3_ref_kernel(case):
     assert_close(got, ref, name="conv_ref_%d_%d" % (cin, cout))
 
 
+@pytest.mark.parametrize("impl", [2, 1])
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv3x3_tensor_core(case, bn):
+def test_conv3x3_tensor_core(case, bn, impl):
     n, h, w, cin, cout, relu = case
     if bn and cout % bn:
         pytest.skip("tile does not divide Cout")
@@ -137,17 +138,23 @@ def test_conv3x3_tensor_core(case, bn):
     _capi.check(U.lib().wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
     out = U.act_alloc(n, h, w, cout)
     U.lib().wctb200_debug_set_conv_bn(bn)
+    U.lib().wctb200_debug_set_conv_impl(impl)
     try:
         _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,
                                             _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
         U.check_device()
     finally:
         U.lib().wctb200_debug_set_conv_bn(0)
+        U.lib().wctb200_debug_set_conv_impl(2)
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
-    # fp32-class tolerance; the tensor core adds into its fp32 accumulator with truncation, so
-    # the error grows ~linearly with the number of K=16 steps (measured 1.2e-5 relative at K=4608)
-    assert_close(got, ref, tol=2e-5 * max(1.0, 9 * cin / 1152.0), name="conv_tc_%d_%d_bn%d" % (cin, cout, bn), x=x, k=k, b=b)
+    # impl 1 accumulates the whole K loop in TMEM: the tensor core adds into its fp32 accumulator
+    # with truncation, so the error grows ~linearly with the number of K=16 steps (measured
+    # -1.2e-5 relative bias at K=4608).  impl 2 (default) sums short chunks in registers (RN).
+    tol = 2e-5 * max(1.0, 9 * cin / 1152.0) if impl == 1 else 1e-5
+    err = np.abs(got - ref) / (1.0 + np.abs(ref))
+    print("impl %d K=%d: max rel err %.2e, mean signed err %.2e" % (impl, 9 * cin, err.max(), (got - ref).mean()))
+    assert_close(got, ref, tol=tol, name="conv_tc%d_%d_%d_bn%d" % (impl, cin, cout, bn), x=x, k=k, b=b)
     padded = U.act_raw_padded(out, n, h, w, cout)
     assert np.isfinite(padded).all(), "halo cells left unwritten"
     assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))

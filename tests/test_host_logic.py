@@ -1,0 +1,165 @@
+"""CPU tests of the host-side logic: level-wiring bookkeeping (bit-exact against the
+reference's tables), weight IO, the C-ABI surface, frame sharding (gloo, world_size 2)."""
+import ctypes
+import itertools
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import nets
+from wct_tf_b200 import model as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_decoder_plan_matches_reference_naming():
+    for relu in M.RELU_TARGETS_ALL:
+        ours = [(op.kind, op.name, op.cout if op.kind == "conv" else None) for op in M.decoder_plan(relu)]
+        ref = [(t, n, f) for t, n, f, _ in nets.decoder_layers(relu)]
+        assert ours == ref
+    p5 = M.decoder_plan("relu5_1")
+    assert [op.name for op in p5] == ["relu5_1_%d" % i for i in range(17)]          # model.py:283-298
+    assert [(op.cin, op.cout) for op in p5 if op.kind == "conv"][-1] == (64, 3)
+    assert sum(op.kind == "up" for op in p5) == 4
+
+
+def test_encoder_plan_matches_reference_module_walk():
+    for relu in M.RELU_TARGETS_ALL:
+        ours = [op.name for op in M.encoder_plan(relu)]
+        ref = []
+        for typ, name in nets.VGG_MODULES[1:]:
+            if typ in ("conv", "pool"):
+                ref.append(name)
+            if name == relu:
+                break
+        assert ours == ref
+    assert [op.name for op in M.encoder_plan("relu1_1")] == ["conv1_1"]
+    assert sum(op.kind == "pool" for op in M.encoder_plan("relu5_1")) == 4
+
+
+@pytest.mark.parametrize("r", [1, 2, 3, 5])
+def test_level_wiring_for_every_ordered_subset(r):
+    for targets in itertools.permutations(M.RELU_TARGETS_ALL, r):
+        m = M.WCTModel(mode="test", relu_targets=list(targets))
+        assert m.deepest_target == sorted(targets)[-1]                               # model.py:60
+        assert [l.relu_target for l in m.levels] == list(targets)                   # zip order, model.py:78
+        assert [l.clip_input for l in m.levels] == [False] + [True] * (r - 1)        # model.py:86, not the first
+        assert m.style_taps == list(targets)                                         # model.py:70
+        assert [l.channels for l in m.levels] == [M.RELU_CHANNELS[t] for t in targets]
+        # the style plan reaches every tap
+        names = [op.name.replace("conv", "relu") for op in m.style_plan if op.kind == "conv"]
+        assert all(t in names for t in targets)
+
+
+def test_transform_rule_matches_tf_case():
+    # model.py:144-158
+    assert M.WCTModel.transform_for("relu5_1", True, True) == "style_swap"
+    assert M.WCTModel.transform_for("relu5_1", False, True) == "adain"
+    assert M.WCTModel.transform_for("relu5_1", False, False) == "wct"
+    assert M.WCTModel.transform_for("relu4_1", True, False) == "wct"     # swap5 only applies at relu5_1
+    assert M.WCTModel.transform_for("relu4_1", True, True) == "adain"
+    with pytest.raises(NotImplementedError):
+        M.WCTModel(mode="train")
+    with pytest.raises(ValueError):
+        M.WCTModel(mode="test", relu_targets=["relu6_1"])
+
+
+def test_weights_roundtrip_and_checkpoint_pairing(tmp_path):
+    from wct_tf_b200 import weights as W
+    w = W.make_synthetic_weights(1, relu_targets=["relu2_1", "relu1_1"])
+    assert [l["name"] for l in w["vgg"]][:3] == ["preprocess", "conv1_1", "conv1_2"]
+    assert w["vgg"][1]["weight"].shape == (64, 3, 3, 3)                              # (O,I,kH,kW), vgg_normalised.py:33
+    assert w["decoders"]["relu2_1"][0]["kernel"].shape == (3, 3, 128, 64)
+    p = str(tmp_path / "bundle.npz")
+    W.save_weights(p, w)
+    w2 = W.load_weights(p, [p, p], ["relu2_1", "relu1_1"])
+    for a, b in zip(w["decoders"]["relu2_1"], w2["decoders"]["relu2_1"]):
+        assert a["name"] == b["name"] and np.array_equal(a["kernel"], b["kernel"])
+    assert np.array_equal(w["vgg"][5]["weight"], w2["vgg"][5]["weight"])
+    with pytest.raises(Exception, match="No checkpoint found"):                        # wct.py:57-58
+        W.load_weights(p, [p, p], ["relu2_1", "relu3_1"])
+    w3 = W.make_synthetic_weights(1, relu_targets=["relu2_1", "relu1_1"])
+    assert np.array_equal(w["vgg"][7]["weight"], w3["vgg"][7]["weight"])             # deterministic in the seed
+
+
+def test_capi_exports_every_declared_symbol():
+    """The shared library loads on a CPU-only box and exports exactly what include/wctb200.h declares."""
+    from wct_tf_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "wctb200.h")).read()
+    declared = set(re.findall(r"WCTB200_API[^;]*?\b(wctb200_\w+)\s*\(", header))
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    lib = _capi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.wctb200_abi_version() == 1
+    # argument validation runs before any CUDA call
+    assert lib.wctb200_act_bytes(2, 4, 6, 64) == 2 * 2 * 6 * 8 * 64 * 2
+    assert lib.wctb200_act_bytes(1, 1, 4, 64) == 0
+    assert lib.wctb200_conv3x3(None, 1, 4, 4, 64, None, None, 64, 0, None, None) == -1
+    assert b"null" in lib.wctb200_last_error()
+    assert lib.wctb200_wct_workspace_bytes(512, 1, 1) > 6 * 512 * 512 * 4
+
+
+def test_device_string_mapping_and_no_cpu_fallback():
+    from wct_tf_b200.wct import _torch_device
+    assert _torch_device("/gpu:0") == "cuda:0" and _torch_device("/GPU:3") == "cuda:3"
+    assert _torch_device("cuda:1") == "cuda:1"
+    with pytest.raises(ValueError):
+        _torch_device("/cpu:0")
+    import torch
+    if not torch.cuda.is_available():
+        from wct_tf_b200 import _capi
+        from wct_tf_b200.engine import Engine
+        from wct_tf_b200.weights import make_synthetic_weights
+        with pytest.raises(_capi.WctB200Error):     # the product path fails loudly without a GPU
+            Engine(make_synthetic_weights(0, relu_targets=["relu1_1"]), ["relu1_1"])
+
+
+def test_shard_range_partition():
+    from wct_tf_b200.parallel import owner_of, shard_range
+    for B in [1, 3, 8, 64, 65]:
+        for G in [1, 2, 4, 8]:
+            cover = []
+            for r in range(G):
+                lo, hi = shard_range(B, G, r)
+                cover += list(range(lo, hi))
+                for i in range(lo, hi):
+                    assert owner_of(i, B, G) == r
+            assert cover == list(range(B))
+    assert [shard_range(64, 8, r) for r in (0, 7)] == [(0, 8), (56, 64)]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from wct_tf_b200.parallel import stylize_sharded
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+B = int(sys.argv[3])
+contents = (torch.arange(B, dtype=torch.uint8).view(B, 1, 1, 1) * torch.ones(B, 4, 6, 3, dtype=torch.uint8))
+styles = torch.full((B, 2, 2, 3), 7, dtype=torch.uint8)
+seen = []
+def fake_engine(c, s):           # stands in for WCT.predict_batch: marks which rank processed the frame
+    seen.append(c.shape[0])
+    return c + 100 + 10 * dist.get_rank() + s[:, :1, :1, :1] * 0
+out = stylize_sharded(fake_engine, contents, styles)
+exp = torch.stack([torch.full((4, 6, 3), i + 100 + 10 * ((i * 2) // B), dtype=torch.uint8) for i in range(B)])
+assert out.shape == (B, 4, 6, 3) and torch.equal(out, exp), (out[:, 0, 0, 0], exp[:, 0, 0, 0])
+assert sum(seen) == (B + 1 - dist.get_rank()) // 2 if B %% 2 else sum(seen) == B // 2
+dist.destroy_process_group()
+print("ok")
+""" % ROOT
+
+
+@pytest.mark.parametrize("B", [4, 5])
+def test_frame_sharding_world2_gloo(B, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + (os.getpid() % 400) + B)
+    procs = [subprocess.Popen([sys.executable, str(script), port, str(r), str(B)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)

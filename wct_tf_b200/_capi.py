@@ -37,6 +37,7 @@ SIGNATURES = {
     "wctb200_adain_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wctb200_debug_set_conv_bn": (_i, [_i]),
+    "wctb200_debug_set_conv_impl": (_i, [_i]),
 }
 
 _lib = None

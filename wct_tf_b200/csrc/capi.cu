@@ -52,6 +52,7 @@ int launch_adain_level(const __half*, int, int, int, const __half*, int, int, in
 int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
 int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
+extern int g_conv_impl;
 
 static bool geom_ok(int N, int H, int W, int C) { return N >= 1 && H >= 2 && W >= 2 && C >= 8 && C % 8 == 0; }
 
@@ -182,6 +183,10 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
 int wctb200_debug_set_conv_bn(int bn) {
     g_conv_bn_override = bn;
     return 0;
+}
+int wctb200_debug_set_conv_impl(int impl) {
+    if (impl == 1 || impl == 2) g_conv_impl = impl;
+    return g_conv_impl;
 }
 
 }  // extern "C"

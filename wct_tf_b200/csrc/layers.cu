@@ -123,7 +123,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (
 __global__ void __launch_bounds__(256)
 k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
             const float* __restrict__ b, __half* __restrict__ out) {
-    __shared__ float sw[27 * 64];
+    __shared__ __align__(16) float sw[27 * 64];
     __shared__ float sb[64];
     for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
@@ -150,8 +150,12 @@ k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __r
                 for (int ci = 0; ci < 3; ++ci) {
                     const float v = __ldg(px + ci);
                     const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * 64 + c0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                    acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                    acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                    acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                    acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
                 }
             }
         }
@@ -170,9 +174,13 @@ k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __r
 __global__ void __launch_bounds__(256)
 k_conv_tail(const __half* __restrict__ in, ActGeom gi, const float* __restrict__ w, const float* __restrict__ b,
             int flags, float* __restrict__ img) {
-    extern __shared__ float swt[];   // [9*Cin][3]
+    extern __shared__ __align__(16) float swt[];   // [9][Cin/8][3][8]: (tap, 8-channel group, output, channel)
     const int K = 9 * gi.C;
-    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) swt[i] = w[i];
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) {
+        const int o = i % 3, k = i / 3;            // w is [9*Cin][3], k = tap*Cin + c
+        const int tap = k / gi.C, c = k - tap * gi.C;
+        swt[((tap * (gi.C / 8) + c / 8) * 3 + o) * 8 + (c & 7)] = w[i];
+    }
     __syncthreads();
     const int cgs = gi.C / 8;                      // 8-channel groups per pixel
     const long long npix = (long long)gi.N * gi.H * gi.W;
@@ -195,13 +203,14 @@ k_conv_tail(const __half* __restrict__ in, ActGeom gi, const float* __restrict__
                     for (int cgi = sub; cgi < cgs; cgi += 8) {
                         float v[8];
                         load8(in, gi, pos, cgi * 8, v);
-                        const float* wr = swt + ((ky * 3 + kx) * gi.C + cgi * 8) * 3;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            a0 = fmaf(v[j], wr[j * 3 + 0], a0);
-                            a1 = fmaf(v[j], wr[j * 3 + 1], a1);
-                            a2 = fmaf(v[j], wr[j * 3 + 2], a2);
-                        }
+                        const float4* wr = reinterpret_cast<const float4*>(swt + ((ky * 3 + kx) * cgs + cgi) * 24);
+                        const float4 p0 = wr[0], p1 = wr[1], q0 = wr[2], q1 = wr[3], r0 = wr[4], r1 = wr[5];
+                        a0 = fmaf(v[0], p0.x, a0); a0 = fmaf(v[1], p0.y, a0); a0 = fmaf(v[2], p0.z, a0); a0 = fmaf(v[3], p0.w, a0);
+                        a0 = fmaf(v[4], p1.x, a0); a0 = fmaf(v[5], p1.y, a0); a0 = fmaf(v[6], p1.z, a0); a0 = fmaf(v[7], p1.w, a0);
+                        a1 = fmaf(v[0], q0.x, a1); a1 = fmaf(v[1], q0.y, a1); a1 = fmaf(v[2], q0.z, a1); a1 = fmaf(v[3], q0.w, a1);
+                        a1 = fmaf(v[4], q1.x, a1); a1 = fmaf(v[5], q1.y, a1); a1 = fmaf(v[6], q1.z, a1); a1 = fmaf(v[7], q1.w, a1);
+                        a2 = fmaf(v[0], r0.x, a2); a2 = fmaf(v[1], r0.y, a2); a2 = fmaf(v[2], r0.z, a2); a2 = fmaf(v[3], r0.w, a2);
+                        a2 = fmaf(v[4], r1.x, a2); a2 = fmaf(v[5], r1.y, a2); a2 = fmaf(v[6], r1.z, a2); a2 = fmaf(v[7], r1.w, a2);
                     }
                 }
         }

@@ -252,17 +252,76 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
     return ratio;
 }
 
+// ---- register-blocked cross-pair rotation: operands live in registers, norms are cached ----
+template <int EPL>
+__device__ __forceinline__ void rot_regs(float (&x)[EPL], float (&y)[EPL], float& a, float& b, float tol, float& wmax) {
+    float g = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) g = fmaf(x[i], y[i], g);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+    const float nrm = sqrtf(a) * sqrtf(b);
+    if (!(nrm > 0.f)) return;
+    const float ratio = fabsf(g) / nrm;
+    wmax = fmaxf(wmax, ratio);
+    if (ratio <= tol) return;
+    const float zeta = (b - a) / (2.f * g);
+    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+    const float c = 1.f / sqrtf(1.f + t * t);
+    const float s = c * t;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+        const float xv = x[i], yv = y[i];
+        x[i] = c * xv - s * yv;
+        y[i] = s * xv + c * yv;
+    }
+    a = fmaxf(a - t * g, 0.f);      // |x'|^2 = |x|^2 - t*g ,  |y'|^2 = |y|^2 + t*g
+    b = fmaxf(b + t * g, 0.f);
+}
+
 template <int NN>
-__global__ void __launch_bounds__(1024, 1)
+__device__ __forceinline__ void load_col(const float* __restrict__ c, int lane, float (&r)[NN / 32]) {
+    using Cfg = JacobiCfg<NN>;
+#pragma unroll
+    for (int v = 0; v < Cfg::NV; ++v) {
+        const int off = (v * 32 + lane) * Cfg::VEC;
+        if (Cfg::VEC == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(c + off);
+            r[v * 4] = a.x; r[v * 4 + 1] = a.y; r[v * 4 + 2] = a.z; r[v * 4 + 3] = a.w;
+        } else {
+            const float2 a = *reinterpret_cast<const float2*>(c + off);
+            r[v * 2] = a.x; r[v * 2 + 1] = a.y;
+        }
+    }
+}
+template <int NN>
+__device__ __forceinline__ void store_col(float* __restrict__ c, int lane, const float (&r)[NN / 32]) {
+    using Cfg = JacobiCfg<NN>;
+#pragma unroll
+    for (int v = 0; v < Cfg::NV; ++v) {
+        const int off = (v * 32 + lane) * Cfg::VEC;
+        if (Cfg::VEC == 4) *reinterpret_cast<float4*>(c + off) = make_float4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+        else *reinterpret_cast<float2*>(c + off) = make_float2(r[v * 2], r[v * 2 + 1]);
+    }
+}
+
+// 512 threads = 16 warps.  Cross phase: warp w keeps top columns 2w,2w+1 in REGISTERS for the
+// whole round and walks over the 16 bottom column pairs; each bottom pair is loaded/stored once
+// per 4 rotations (shared-memory traffic /4 vs one pair per warp), column norms are cached and
+// updated analytically, so a rotation costs one dot product instead of three.
+template <int NN>
+__global__ void __launch_bounds__(512, 1)
 k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol) {
     using Cfg = JacobiCfg<NN>;
     constexpr int P = Cfg::P;
-    constexpr int NB = 2 * P;          // column blocks of 32
-    constexpr int M = NB - 1;          // tournament rounds per sweep
+    constexpr int NB = 2 * P;
+    constexpr int M = NB - 1;
+    constexpr int EPL = NN / 32;
     extern __shared__ __align__(16) float cols[];          // [64][NN]
+    __shared__ float nrm[64];
     __shared__ unsigned int s_max;
 
-    const int rank = blockIdx.x;       // cluster rank (cluster spans blockIdx.x = 0..P-1)
+    const int rank = blockIdx.x;
     const int prob = blockIdx.y;
     float* G = Gall + (long long)prob * NN * NN;
     float* cw = conv_ws + (long long)prob * 16;
@@ -278,39 +337,73 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             if (P == 1) { bt = 0; bb = 1; }
             else if (rank == 0) { bt = NB - 1; bb = r; }
             else { bt = (r + rank) % M; bb = (r - rank + M) % M; }
-            // ---- stage the two column blocks (P==1: only once, they never move) ----
             if (P > 1 || sweep == 0) {
                 const float4* s0 = reinterpret_cast<const float4*>(G + (long long)bt * 32 * NN);
                 const float4* s1 = reinterpret_cast<const float4*>(G + (long long)bb * 32 * NN);
                 float4* d = reinterpret_cast<float4*>(cols);
-                for (int i = threadIdx.x; i < 32 * NN / 4; i += 1024) {
+                for (int i = threadIdx.x; i < 32 * NN / 4; i += 512) {
                     d[i] = __ldcg(s0 + i);                 // L2 (peers of the cluster wrote these columns)
                     d[32 * NN / 4 + i] = __ldcg(s1 + i);
                 }
             }
             __syncthreads();
-            // ---- pairs inside each block: once per sweep (round 0); top block on warps 0-15, bottom on 16-31
+            // ---- pairs inside each 32-column block: once per sweep, plain one-pair-per-warp steps
             if (r == 0) {
-                const int half = warp >> 4, w = warp & 15;
-                float* base = cols + half * 32 * NN;
-                for (int s = 0; s < 31; ++s) {
-                    int a, b;
-                    if (w == 0) { a = 31; b = s; }
-                    else { a = (s + w) % 31; b = (s - w + 31) % 31; }
-                    wmax = fmaxf(wmax, jacobi_pair<NN>(base + a * NN, base + b * NN, lane, tol));
-                    __syncthreads();
+                for (int half = 0; half < 2; ++half) {
+                    float* base = cols + half * 32 * NN;
+                    for (int s = 0; s < 31; ++s) {
+                        int a, b;
+                        if (warp == 0) { a = 31; b = s; }
+                        else { a = (s + warp) % 31; b = (s - warp + 31) % 31; }
+                        wmax = fmaxf(wmax, jacobi_pair<NN>(base + a * NN, base + b * NN, lane, tol));
+                        __syncthreads();
+                    }
                 }
             }
-            // ---- cross pairs: step s pairs top[w] with bottom[(w+s)%32]
-            for (int s = 0; s < 32; ++s) {
-                wmax = fmaxf(wmax, jacobi_pair<NN>(cols + warp * NN, cols + (32 + ((warp + s) & 31)) * NN, lane, tol));
-                __syncthreads();
+            // ---- column norms (fresh every round: the cached values never drift far)
+            for (int c = warp * 4; c < warp * 4 + 4; ++c) {
+                float v[EPL];
+                load_col<NN>(cols + c * NN, lane, v);
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) ss = fmaf(v[i], v[i], ss);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) nrm[c] = ss;
             }
+            __syncthreads();
+            // ---- cross pairs: 16 steps x 4 rotations per warp
+            {
+                float x0[EPL], x1[EPL];
+                load_col<NN>(cols + (2 * warp) * NN, lane, x0);
+                load_col<NN>(cols + (2 * warp + 1) * NN, lane, x1);
+                float a0 = nrm[2 * warp], a1 = nrm[2 * warp + 1];
+                for (int s = 0; s < 16; ++s) {
+                    const int j = (warp + s) & 15;
+                    float* cy0 = cols + (32 + 2 * j) * NN;
+                    float* cy1 = cy0 + NN;
+                    float y0[EPL], y1[EPL];
+                    load_col<NN>(cy0, lane, y0);
+                    load_col<NN>(cy1, lane, y1);
+                    float b0 = nrm[32 + 2 * j], b1 = nrm[32 + 2 * j + 1];
+                    rot_regs<EPL>(x0, y0, a0, b0, tol, wmax);
+                    rot_regs<EPL>(x1, y1, a1, b1, tol, wmax);
+                    rot_regs<EPL>(x0, y1, a0, b1, tol, wmax);
+                    rot_regs<EPL>(x1, y0, a1, b0, tol, wmax);
+                    store_col<NN>(cy0, lane, y0);
+                    store_col<NN>(cy1, lane, y1);
+                    if (lane == 0) { nrm[32 + 2 * j] = b0; nrm[32 + 2 * j + 1] = b1; }
+                    __syncthreads();
+                }
+                store_col<NN>(cols + (2 * warp) * NN, lane, x0);
+                store_col<NN>(cols + (2 * warp + 1) * NN, lane, x1);
+            }
+            __syncthreads();
             if (P > 1) {
                 float4* d0 = reinterpret_cast<float4*>(G + (long long)bt * 32 * NN);
                 float4* d1 = reinterpret_cast<float4*>(G + (long long)bb * 32 * NN);
                 const float4* sc = reinterpret_cast<const float4*>(cols);
-                for (int i = threadIdx.x; i < 32 * NN / 4; i += 1024) {
+                for (int i = threadIdx.x; i < 32 * NN / 4; i += 512) {
                     d0[i] = sc[i];
                     d1[i] = sc[32 * NN / 4 + i];
                 }
@@ -338,7 +431,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     if (P == 1) {
         float4* d = reinterpret_cast<float4*>(G);
         const float4* sc = reinterpret_cast<const float4*>(cols);
-        for (int i = threadIdx.x; i < 64 * NN / 4; i += 1024) d[i] = sc[i];
+        for (int i = threadIdx.x; i < 64 * NN / 4; i += 512) d[i] = sc[i];
     }
     if (rank == 0 && threadIdx.x == 0 && sweeps_out) sweeps_out[prob] = sweep;
 }
@@ -540,7 +633,7 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
     const int max_sweeps = 40;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(C / 64), (unsigned)count, 1);
-    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
