@@ -1,0 +1,40 @@
+"""CLI surface: the reference's flags (stylize.py:16-37) are all accepted with the same
+defaults; image helpers behave like utils.py."""
+import numpy as np
+
+import stylize
+from wct_tf_b200 import imageio as io
+
+
+def test_reference_flags_and_defaults():
+    p = stylize.build_parser()
+    a = p.parse_args(["--relu-targets", "relu5_1", "relu1_1", "--checkpoints", "a", "b"])
+    assert a.relu_targets == ["relu5_1", "relu1_1"] and a.checkpoints == ["a", "b"]
+    assert (a.alpha, a.passes, a.device, a.adain, a.keep_colors, a.concat, a.swap5) == (1, 1, "/gpu:0", False, False, False, False)
+    assert (a.style_size, a.crop_size, a.content_size, a.random) == (0, 0, 0, 0)
+    assert (a.ss_alpha, a.ss_patch_size, a.ss_stride) == (0.6, 3, 1)
+    b = p.parse_args(["--relu-targets", "relu1_1", "--alpha", "0.8", "--adain", "--style-size", "512", "-r", "2"])
+    assert b.alpha == 0.8 and b.adain and b.style_size == 512 and b.random == 2
+
+
+def test_resize_and_crop_semantics():
+    img = np.random.default_rng(0).integers(0, 256, (40, 60, 3), dtype=np.uint8)
+    r = io.resize_to(img, 20)
+    assert r.shape == (20, 30, 3)                     # short side -> 20 (utils.py:55-67)
+    r2 = io.resize_to(np.transpose(img, (1, 0, 2)), 20)
+    assert r2.shape == (30, 20, 3)
+    c = io.center_crop(img, 32)
+    assert c.shape == (32, 32, 3) and np.array_equal(c, img[4:36, 14:46])
+    up = io.center_crop(img[:10, :10], 16)            # too small -> upscale first (utils.py:32-34)
+    assert up.shape == (16, 16, 3)
+
+
+def test_coral_matches_target_statistics():
+    rng = np.random.default_rng(1)
+    src = rng.random((16, 16, 3)) * 0.5
+    tgt = rng.random((12, 20, 3)) * np.array([0.2, 0.9, 0.4]) + 0.1
+    out = io.coral(src, tgt)
+    assert out.shape == src.shape
+    assert np.allclose(out.reshape(-1, 3).mean(0), tgt.reshape(-1, 3).mean(0), atol=1e-6)
+    u8 = io.preserve_colors_np(np.uint8(src * 255), np.uint8(tgt * 255))
+    assert u8.dtype == np.uint8 and u8.shape == src.shape

@@ -39,7 +39,7 @@ def test_jacobi_eigh_matches_lapack(n):
     for i in range(count):
         w = np.linalg.eigvalsh(a[i].astype(np.float64))[::-1]
         got = np.sort(sg[i])[::-1]
-        assert np.abs(got - np.abs(w)).max() <= 3e-5 * np.abs(w).max(), (i, np.abs(got - np.abs(w)).max())
+        assert np.abs(got - np.abs(w)).max() <= 4e-5 * np.abs(w).max(), (i, np.abs(got - np.abs(w)).max())
         # reconstruct A = sum_i u_i u_i^T sigma_i = G diag(1/sigma) G^T over the non-null columns
         keep = sg[i] > 1e-6 * sg[i].max()
         gi = g[i][keep]                       # rows = columns of G

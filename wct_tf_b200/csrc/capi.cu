@@ -54,7 +54,11 @@ int launch_eig_post(const float*, int, int, float, float, int, float*, float*, i
 extern int g_conv_bn_override;
 extern int g_conv_impl;
 
-static bool geom_ok(int N, int H, int W, int C) { return N >= 1 && H >= 2 && W >= 2 && C >= 8 && C % 8 == 0; }
+// kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
+static bool geom_ok(int N, int H, int W, int C) {
+    return N >= 1 && H >= 2 && W >= 2 && C >= 8 && C % 8 == 0 &&
+           (long long)N * (2ll * H + 2) * (2ll * W + 2) * (C / 8) < (1ll << 32) && (long long)H * W < (1ll << 31);
+}
 
 }  // namespace wctb
 
@@ -133,7 +137,7 @@ int wctb200_conv3x3_ref(const void* act_in, int N, int H, int W, int Cin, const 
     return launch_conv3x3_ref(HCP(act_in), ActGeom(N, H, W, Cin), w_hwio, bias, Cout, flags, HP(act_out), ST(stream));
 }
 int wctb200_conv_head(const float* img, int N, int H, int W, const float* w, const float* b, void* act_out, void* stream) {
-    WCTB_REQUIRE(img && w && b && act_out && N >= 1 && H >= 2 && W >= 2, "conv_head: bad arguments");
+    WCTB_REQUIRE(img && w && b && act_out && geom_ok(N, H, W, 64), "conv_head: bad arguments");
     return launch_conv_head(img, N, H, W, w, b, HP(act_out), ST(stream));
 }
 int wctb200_conv_tail(const void* act_in, int N, int H, int W, int Cin, const float* w, const float* b, int flags,
@@ -158,12 +162,14 @@ int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc, const void* s
                       float alpha, float eps_cov, float eps_eig, float thresh, int readd_content_mean, void* out,
                       int32_t* k_out, void* ws, size_t ws_bytes, void* stream) {
     WCTB_REQUIRE(content && style && out && ws, "wct_level: null pointer");
+    WCTB_REQUIRE(geom_ok(Nc, Hc, Wc, C) && geom_ok(Ns, Hs, Ws, C), "wct_level: bad geometry");
     return launch_wct_level(HCP(content), Nc, Hc, Wc, HCP(style), Ns, Hs, Ws, C, alpha, eps_cov, eps_eig, thresh,
                             readd_content_mean, HP(out), k_out, ws, ws_bytes, ST(stream));
 }
 int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc, const void* style, int Ns, int Hs, int Ws, int C,
                         float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream) {
     WCTB_REQUIRE(content && style && out && ws, "adain_level: null pointer");
+    WCTB_REQUIRE(geom_ok(Nc, Hc, Wc, C) && geom_ok(Ns, Hs, Ws, C), "adain_level: bad geometry");
     return launch_adain_level(HCP(content), Nc, Hc, Wc, HCP(style), Ns, Hs, Ws, C, alpha, eps, HP(out), ws, ws_bytes,
                               ST(stream));
 }

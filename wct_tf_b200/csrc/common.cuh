@@ -103,18 +103,25 @@ __device__ __forceinline__ int halo_rows(int y, int H, int* rows) {
 }
 
 // store one 8-channel group (hi+lo) of pixel (n,y,x) to every padded cell that holds it
+// (fully unrolled with predicates: no local-memory index arrays)
 __device__ __forceinline__ void store8_with_halo(__half* __restrict__ act, const ActGeom& g, int n, int y, int x,
                                                  int c0, const Half8& hi, const Half8& lo) {
-    int rows[3], cols[3];
-    int nr = halo_rows(y, g.H, rows);
-    int nc = halo_rows(x, g.W, cols);
-    for (int a = 0; a < nr; ++a)
-        for (int b = 0; b < nc; ++b) {
-            long long pos = ((long long)n * g.Hp + rows[a]) * g.Wp + cols[b];
-            long long off = pos * g.C + c0;
+    const int r1 = (y == 1) ? 0 : -1, r2 = (y == g.H - 2) ? g.H + 1 : -1;
+    const int q1 = (x == 1) ? 0 : -1, q2 = (x == g.W - 2) ? g.W + 1 : -1;
+    const long long img = (long long)n * g.Hp;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int ra = a == 0 ? y + 1 : (a == 1 ? r1 : r2);
+        if (ra < 0) continue;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int cb = b == 0 ? x + 1 : (b == 1 ? q1 : q2);
+            if (cb < 0) continue;
+            const long long off = ((img + ra) * g.Wp + cb) * g.C + c0;
             *reinterpret_cast<Half8*>(act + off) = hi;
             *reinterpret_cast<Half8*>(act + g.plane + off) = lo;
         }
+    }
 }
 
 __device__ __forceinline__ void load8(const __half* __restrict__ act, const ActGeom& g, long long pos, int c0,

@@ -28,12 +28,13 @@ __global__ void k_f32_to_u8(const float* __restrict__ in, size_t n, uint8_t* __r
 __global__ void k_act_from_f32(const float* __restrict__ in, ActGeom g, __half* __restrict__ act) {
     const int cg = g.C / 8;
     const long long total = (long long)g.N * g.H * g.W * cg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cg) * 8;
-        long long pix = i / cg;
-        const int x = (int)(pix % g.W); pix /= g.W;
-        const int y = (int)(pix % g.H);
-        const int n = (int)(pix / g.H);
+    // 32-bit index arithmetic (launcher guarantees total < 2^32): 64-bit div/mod costs ~100 instructions each
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cg) * 8;
+        unsigned pix = i / (unsigned)cg;
+        const int x = (int)(pix % (unsigned)g.W); pix /= (unsigned)g.W;
+        const int y = (int)(pix % (unsigned)g.H);
+        const int n = (int)(pix / (unsigned)g.H);
         const float* src = in + (((long long)n * g.H + y) * g.W + x) * g.C + c0;
         float v[8];
         *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(src);
@@ -46,12 +47,13 @@ __global__ void k_act_from_f32(const float* __restrict__ in, ActGeom g, __half* 
 __global__ void k_act_to_f32(const __half* __restrict__ act, ActGeom g, float* __restrict__ out) {
     const int cg = g.C / 8;
     const long long total = (long long)g.N * g.H * g.W * cg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cg) * 8;
-        long long pix = i / cg;
-        const int x = (int)(pix % g.W); pix /= g.W;
-        const int y = (int)(pix % g.H);
-        const int n = (int)(pix / g.H);
+    // 32-bit index arithmetic (launcher guarantees total < 2^32): 64-bit div/mod costs ~100 instructions each
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cg) * 8;
+        unsigned pix = i / (unsigned)cg;
+        const int x = (int)(pix % (unsigned)g.W); pix /= (unsigned)g.W;
+        const int y = (int)(pix % (unsigned)g.H);
+        const int n = (int)(pix / (unsigned)g.H);
         const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
         float v[8];
         load8(act, g, pos, c0, v);
@@ -130,12 +132,12 @@ k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __r
     __syncthreads();
     const ActGeom go(N, H, W, 64);
     const long long total = (long long)N * H * W * 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i & 7) * 8;
-        long long pix = i >> 3;
-        const int x = (int)(pix % W); pix /= W;
-        const int y = (int)(pix % H);
-        const int n = (int)(pix / H);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i & 7u) * 8;
+        unsigned pix = i >> 3;
+        const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
+        const int y = (int)(pix % (unsigned)H);
+        const int n = (int)(pix / (unsigned)H);
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
@@ -191,10 +193,10 @@ k_conv_tail(const __half* __restrict__ in, ActGeom gi, const float* __restrict__
          wbase += ((long long)gridDim.x * blockDim.x) >> 3) {
         const long long pix = wbase + (lane >> 3);
         const bool ok = pix < npix;
-        long long t = ok ? pix : 0;
-        const int x = (int)(t % gi.W); t /= gi.W;
-        const int y = (int)(t % gi.H);
-        const int n = (int)(t / gi.H);
+        unsigned t = ok ? (unsigned)pix : 0u;
+        const int x = (int)(t % (unsigned)gi.W); t /= (unsigned)gi.W;
+        const int y = (int)(t % (unsigned)gi.H);
+        const int n = (int)(t / (unsigned)gi.H);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
         if (ok) {
             for (int ky = 0; ky < 3; ++ky)
@@ -240,12 +242,13 @@ __global__ void k_maxpool2(const __half* __restrict__ in, ActGeom gi, __half* __
     const ActGeom go(gi.N, (gi.H + 1) / 2, (gi.W + 1) / 2, gi.C);
     const int cg = gi.C / 8;
     const long long total = (long long)go.N * go.H * go.W * cg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cg) * 8;
-        long long pix = i / cg;
-        const int x = (int)(pix % go.W); pix /= go.W;
-        const int y = (int)(pix % go.H);
-        const int n = (int)(pix / go.H);
+    // 32-bit index arithmetic (launcher guarantees total < 2^32): 64-bit div/mod costs ~100 instructions each
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cg) * 8;
+        unsigned pix = i / (unsigned)cg;
+        const int x = (int)(pix % (unsigned)go.W); pix /= (unsigned)go.W;
+        const int y = (int)(pix % (unsigned)go.H);
+        const int n = (int)(pix / (unsigned)go.H);
         float m[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = -3.0e38f;
@@ -271,12 +274,13 @@ __global__ void k_upsample2(const __half* __restrict__ in, ActGeom gi, __half* _
     const ActGeom go(gi.N, gi.H * 2, gi.W * 2, gi.C);
     const int cg = gi.C / 8;
     const long long total = (long long)go.N * go.H * go.W * cg;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cg) * 8;
-        long long pix = i / cg;
-        const int x = (int)(pix % go.W); pix /= go.W;
-        const int y = (int)(pix % go.H);
-        const int n = (int)(pix / go.H);
+    // 32-bit index arithmetic (launcher guarantees total < 2^32): 64-bit div/mod costs ~100 instructions each
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cg) * 8;
+        unsigned pix = i / (unsigned)cg;
+        const int x = (int)(pix % (unsigned)go.W); pix /= (unsigned)go.W;
+        const int y = (int)(pix % (unsigned)go.H);
+        const int n = (int)(pix / (unsigned)go.H);
         const long long off = (((long long)n * gi.Hp + (y >> 1) + 1) * gi.Wp + (x >> 1) + 1) * gi.C + c0;
         const Half8 hi = *reinterpret_cast<const Half8*>(in + off);
         const Half8 lo = *reinterpret_cast<const Half8*>(in + gi.plane + off);

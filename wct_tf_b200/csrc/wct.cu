@@ -37,7 +37,7 @@ k_chan_sums(const __half* __restrict__ act, ActGeom g, int chunk_pix, double* __
     for (int j = 0; j < 8; ++j) { s[j] = 0.f; s2[j] = 0.f; }
     if (rl < rows) {
         for (long long q = q0 + rl; q < q1; q += rows) {
-            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+            const int y = (int)((unsigned)q / (unsigned)g.W), x = (int)((unsigned)q - (unsigned)y * (unsigned)g.W);
             float v[8];
             load8(act, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, grp * 8, v);
 #pragma unroll
@@ -115,7 +115,7 @@ k_cov_partial(const __half* __restrict__ act, ActGeom g, const float* __restrict
         const long long q = qs + lp;
         float vi[8], vj[8];
         if (q < q1) {
-            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+            const int y = (int)((unsigned)q / (unsigned)g.W), x = (int)((unsigned)q - (unsigned)y * (unsigned)g.W);
             const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
             load8(act, g, pos, bi * 64 + lg * 8, vi);
 #pragma unroll
@@ -255,28 +255,53 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
 // ---- register-blocked cross-pair rotation: operands live in registers, norms are cached ----
 template <int EPL>
 __device__ __forceinline__ void rot_regs(float (&x)[EPL], float (&y)[EPL], float& a, float& b, float tol, float& wmax) {
-    float g = 0.f;
+    // dot product with 4 independent chains (ILP), then a butterfly reduction
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    if (EPL >= 4) {
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) g = fmaf(x[i], y[i], g);
+        for (int i = 0; i < EPL; i += 4) {
+            g0 = fmaf(x[i], y[i], g0);
+            g1 = fmaf(x[i + 1], y[i + 1], g1);
+            g2 = fmaf(x[i + 2], y[i + 2], g2);
+            g3 = fmaf(x[i + 3], y[i + 3], g3);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) g0 = fmaf(x[i], y[i], g0);
+    }
+    float g = (g0 + g1) + (g2 + g3);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-    const float nrm = sqrtf(a) * sqrtf(b);
-    if (!(nrm > 0.f)) return;
-    const float ratio = fabsf(g) / nrm;
+    const float ab = a * b;
+    if (!(ab > 0.f)) return;
+    const float ratio = fabsf(g) * rsqrtf(ab);
     wmax = fmaxf(wmax, ratio);
     if (ratio <= tol) return;
-    const float zeta = (b - a) / (2.f * g);
-    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-    const float c = 1.f / sqrtf(1.f + t * t);
+    // Rotation angle: approximate (MUFU) arithmetic is fine for t -- any t yields an exact
+    // rotation as long as (c,s) is orthonormal; a slightly-off t only leaves a residual for
+    // the next sweep.  c gets one Newton step so c^2(1+t^2) = 1 to ~1 ulp WITHOUT bias
+    // (a biased c shrinks the column norms, i.e. the eigenvalues, at every rotation).
+    const float zeta = __fdividef(b - a, 2.f * g);
+    const float az = fabsf(zeta);
+    float t;
+    if (az > 1e8f) {
+        t = __fdividef(0.5f, zeta);                       // asymptote; avoids zeta^2 overflow
+    } else {
+        const float h2 = fmaf(zeta, zeta, 1.f);
+        t = __fdividef(copysignf(1.f, zeta), az + h2 * rsqrtf(h2));
+    }
+    const float h = fmaf(t, t, 1.f);
+    float c = rsqrtf(h);
+    c = c * fmaf(-0.5f * h, c * c, 1.5f);
     const float s = c * t;
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
         const float xv = x[i], yv = y[i];
-        x[i] = c * xv - s * yv;
-        y[i] = s * xv + c * yv;
+        x[i] = fmaf(c, xv, -s * yv);
+        y[i] = fmaf(s, xv, c * yv);
     }
-    a = fmaxf(a - t * g, 0.f);      // |x'|^2 = |x|^2 - t*g ,  |y'|^2 = |y|^2 + t*g
-    b = fmaxf(b + t * g, 0.f);
+    a = fmaxf(fmaf(-t, g, a), 0.f);      // |x'|^2 = |x|^2 - t*g ,  |y'|^2 = |y|^2 + t*g
+    b = fmaxf(fmaf(t, g, b), 0.f);
 }
 
 template <int NN>
@@ -563,12 +588,12 @@ __global__ void k_affine_apply(const __half* __restrict__ in, ActGeom g, const f
                                const float* __restrict__ shift, __half* __restrict__ out) {
     const int cgs = g.C / 8;
     const long long total = (long long)g.N * g.H * g.W * cgs;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cgs) * 8;
-        long long pix = i / cgs;
-        const int x = (int)(pix % g.W); pix /= g.W;
-        const int y = (int)(pix % g.H);
-        const int n = (int)(pix / g.H);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cgs) * 8;
+        unsigned pix = i / (unsigned)cgs;
+        const int x = (int)(pix % (unsigned)g.W); pix /= (unsigned)g.W;
+        const int y = (int)(pix % (unsigned)g.H);
+        const int n = (int)(pix / (unsigned)g.H);
         float v[8];
         load8(in, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, c0, v);
         const float* sc = scale + (long long)n * g.C + c0;
