@@ -122,115 +122,169 @@ __global__ void k_conv3x3_ref(const __half* __restrict__ in, ActGeom gi, const f
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
+// one thread = 4 horizontally adjacent pixels x 8 output channels: each conflict-free LDS.128
+// pair of weights feeds 32 FMAs (the first version, 1 pixel per thread, was shared-memory bound:
+// ncu short_scoreboard + mio_throttle, 2-way bank conflicts on the 32-byte-strided weight reads)
 __global__ void __launch_bounds__(256)
 k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
             const float* __restrict__ b, __half* __restrict__ out) {
+    // weights re-laid out [k][half][group][4] (channel c = 8*group + 4*half + j): the 8 lanes of a
+    // quarter-warp read 8 consecutive 16-byte words
     __shared__ __align__(16) float sw[27 * 64];
     __shared__ float sb[64];
-    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+        const int k = i >> 6, c = i & 63;
+        sw[(k * 2 + ((c >> 2) & 1)) * 32 + (c >> 3) * 4 + (c & 3)] = w[i];
+    }
     if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
     __syncthreads();
     const ActGeom go(N, H, W, 64);
-    const long long total = (long long)N * H * W * 8;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
-        const int c0 = (int)(i & 7u) * 8;
-        unsigned pix = i >> 3;
-        const int x = (int)(pix % (unsigned)W); pix /= (unsigned)W;
-        const int y = (int)(pix % (unsigned)H);
-        const int n = (int)(pix / (unsigned)H);
-        float acc[8];
+    const unsigned segs = (unsigned)(W + 3) / 4u;
+    const unsigned total = (unsigned)N * (unsigned)H * segs * 8u;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int g = (int)(i & 7u);
+        unsigned t = i >> 3;
+        const int xs = (int)(t % segs) * 4; t /= segs;
+        const int y = (int)(t % (unsigned)H);
+        const int n = (int)(t / (unsigned)H);
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = sb[g * 8 + j];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int yy = reflect_idx(y + ky - 1, H);
+            const float* row = img + ((long long)n * H + yy) * W * 3;
+            float in[6][3];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int xx = reflect_idx(x + kx - 1, W);
-                const float* px = img + (((long long)n * H + yy) * W + xx) * 3;
+            for (int j = 0; j < 6; ++j) {
+                int xx = reflect_idx(xs + j - 1, W);
+                xx = min(max(xx, 0), W - 1);                 // columns past the ragged right edge: any valid address
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) in[j][ci] = __ldg(row + xx * 3 + ci);
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
-                    const float v = __ldg(px + ci);
-                    const float* wr = sw + ((ky * 3 + kx) * 3 + ci) * 64 + c0;
-                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-                    acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-                    acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-                    acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-                    acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                    const int k = (ky * 3 + kx) * 3 + ci;
+                    const float4 w0 = *reinterpret_cast<const float4*>(sw + (k * 2) * 32 + g * 4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sw + (k * 2 + 1) * 32 + g * 4);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float v = in[p + kx][ci];
+                        acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+                        acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+                        acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+                        acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                    }
                 }
-            }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-        Half8 hi, lo;
-        split8(acc, hi, lo);
-        store8_with_halo(out, go, n, y, x, c0, hi, lo);
+        for (int p = 0; p < 4; ++p) {
+            if (xs + p < W) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[p][j], 0.f);
+                Half8 hi, lo;
+                split8(v, hi, lo);
+                store8_with_halo(out, go, n, y, xs + p, g * 8, hi, lo);
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
 // decoder tail: Conv2DReflect Cin->3, no activation (model.py:297-298) [+ clip, model.py:86]
-//   8 lanes cooperate on one pixel (each owns Cin/8 channels... in 8-wide groups), shuffle-reduce.
+//   8 lanes cooperate on 4 horizontally adjacent pixels (lane = 8-channel group, looped for
+//   Cin > 64): each activation vector is loaded/merged once and used by 3 horizontal taps,
+//   each weight LDS.128 (conflict-free layout) feeds 16 FMAs; 3-step shuffle reduction.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_conv_tail(const __half* __restrict__ in, ActGeom gi, const float* __restrict__ w, const float* __restrict__ b,
             int flags, float* __restrict__ img) {
-    extern __shared__ __align__(16) float swt[];   // [9][Cin/8][3][8]: (tap, 8-channel group, output, channel)
+    extern __shared__ __align__(16) float swt[];   // [tap][out][half][group][4], channel c = 8*group + 4*half + j
     const int K = 9 * gi.C;
+    const int cgs = gi.C / 8;
     for (int i = threadIdx.x; i < K * 3; i += blockDim.x) {
         const int o = i % 3, k = i / 3;            // w is [9*Cin][3], k = tap*Cin + c
         const int tap = k / gi.C, c = k - tap * gi.C;
-        swt[((tap * (gi.C / 8) + c / 8) * 3 + o) * 8 + (c & 7)] = w[i];
+        swt[((((tap * 3 + o) * 2 + ((c >> 2) & 1)) * cgs) + (c >> 3)) * 4 + (c & 3)] = w[i];
     }
     __syncthreads();
-    const int cgs = gi.C / 8;                      // 8-channel groups per pixel
-    const long long npix = (long long)gi.N * gi.H * gi.W;
-    const int sub = threadIdx.x & 7;               // 8 lanes per pixel, 4 pixels per warp
+    const unsigned segs = (unsigned)(gi.W + 3) / 4u;
+    const unsigned nseg = (unsigned)gi.N * (unsigned)gi.H * segs;
+    const int sub = threadIdx.x & 7;
     const int lane = threadIdx.x & 31;
-    // warp-uniform loop bound (the shuffles below need the whole warp)
-    for (long long wbase = (((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane) >> 3; wbase < npix;
-         wbase += ((long long)gridDim.x * blockDim.x) >> 3) {
-        const long long pix = wbase + (lane >> 3);
-        const bool ok = pix < npix;
-        unsigned t = ok ? (unsigned)pix : 0u;
-        const int x = (int)(t % (unsigned)gi.W); t /= (unsigned)gi.W;
+    // warp-uniform loop bound (the shuffles below need the whole warp): 4 segments per warp
+    for (unsigned wbase = ((blockIdx.x * blockDim.x + threadIdx.x) - lane) >> 3; wbase < nseg;
+         wbase += (gridDim.x * blockDim.x) >> 3) {
+        const unsigned seg = wbase + (lane >> 3);
+        const bool ok = seg < nseg;
+        unsigned t = ok ? seg : 0u;
+        const int xs = (int)(t % segs) * 4; t /= segs;
         const int y = (int)(t % (unsigned)gi.H);
         const int n = (int)(t / (unsigned)gi.H);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        float acc[4][3];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
         if (ok) {
-            for (int ky = 0; ky < 3; ++ky)
-                for (int kx = 0; kx < 3; ++kx) {
-                    const long long pos = ((long long)n * gi.Hp + y + ky) * gi.Wp + x + kx;
-                    for (int cgi = sub; cgi < cgs; cgi += 8) {
-                        float v[8];
-                        load8(in, gi, pos, cgi * 8, v);
-                        const float4* wr = reinterpret_cast<const float4*>(swt + ((ky * 3 + kx) * cgs + cgi) * 24);
-                        const float4 p0 = wr[0], p1 = wr[1], q0 = wr[2], q1 = wr[3], r0 = wr[4], r1 = wr[5];
-                        a0 = fmaf(v[0], p0.x, a0); a0 = fmaf(v[1], p0.y, a0); a0 = fmaf(v[2], p0.z, a0); a0 = fmaf(v[3], p0.w, a0);
-                        a0 = fmaf(v[4], p1.x, a0); a0 = fmaf(v[5], p1.y, a0); a0 = fmaf(v[6], p1.z, a0); a0 = fmaf(v[7], p1.w, a0);
-                        a1 = fmaf(v[0], q0.x, a1); a1 = fmaf(v[1], q0.y, a1); a1 = fmaf(v[2], q0.z, a1); a1 = fmaf(v[3], q0.w, a1);
-                        a1 = fmaf(v[4], q1.x, a1); a1 = fmaf(v[5], q1.y, a1); a1 = fmaf(v[6], q1.z, a1); a1 = fmaf(v[7], q1.w, a1);
-                        a2 = fmaf(v[0], r0.x, a2); a2 = fmaf(v[1], r0.y, a2); a2 = fmaf(v[2], r0.z, a2); a2 = fmaf(v[3], r0.w, a2);
-                        a2 = fmaf(v[4], r1.x, a2); a2 = fmaf(v[5], r1.y, a2); a2 = fmaf(v[6], r1.z, a2); a2 = fmaf(v[7], r1.w, a2);
+            for (int cgi = sub; cgi < cgs; cgi += 8) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    float v[6][8];
+                    const long long rowpos = ((long long)n * gi.Hp + y + ky) * gi.Wp + xs;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        if (xs + j <= gi.W + 1) load8(in, gi, rowpos + j, cgi * 8, v[j]);
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
+                        }
                     }
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) {
+                            const int base = (((ky * 3 + kx) * 3 + o) * 2) * cgs;
+                            const float4 w0 = *reinterpret_cast<const float4*>(swt + (base + cgi) * 4);
+                            const float4 w1 = *reinterpret_cast<const float4*>(swt + (base + cgs + cgi) * 4);
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const float* vv = v[p + kx];
+                                float a = acc[p][o];
+                                a = fmaf(vv[0], w0.x, a); a = fmaf(vv[1], w0.y, a); a = fmaf(vv[2], w0.z, a); a = fmaf(vv[3], w0.w, a);
+                                a = fmaf(vv[4], w1.x, a); a = fmaf(vv[5], w1.y, a); a = fmaf(vv[6], w1.z, a); a = fmaf(vv[7], w1.w, a);
+                                acc[p][o] = a;
+                            }
+                        }
                 }
+            }
         }
 #pragma unroll
-        for (int o = 4; o >= 1; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
-        if (ok && sub == 0) {
-            a0 += b[0]; a1 += b[1]; a2 += b[2];
-            if (flags & WCTB200_CLIP01) {
-                a0 = fminf(fmaxf(a0, 0.f), 1.f);
-                a1 = fminf(fmaxf(a1, 0.f), 1.f);
-                a2 = fminf(fmaxf(a2, 0.f), 1.f);
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                float a = acc[p][o];
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                acc[p][o] = a;
             }
-            float* d = img + pix * 3;
-            d[0] = a0; d[1] = a1; d[2] = a2;
+        if (ok && sub == 0) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (xs + p < gi.W) {
+                    float* d = img + (((long long)n * gi.H + y) * gi.W + xs + p) * 3;
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) {
+                        float a = acc[p][o] + b[o];
+                        if (flags & WCTB200_CLIP01) a = fminf(fmaxf(a, 0.f), 1.f);
+                        d[o] = a;
+                    }
+                }
+            }
         }
     }
 }
@@ -329,13 +383,13 @@ int launch_conv3x3_ref(const __half* in, ActGeom gi, const float* w, const float
     return 0;
 }
 int launch_conv_head(const float* img, int N, int H, int W, const float* w, const float* b, __half* out, cudaStream_t st) {
-    k_conv_head<<<grid_for((long long)N * H * W * 8, 256), 256, 0, st>>>(img, N, H, W, w, b, out);
+    k_conv_head<<<grid_for((long long)N * H * ((W + 3) / 4) * 8, 256), 256, 0, st>>>(img, N, H, W, w, b, out);
     WCTB_CHECK_LAUNCH("k_conv_head");
     return 0;
 }
 int launch_conv_tail(const __half* in, ActGeom gi, const float* w, const float* b, int flags, float* img, cudaStream_t st) {
     const size_t smem = (size_t)9 * gi.C * 3 * sizeof(float);
-    k_conv_tail<<<grid_for((long long)gi.N * gi.H * gi.W * 8, 256), 256, smem, st>>>(in, gi, w, b, flags, img);
+    k_conv_tail<<<grid_for((long long)gi.N * gi.H * ((gi.W + 3) / 4) * 8, 256), 256, smem, st>>>(in, gi, w, b, flags, img);
     WCTB_CHECK_LAUNCH("k_conv_tail");
     return 0;
 }

@@ -229,8 +229,12 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
     // rotation that makes the two columns orthogonal (Hestenes)
     const float zeta = (be - al) / (2.f * ga);
     const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-    const float c = 1.f / sqrtf(1.f + t * t);   // IEEE sqrt/div: rsqrtf's 2-ulp bias would shrink |column| every rotation
-    const float s = c * t;
+    // c = 1 + cm1 with cm1 = -t^2/(sqrt(h)(1+sqrt(h))): for small angles c rounds to exactly 1 and
+    // [[1,-s],[s,1]] would GROW the columns by t^2/2 per rotation (eigenvalue bias ~ #rotations)
+    const float h = 1.f + t * t;
+    const float rh = sqrtf(h);
+    const float s = t / rh;
+    const float cm1 = -(t * t) / (rh * (1.f + rh));
 #pragma unroll
     for (int v = 0; v < Cfg::NV; ++v) {
         const int off = (v * 32 + lane) * Cfg::VEC;
@@ -238,8 +242,8 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
 #pragma unroll
         for (int e = 0; e < Cfg::VEC; ++e) {
             const float xv = x[v * Cfg::VEC + e], yv = y[v * Cfg::VEC + e];
-            nx[e] = c * xv - s * yv;
-            ny[e] = s * xv + c * yv;
+            nx[e] = fmaf(cm1, xv, fmaf(-s, yv, xv));
+            ny[e] = fmaf(cm1, yv, fmaf(s, xv, yv));
         }
         if (Cfg::VEC == 4) {
             *reinterpret_cast<float4*>(cx + off) = make_float4(nx[0], nx[1], nx[2], nx[3]);
@@ -252,24 +256,33 @@ __device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __re
     return ratio;
 }
 
-// ---- register-blocked cross-pair rotation: operands live in registers, norms are cached ----
-template <int EPL>
-__device__ __forceinline__ void rot_regs(float (&x)[EPL], float (&y)[EPL], float& a, float& b, float tol, float& wmax) {
-    // dot product with 4 independent chains (ILP), then a butterfly reduction
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-    if (EPL >= 4) {
+// ---- register-blocked cross-pair rotation: operands live in registers as PACKED fp32 pairs
+// (fma.rn.f32x2: two FMAs per instruction on sm_100), column norms are cached ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+template <int HP>   // HP = packed pairs per lane per column = NN/64
+__device__ __forceinline__ void rot_regs(f32x2 (&x)[HP], f32x2 (&y)[HP], float& a, float& b, float tol, float& wmax) {
+    f32x2 d0 = 0ull, d1 = 0ull;                     // +0.0f pairs
 #pragma unroll
-        for (int i = 0; i < EPL; i += 4) {
-            g0 = fmaf(x[i], y[i], g0);
-            g1 = fmaf(x[i + 1], y[i + 1], g1);
-            g2 = fmaf(x[i + 2], y[i + 2], g2);
-            g3 = fmaf(x[i + 3], y[i + 3], g3);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < EPL; ++i) g0 = fmaf(x[i], y[i], g0);
+    for (int i = 0; i < HP; ++i) {
+        if (i & 1) d1 = fma2(x[i], y[i], d1);
+        else d0 = fma2(x[i], y[i], d0);
     }
-    float g = (g0 + g1) + (g2 + g3);
+    float p0, p1, p2, p3;
+    unpack2(d0, p0, p1);
+    unpack2(d1, p2, p3);
+    float g = (p0 + p1) + (p2 + p3);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
     const float ab = a * b;
@@ -278,9 +291,9 @@ __device__ __forceinline__ void rot_regs(float (&x)[EPL], float (&y)[EPL], float
     wmax = fmaxf(wmax, ratio);
     if (ratio <= tol) return;
     // Rotation angle: approximate (MUFU) arithmetic is fine for t -- any t yields an exact
-    // rotation as long as (c,s) is orthonormal; a slightly-off t only leaves a residual for
-    // the next sweep.  c gets one Newton step so c^2(1+t^2) = 1 to ~1 ulp WITHOUT bias
-    // (a biased c shrinks the column norms, i.e. the eigenvalues, at every rotation).
+    // rotation as long as (c,s) is orthonormal; a slightly-off t only leaves a residual for the
+    // next sweep.  (c,s) come from r = h^-1/2 refined by one Newton step, and c is applied as
+    // 1 + cm1 so that small angles neither shrink nor grow the columns (no eigenvalue bias).
     const float zeta = __fdividef(b - a, 2.f * g);
     const float az = fabsf(zeta);
     float t;
@@ -291,42 +304,44 @@ __device__ __forceinline__ void rot_regs(float (&x)[EPL], float (&y)[EPL], float
         t = __fdividef(copysignf(1.f, zeta), az + h2 * rsqrtf(h2));
     }
     const float h = fmaf(t, t, 1.f);
-    float c = rsqrtf(h);
-    c = c * fmaf(-0.5f * h, c * c, 1.5f);
-    const float s = c * t;
+    float r = rsqrtf(h);
+    r = r * fmaf(-0.5f * h, r * r, 1.5f);
+    const float s = t * r;
+    const float cm1 = -__fdividef(t * t * r, fmaf(h, r, 1.f));
+    const f32x2 s2 = pack2(s, s), ns2 = pack2(-s, -s), c2 = pack2(cm1, cm1);
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        const float xv = x[i], yv = y[i];
-        x[i] = fmaf(c, xv, -s * yv);
-        y[i] = fmaf(s, xv, c * yv);
+    for (int i = 0; i < HP; ++i) {
+        const f32x2 xv = x[i], yv = y[i];
+        x[i] = fma2(c2, xv, fma2(ns2, yv, xv));       // x' = x + cm1*x - s*y
+        y[i] = fma2(c2, yv, fma2(s2, xv, yv));        // y' = y + cm1*y + s*x
     }
     a = fmaxf(fmaf(-t, g, a), 0.f);      // |x'|^2 = |x|^2 - t*g ,  |y'|^2 = |y|^2 + t*g
     b = fmaxf(fmaf(t, g, b), 0.f);
 }
 
 template <int NN>
-__device__ __forceinline__ void load_col(const float* __restrict__ c, int lane, float (&r)[NN / 32]) {
+__device__ __forceinline__ void load_col(const float* __restrict__ c, int lane, f32x2 (&r)[NN / 64]) {
     using Cfg = JacobiCfg<NN>;
 #pragma unroll
     for (int v = 0; v < Cfg::NV; ++v) {
         const int off = (v * 32 + lane) * Cfg::VEC;
         if (Cfg::VEC == 4) {
-            const float4 a = *reinterpret_cast<const float4*>(c + off);
-            r[v * 4] = a.x; r[v * 4 + 1] = a.y; r[v * 4 + 2] = a.z; r[v * 4 + 3] = a.w;
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(c + off);
+            r[v * 2] = a.x;
+            r[v * 2 + 1] = a.y;
         } else {
-            const float2 a = *reinterpret_cast<const float2*>(c + off);
-            r[v * 2] = a.x; r[v * 2 + 1] = a.y;
+            r[v] = *reinterpret_cast<const unsigned long long*>(c + off);
         }
     }
 }
 template <int NN>
-__device__ __forceinline__ void store_col(float* __restrict__ c, int lane, const float (&r)[NN / 32]) {
+__device__ __forceinline__ void store_col(float* __restrict__ c, int lane, const f32x2 (&r)[NN / 64]) {
     using Cfg = JacobiCfg<NN>;
 #pragma unroll
     for (int v = 0; v < Cfg::NV; ++v) {
         const int off = (v * 32 + lane) * Cfg::VEC;
-        if (Cfg::VEC == 4) *reinterpret_cast<float4*>(c + off) = make_float4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
-        else *reinterpret_cast<float2*>(c + off) = make_float2(r[v * 2], r[v * 2 + 1]);
+        if (Cfg::VEC == 4) *reinterpret_cast<ulonglong2*>(c + off) = make_ulonglong2(r[v * 2], r[v * 2 + 1]);
+        else *reinterpret_cast<unsigned long long*>(c + off) = r[v];
     }
 }
 
@@ -341,7 +356,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     constexpr int P = Cfg::P;
     constexpr int NB = 2 * P;
     constexpr int M = NB - 1;
-    constexpr int EPL = NN / 32;
+    constexpr int HP = NN / 64;
     extern __shared__ __align__(16) float cols[];          // [64][NN]
     __shared__ float nrm[64];
     __shared__ unsigned int s_max;
@@ -387,11 +402,14 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             }
             // ---- column norms (fresh every round: the cached values never drift far)
             for (int c = warp * 4; c < warp * 4 + 4; ++c) {
-                float v[EPL];
+                f32x2 v[HP];
                 load_col<NN>(cols + c * NN, lane, v);
-                float ss = 0.f;
+                f32x2 q = 0ull;
 #pragma unroll
-                for (int i = 0; i < EPL; ++i) ss = fmaf(v[i], v[i], ss);
+                for (int i = 0; i < HP; ++i) q = fma2(v[i], v[i], q);
+                float q0, q1;
+                unpack2(q, q0, q1);
+                float ss = q0 + q1;
 #pragma unroll
                 for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 if (lane == 0) nrm[c] = ss;
@@ -399,7 +417,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             __syncthreads();
             // ---- cross pairs: 16 steps x 4 rotations per warp
             {
-                float x0[EPL], x1[EPL];
+                f32x2 x0[HP], x1[HP];
                 load_col<NN>(cols + (2 * warp) * NN, lane, x0);
                 load_col<NN>(cols + (2 * warp + 1) * NN, lane, x1);
                 float a0 = nrm[2 * warp], a1 = nrm[2 * warp + 1];
@@ -407,14 +425,14 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                     const int j = (warp + s) & 15;
                     float* cy0 = cols + (32 + 2 * j) * NN;
                     float* cy1 = cy0 + NN;
-                    float y0[EPL], y1[EPL];
+                    f32x2 y0[HP], y1[HP];
                     load_col<NN>(cy0, lane, y0);
                     load_col<NN>(cy1, lane, y1);
                     float b0 = nrm[32 + 2 * j], b1 = nrm[32 + 2 * j + 1];
-                    rot_regs<EPL>(x0, y0, a0, b0, tol, wmax);
-                    rot_regs<EPL>(x1, y1, a1, b1, tol, wmax);
-                    rot_regs<EPL>(x0, y1, a0, b1, tol, wmax);
-                    rot_regs<EPL>(x1, y0, a1, b0, tol, wmax);
+                    rot_regs<HP>(x0, y0, a0, b0, tol, wmax);
+                    rot_regs<HP>(x1, y1, a1, b1, tol, wmax);
+                    rot_regs<HP>(x0, y1, a0, b1, tol, wmax);
+                    rot_regs<HP>(x1, y0, a1, b0, tol, wmax);
                     store_col<NN>(cy0, lane, y0);
                     store_col<NN>(cy1, lane, y1);
                     if (lane == 0) { nrm[32 + 2 * j] = b0; nrm[32 + 2 * j + 1] = b1; }
@@ -641,12 +659,24 @@ static WctWs wct_layout(int C, int Nc, int Ns) {
 }
 size_t wct_workspace_bytes(int C, int Nc, int Ns) { return wct_layout(C, Nc, Ns).total; }
 
-static int pick_chunk(long long HW) { return HW >= 65536 ? 512 : 256; }
+static int pick_chunk(long long HW, int nblk_pairs, int n) {
+    // 32-pixel steps; aim for >= ~600 blocks, cap the fp32 partial sums at 512 pixels
+    long long chunk = (HW * nblk_pairs * n + 599) / 600;
+    chunk = (chunk + 31) / 32 * 32;
+    if (chunk < 64) chunk = 64;
+    if (chunk > 512) chunk = 512;
+    return (int)chunk;
+}
 
 template <bool SQ>
 static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq, cudaStream_t st) {
     const long long HW = (long long)g.H * g.W;
-    const int chunk = 1024;
+    // enough blocks to fill the chip (~4 per SM) even for small feature maps, at most 1024 px per block
+    long long chunk = (HW * g.N + 591) / 592;
+    const int rows = 256 / (g.C / 8) > 0 ? 256 / (g.C / 8) : 1;
+    chunk = (chunk + rows - 1) / rows * rows;
+    if (chunk < rows) chunk = rows;
+    if (chunk > 1024) chunk = 1024;
     dim3 grid((unsigned)cdiv(HW, chunk), (unsigned)g.N);
     k_chan_sums<SQ><<<grid, 256, 0, st>>>(act, g, chunk, sum, sumsq);
     WCTB_CHECK_LAUNCH("k_chan_sums");
@@ -708,7 +738,7 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
     k_mean_finalize<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(sum, nullptr, HW, g.N * g.C, mean, nullptr);
     WCTB_CHECK_LAUNCH("k_mean_finalize");
     const int nb = g.C / 64;
-    const int chunk = pick_chunk(HW);
+    const int chunk = pick_chunk(HW, nb * (nb + 1) / 2, g.N);
     dim3 grid((unsigned)(nb * (nb + 1) / 2), (unsigned)cdiv(HW, chunk), (unsigned)g.N);
     k_cov_partial<<<grid, 256, 0, st>>>(act, g, mean, chunk, cov);
     WCTB_CHECK_LAUNCH("k_cov_partial");
