@@ -135,8 +135,11 @@ WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, in
  * (64/128/256; 0 = built-in heuristic).  Used by bench/profiling scripts. */
 WCTB200_API int wctb200_debug_set_conv_bn(int bn);
 /* 1 = one tile per CTA with all-TMEM accumulation, 2 = persistent CTAs with chunked register
- * accumulation (default).  Returns the implementation now selected. */
+ * accumulation, 3 = 2 + on-chip tap reuse of the activation patch and cluster-multicast weights.
+ * Returns the implementation now selected. */
 WCTB200_API int wctb200_debug_set_conv_impl(int impl);
+/* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
+WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wctb200_debug_set_conv_bn": (_i, [_i]),
     "wctb200_debug_set_conv_impl": (_i, [_i]),
+    "wctb200_debug_set_conv3": (_i, [_i, _i]),
 }
 
 _lib = None

@@ -53,6 +53,8 @@ int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
 int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
 extern int g_conv_impl;
+extern int g_conv3_cluster;
+extern int g_conv3_bo_mode;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
 static bool geom_ok(int N, int H, int W, int C) {
@@ -191,8 +193,13 @@ int wctb200_debug_set_conv_bn(int bn) {
     return 0;
 }
 int wctb200_debug_set_conv_impl(int impl) {
-    if (impl == 1 || impl == 2) g_conv_impl = impl;
+    if (impl >= 1 && impl <= 3) g_conv_impl = impl;
     return g_conv_impl;
+}
+int wctb200_debug_set_conv3(int cluster, int bo_mode) {
+    g_conv3_cluster = cluster == 1 ? 1 : 2;
+    g_conv3_bo_mode = bo_mode ? 1 : 0;
+    return 0;
 }
 
 }  // extern "C"

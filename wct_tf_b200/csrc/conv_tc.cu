@@ -26,6 +26,9 @@
 
 namespace wctb {
 
+extern int g_conv_bn_override;
+extern int g_conv_impl;
+
 struct ConvParams {
     int N, H, W, Cin, Cout, Hp, Wp;
     long long P;
@@ -528,6 +531,9 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
 int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent, chunked register accumulation
 
+int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
+                       int flags, __half* out, int bn_override, cudaStream_t st);
+
 int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __half* w_split, int taps, int nsets,
                       const float* bias, int Cout, int flags, __half* out, cudaStream_t st) {
     WCTB_REQUIRE(N >= 1 && H >= 2 && W >= 2, "conv3x3: bad geometry N=%d H=%d W=%d", N, H, W);
@@ -537,6 +543,10 @@ int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __ha
     ActGeom gi(N, H, W, Cin);
     WCTB_REQUIRE(gi.P < (1ll << 31) - 4096, "conv3x3: too many padded positions (%lld)", gi.P);
 
+    if (g_conv_impl == 3 && taps == 9 && nsets == 1) {
+        const int r = launch_conv3x3_tc3(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
+        if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v3 -> v2 below
+    }
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     if (BN == 256) BN = 128;  // v1 default: 3-stage pipeline beats the 2-stage 256-wide tile until 2-CTA lands
     if (g_conv_bn_override && Cout % g_conv_bn_override == 0) BN = g_conv_bn_override;
@@ -559,7 +569,7 @@ int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __ha
     p.out = out;
     p.err = device_error_word();
     dim3 grid(p.per_image ? (unsigned)(N * p.tiles_per_image) : (unsigned)cdiv(gi.P, 128), (unsigned)(Cout / BN));
-    if (g_conv_impl == 2) {
+    if (g_conv_impl >= 2) {
         const int n_tiles = Cout / BN;
         const int total = (int)grid.x * n_tiles;
         switch (BN) {

@@ -1,0 +1,497 @@
+// conv_tc3: Conv2DReflect 3x3 as an implicit GEMM with ON-CHIP TAP REUSE and cluster multicast.
+//
+// v2 (conv_tc.cu) re-fetches the 128x64 activation tile from L2 for each of the 9 filter taps
+// and the weight tile for every CTA; ncu showed it L2->SM operand-bandwidth bound (tensor pipe
+// ~57 % active, 125 B/clk/SM requested for the 64-channel layers vs ~42 B/clk/SM available).
+// v3 cuts the operand traffic:
+//
+//   A (activations): per 64-channel slice ONE patch of the padded plane is staged in shared
+//     memory and all 9 taps read it through shifted UMMA descriptors (start address
+//     + (ky*PW + kx) rows of 128 B; the 128B swizzle is address based, so a row shift keeps the
+//     pattern TMA wrote).  Two tilings:
+//       FLAT (W <= 64): tile = 128 consecutive padded positions, patch = 128 + 2*(W+2) + 2 rows;
+//       2-D  (W >= 128): tile = 4 rows x 32 padded columns (30 valid + 2 junk), patch = 6 x 32
+//         positions loaded by one 5-D TMA box; tiles at the ragged right/bottom edge shift
+//         inwards (the overlap is recomputed identically).
+//     A traffic per tile drops from 9 tiles to ~1.5-2 tiles per slice.
+//   B (weights): a cluster of 2 CTAs works on two M tiles of the same cout tile; each CTA loads
+//     HALF of every weight tile and TMA-multicasts it into both CTAs' shared memory
+//     (.multicast::cluster), the MMA warps release a stage with a multicast tcgen05.commit.
+//
+// Everything else is v2: persistent CTAs, 4-k-iteration accumulation chunks in a TMEM ring
+// drained into registers with round-to-nearest adds, split-fp16 x3 products.
+#include "common.cuh"
+
+namespace wctb {
+
+struct Conv3Params {
+    int N, H, W, Cin, Cout, Hp, Wp;
+    long long P;
+    int mode2d;          // 0 = FLAT, 1 = 2-D tiles
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int pw;              // rows between vertical taps inside the patch: Wp (FLAT) or 32 (2-D)
+    int box_rows;        // FLAT: rows per TMA box (2 boxes per plane); 2-D: unused
+    int a_plane_bytes;   // shared-memory bytes of one plane of the patch (1024-aligned)
+    int a_tx_bytes;      // bytes TMA delivers per A stage (both planes)
+    int nb_stages;       // B ring depth
+    int cluster;         // 1 or 2
+    int bo_mode;         // 1: descriptor base_offset = (start>>7)&7 (PTX ISA), 0: leave 0
+    int flags;
+    const float* bias;
+    __half* out;
+    unsigned int* err;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1),
+        "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// K-major SW128 descriptor whose start may sit on any 128-byte row of the staged patch
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t smem_addr, int bo_mode) {
+    uint64_t d = umma_desc_sw128(smem_addr);
+    if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;   // matrix base offset (PTX ISA: tcgen05 smem descriptor)
+    return d;
+}
+
+template <int BN>
+struct Conv3Cfg {
+    static constexpr int B_BYTES = BN * 64 * 2;             // one plane of one weight tile
+    static constexpr int B_STAGE = 2 * B_BYTES;
+    static constexpr int NBUF = BN == 256 ? 2 : 4;
+    static constexpr int TMEM_COLS = NBUF * BN;
+    static constexpr int CH = 4;
+    static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int NACC = BN / (EPI_WARPS / 4);
+    static constexpr int AUX_BYTES = 512 + BN * 4;
+    static constexpr int MAX_B_STAGES = 6;
+};
+
+struct Tile3 {
+    int n0;
+    long long p0;        // FLAT: first padded position of the tile
+    int img, y0, x0;     // 2-D: image and first valid pixel of the tile
+    bool live;           // false: padding tile of an odd cluster pair (runs the pipeline, stores nothing)
+};
+
+__device__ __forceinline__ Tile3 tile3(const Conv3Params& p, int m_tile, int n_idx, int BN) {
+    Tile3 t;
+    t.n0 = n_idx * BN;
+    t.live = m_tile < p.m_tiles;
+    const int mt = t.live ? m_tile : p.m_tiles - 1;
+    if (p.mode2d) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        t.img = mt / per_img;
+        const int r = mt - t.img * per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        t.y0 = min(ty * 4, p.H - 4);
+        t.x0 = min(tx * 30, p.W - 30);
+        t.p0 = 0;
+    } else {
+        t.p0 = (long long)mt * 128;
+        t.img = t.y0 = t.x0 = 0;
+    }
+    return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(Conv3Cfg<BN>::THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Conv3Params p) {
+    using Cfg = Conv3Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int a_stage = 2 * p.a_plane_bytes;
+    uint8_t* a_base = smem;
+    uint8_t* b_base = smem + 2 * a_stage;
+    uint8_t* aux = b_base + p.nb_stages * Cfg::B_STAGE;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* emptyA = fullA + 2;
+    uint64_t* fullB = emptyA + 2;
+    uint64_t* emptyB = fullB + Cfg::MAX_B_STAGES;
+    uint64_t* tfull = emptyB + Cfg::MAX_B_STAGES;
+    uint64_t* tempty = tfull + Cfg::NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NBUF);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* sbias = reinterpret_cast<float*>(aux + 512);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+    const uint16_t mc_mask = (uint16_t)((1u << p.cluster) - 1u);
+
+    // NOTE: no early exit on a previous error here: both CTAs of a cluster must take the same path
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&fullA[s], 1);
+            mbar_init(&emptyA[s], 1);
+        }
+        for (int s = 0; s < p.nb_stages; ++s) {
+            mbar_init(&fullB[s], 1);
+            mbar_init(&emptyB[s], p.cluster);          // released by every CTA of the cluster
+        }
+        for (int b = 0; b < Cfg::NBUF; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], Cfg::EPI_WARPS);
+        }
+        *abort_flag = 0;
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();             // peers' barriers are initialised before any multicast lands
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksl = p.Cin / 64;
+    const int kiters = 9 * ksl;
+    const int nchunks = (kiters + Cfg::CH - 1) / Cfg::CH;
+    const int num_clusters = gridDim.x / p.cluster;
+    const int cid = blockIdx.x / p.cluster;
+    const int m_pairs = (p.m_tiles + p.cluster - 1) / p.cluster;
+    const int total_q = m_pairs * p.n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;
+            for (int q = cid; q < total_q; q += num_clusters) {
+                const Tile3 t = tile3(p, (q / p.n_tiles) * p.cluster + (int)crank, q % p.n_tiles, BN);
+                for (int ks = 0; ks < ksl; ++ks, ++ia) {
+                    const int sa = ia & 1;
+                    mbar_wait(&emptyA[sa], ((ia >> 1) & 1) ^ 1u, abort_flag, p.err, 0x110u + sa);
+                    uint8_t* st = a_base + sa * a_stage;
+                    mbar_arrive_expect_tx(&fullA[sa], (uint32_t)p.a_tx_bytes);
+                    if (p.mode2d) {
+                        tma_load_5d(st, &mapA, &fullA[sa], ks * 64, t.x0, t.y0, t.img, 0);
+                        tma_load_5d(st + p.a_plane_bytes, &mapA, &fullA[sa], ks * 64, t.x0, t.y0, t.img, 1);
+                    } else {
+                        const int row = (int)(t.p0 - p.Wp - 1);
+                        const int hb = p.box_rows * 128;
+                        tma_load_3d(st, &mapA, &fullA[sa], ks * 64, row, 0);
+                        tma_load_3d(st + hb, &mapA, &fullA[sa], ks * 64, row + p.box_rows, 0);
+                        tma_load_3d(st + p.a_plane_bytes, &mapA, &fullA[sa], ks * 64, row, 1);
+                        tma_load_3d(st + p.a_plane_bytes + hb, &mapA, &fullA[sa], ks * 64, row + p.box_rows, 1);
+                    }
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % p.nb_stages;
+                        mbar_wait(&emptyB[sb], ((ib / p.nb_stages) & 1) ^ 1u, abort_flag, p.err, 0x120u + sb);
+                        uint8_t* sbp = b_base + sb * Cfg::B_STAGE;
+                        mbar_arrive_expect_tx(&fullB[sb], Cfg::B_STAGE);
+                        const int kc = tap * p.Cin + ks * 64;
+                        if (p.cluster > 1) {
+                            // this CTA fetches rows [crank*BN/2, +BN/2) of the tile and multicasts them to both CTAs
+                            const int half = BN / 2;
+                            const int ro = (int)crank * half;
+                            tma_load_3d_mc(sbp + ro * 128, &mapB, &fullB[sb], kc, t.n0 + ro, 0, mc_mask);
+                            tma_load_3d_mc(sbp + Cfg::B_BYTES + ro * 128, &mapB, &fullB[sb], kc, t.n0 + ro, 1, mc_mask);
+                        } else {
+                            tma_load_3d(sbp, &mapB, &fullB[sb], kc, t.n0, 0);
+                            tma_load_3d(sbp + Cfg::B_BYTES, &mapB, &fullB[sb], kc, t.n0, 1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, BN);
+            uint32_t ia = 0, ib = 0, cg_ = 0;
+            for (int q = cid; q < total_q; q += num_clusters) {
+                int it = 0;
+                for (int c = 0; c < nchunks; ++c, ++cg_) {
+                    const int b = cg_ % Cfg::NBUF;
+                    mbar_wait(&tempty[b], ((cg_ / Cfg::NBUF) & 1) ^ 1u, abort_flag, p.err, 0x400u + b);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
+                    const int it_end = min(kiters, (c + 1) * Cfg::CH);
+                    for (; it < it_end; ++it, ++ib) {
+                        const int tap = it % 9;
+                        const int sa = ia & 1;
+                        if (tap == 0) mbar_wait(&fullA[sa], (ia >> 1) & 1, abort_flag, p.err, 0x210u + sa);
+                        const int sb = ib % p.nb_stages;
+                        mbar_wait(&fullB[sb], (ib / p.nb_stages) & 1, abort_flag, p.err, 0x220u + sb);
+                        tc_fence_after();
+                        const uint32_t ast = smem_u32(a_base + sa * a_stage) + (uint32_t)(((tap / 3) * p.pw + (tap % 3)) * 128);
+                        const uint32_t bst = smem_u32(b_base + sb * Cfg::B_STAGE);
+                        const bool first = (it == c * Cfg::CH);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_hi = umma_desc_sw128_rows(ast + k * 32, p.bo_mode);
+                            const uint64_t a_lo = umma_desc_sw128_rows(ast + p.a_plane_bytes + k * 32, p.bo_mode);
+                            const uint64_t b_hi = umma_desc_sw128(bst + k * 32);
+                            const uint64_t b_lo = umma_desc_sw128(bst + Cfg::B_BYTES + k * 32);
+                            umma_f16(tacc, a_hi, b_lo, idesc, (first && k == 0) ? 0u : 1u);
+                            umma_f16(tacc, a_lo, b_hi, idesc, 1u);
+                            umma_f16(tacc, a_hi, b_hi, idesc, 1u);
+                        }
+                        if (p.cluster > 1) umma_commit_mc(&emptyB[sb], mc_mask);
+                        else umma_commit(&emptyB[sb]);
+                        if (tap == 8) {
+                            umma_commit(&emptyA[sa]);
+                            ++ia;
+                        }
+                    }
+                    umma_commit(&tfull[b]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int g = warp & 3;
+        const int colbase = (e >> 2) * Cfg::NACC;
+        const int et = threadIdx.x - 64;
+        constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
+        const long long HpWp = (long long)p.Hp * p.Wp;
+        const ActGeom go(p.N, p.H, p.W, p.Cout);
+        const bool relu = (p.flags & WCTB200_RELU) != 0;
+        const int m = g * 32 + lane;
+        uint32_t cg_ = 0;
+        for (int q = cid; q < total_q; q += num_clusters) {
+            const Tile3 t = tile3(p, (q / p.n_tiles) * p.cluster + (int)crank, q % p.n_tiles, BN);
+            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+            for (int i = et; i < BN; i += ETHREADS) sbias[i] = p.bias ? p.bias[t.n0 + i] : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+
+            float acc[Cfg::NACC];
+#pragma unroll
+            for (int i = 0; i < Cfg::NACC; ++i) acc[i] = 0.f;
+            for (int c = 0; c < nchunks; ++c, ++cg_) {
+                const int b = cg_ % Cfg::NBUF;
+                mbar_wait(&tfull[b], (cg_ / Cfg::NBUF) & 1, abort_flag, p.err, 0x300u + b);
+                tc_fence_after();
+                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * BN + colbase);
+#pragma unroll
+                for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tsrc + c0, r0);
+                    if (c0 + 32 < Cfg::NACC) tmem_ld32(tsrc + c0 + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+                    if (c0 + 32 < Cfg::NACC) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[b]);
+            }
+            bool valid = t.live;
+            int n = 0, y = 0, x = 0;
+            if (p.mode2d) {
+                const int c = m & 31;
+                valid = valid && (c < 30);
+                n = t.img;
+                y = t.y0 + (m >> 5);
+                x = t.x0 + c;
+            } else {
+                const long long pos = t.p0 + m;
+                valid = valid && pos < p.P;
+                if (valid) {
+                    n = (int)(pos / HpWp);
+                    const int r = (int)(pos - n * HpWp);
+                    const int yy = r / p.Wp;
+                    const int xx = r - yy * p.Wp;
+                    valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
+                    y = yy - 1;
+                    x = xx - 1;
+                }
+            }
+            if (valid && !*abort_flag) {
+#pragma unroll
+                for (int qd = 0; qd < Cfg::NACC / 8; ++qd) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float tt = acc[qd * 8 + j] + sbias[colbase + qd * 8 + j];
+                        v[j] = relu ? fmaxf(tt, 0.f) : tt;
+                    }
+                    Half8 hi, lo;
+                    split8(v, hi, lo);
+                    store8_with_halo(p.out, go, n, y, x, t.n0 + colbase + qd * 8, hi, lo);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.cluster > 1) cluster_sync_all();      // no CTA exits while its peer may still multicast into it
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled3 get_encode3() {
+    static PFN_encodeTiled3 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled3>(ptr);
+    }
+    return fn;
+}
+
+static int make_map_n(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box) {
+    PFN_encodeTiled3 enc = get_encode3();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return WCTB200_ECUDA;
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(rank %d) failed (%d)", rank, (int)r);
+        return WCTB200_ECUDA;
+    }
+    return 0;
+}
+
+int g_conv3_cluster = 2;     // tuning hooks (wctb200_debug_set_conv3)
+int g_conv3_bo_mode = 1;
+
+template <int BN>
+static int launch3_bn(const CUtensorMap& mA, const CUtensorMap& mB, const Conv3Params& p, int smem_bytes, cudaStream_t st) {
+    using Cfg = Conv3Cfg<BN>;
+    static int sms = 0;
+    static int attr_bytes = 0;
+    if (!sms) {
+        int dev = 0;
+        WCTB_CUDA(cudaGetDevice(&dev));
+        WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    if (smem_bytes > attr_bytes) {
+        WCTB_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_bytes = smem_bytes;
+    }
+    const int m_pairs = (p.m_tiles + p.cluster - 1) / p.cluster;
+    const int total_q = m_pairs * p.n_tiles;
+    int clusters = sms / p.cluster;
+    if (clusters > total_q) clusters = total_q;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * p.cluster), 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)p.cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    WCTB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<BN>, mA, mB, p));
+    return 0;
+}
+
+// returns 1 if this shape is handled by v3 (and launched), 0 if the caller should use v2, <0 on error
+int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
+                       int flags, __half* out, int bn_override, cudaStream_t st) {
+    if (Cin % 64 || Cout % 64 || H < 4 || W < 4) return 0;
+    ActGeom gi(N, H, W, Cin);
+    if (gi.P >= (1ll << 31) - 4096) return 0;
+    Conv3Params p;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Hp = gi.Hp; p.Wp = gi.Wp; p.P = gi.P;
+    p.flags = flags; p.bias = bias; p.out = out; p.err = device_error_word();
+    p.cluster = g_conv3_cluster == 1 ? 1 : 2;
+    p.bo_mode = g_conv3_bo_mode;
+    int BN = Cout % 128 == 0 ? 128 : 64;
+    if (bn_override && Cout % bn_override == 0 && bn_override <= 128) BN = bn_override;
+    if (p.cluster > 1 && BN / 2 < 8) p.cluster = 1;
+    p.n_tiles = Cout / BN;
+
+    CUtensorMap mA, mB;
+    if (W >= 128 || (W > 64 && W >= 30)) {
+        p.mode2d = 1;
+        p.tiles_x = (W + 29) / 30;
+        p.tiles_y = (H + 3) / 4;
+        p.m_tiles = N * p.tiles_x * p.tiles_y;
+        p.pw = 32;
+        p.box_rows = 0;
+        p.a_plane_bytes = 200 * 128;                         // 6*32 = 192 rows written, taps reach row 193
+        p.a_tx_bytes = 2 * 192 * 128;
+        cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)gi.Wp, (cuuint64_t)gi.Hp, (cuuint64_t)N, 2};
+        cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)gi.Wp * Cin * 2, (cuuint64_t)gi.Hp * gi.Wp * Cin * 2,
+                                 (cuuint64_t)gi.plane * 2};
+        cuuint32_t box[5] = {64, 32, 6, 1, 1};
+        int rc = make_map_n(&mA, in, 5, dims, strides, box);
+        if (rc) return rc;
+    } else {
+        p.mode2d = 0;
+        p.tiles_x = p.tiles_y = 0;
+        p.m_tiles = cdiv(gi.P, 128);
+        p.pw = gi.Wp;
+        const int R = 128 + 2 * gi.Wp + 2;
+        p.box_rows = ((R + 1) / 2 + 7) / 8 * 8;              // two boxes per plane, each a multiple of 8 rows
+        if (p.box_rows > 256) return 0;
+        p.a_plane_bytes = 2 * p.box_rows * 128;
+        p.a_tx_bytes = 2 * p.a_plane_bytes;
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)gi.P, 2};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)gi.plane * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.box_rows, 1};
+        int rc = make_map_n(&mA, in, 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)9 * Cin;
+        cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
+        cuuint64_t strides[2] = {K * 2, K * Cout * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)(p.cluster > 1 ? BN / 2 : BN), 1};
+        int rc = make_map_n(&mB, w_split, 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    // shared memory: 2 A stages + as many B stages as fit (<= 6)
+    const int b_stage = 2 * BN * 128;
+    const int aux = 512 + BN * 4 + 1024;
+    const int budget = 227 * 1024 - aux - 2 * 2 * p.a_plane_bytes;
+    int nb = budget / b_stage;
+    if (nb > 6) nb = 6;
+    if (nb < 2) return 0;
+    p.nb_stages = nb;
+    const int smem_bytes = 2 * 2 * p.a_plane_bytes + nb * b_stage + aux;
+    int rc = BN == 128 ? launch3_bn<128>(mA, mB, p, smem_bytes, st) : launch3_bn<64>(mA, mB, p, smem_bytes, st);
+    return rc ? rc : 1;
+}
+
+}  // namespace wctb
