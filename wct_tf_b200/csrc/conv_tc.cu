@@ -529,7 +529,7 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
 }
 
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
-int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent, chunked register accumulation
+int g_conv_impl = 3;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu)
 
 int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
                        int flags, __half* out, int bn_override, cudaStream_t st);

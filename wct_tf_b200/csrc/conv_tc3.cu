@@ -73,10 +73,14 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// K-major SW128 descriptor whose start may sit on any 128-byte row of the staged patch
+// K-major SW128 descriptor whose start may sit on any 128-byte row of the staged patch.
+// Measured on B200 (tools/conv3_probe.py): the 128B swizzle XOR is taken from the absolute
+// shared-memory address bits, so a start address shifted by whole 128-byte rows reads exactly what
+// TMA wrote and the descriptor's base_offset field must stay 0 (setting it to (addr>>7)&7, as the
+// PTX ISA text suggests for unaligned starts, produces garbage).  bo_mode=1 is kept as a probe.
 __device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t smem_addr, int bo_mode) {
     uint64_t d = umma_desc_sw128(smem_addr);
-    if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;   // matrix base offset (PTX ISA: tcgen05 smem descriptor)
+    if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
     return d;
 }
 
@@ -389,7 +393,7 @@ static int make_map_n(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 int g_conv3_cluster = 2;     // tuning hooks (wctb200_debug_set_conv3)
-int g_conv3_bo_mode = 1;
+int g_conv3_bo_mode = 0;     // measured on B200: descriptors at 128-byte row offsets need base_offset = 0
 
 template <int BN>
 static int launch3_bn(const CUtensorMap& mA, const CUtensorMap& mB, const Conv3Params& p, int smem_bytes, cudaStream_t st) {
