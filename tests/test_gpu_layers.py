@@ -151,7 +151,7 @@ def test_conv3x3_tensor_core(case, bn, impl):
         U.check_device()
     finally:
         U.lib().wctb200_debug_set_conv_bn(0)
-        U.lib().wctb200_debug_set_conv_impl(3)
+        U.lib().wctb200_debug_set_conv_impl(2)
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
     # impl 1 accumulates the whole K loop in TMEM: the tensor core adds into its fp32 accumulator

@@ -30,4 +30,4 @@ for cluster in (1, 2):
             bad = int((~np.isfinite(got)).sum())
             print("cluster=%d bo=%d case=%s rc=%d dev=%d maxrel=%.2e nonfinite=%d" % (cluster, bo, case, rc, dev_rc, np.nanmax(err), bad), flush=True)
 lib.wctb200_debug_set_conv3(2, 0)
-lib.wctb200_debug_set_conv_impl(3)
+lib.wctb200_debug_set_conv_impl(2)

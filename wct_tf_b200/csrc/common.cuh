@@ -133,6 +133,52 @@ __device__ __forceinline__ void load8(const __half* __restrict__ act, const ActG
 }
 
 // ---------------------------------------------------------------------------
+// Coalesced tile store for the GEMM epilogues.  Each epilogue thread owns one output
+// position (row) and NACC consecutive channels in registers.  Writing them directly puts
+// 16-byte fragments 128+ bytes apart (ncu: 27 half-filled sectors per store request, the
+// 64-channel convs were bound by L2 write requests).  Instead every warp transposes
+// 64 channels at a time through an 8 KB shared-memory staging buffer (XOR-swizzled, conflict
+// free) so that 8 consecutive lanes write one position's 128 contiguous bytes per plane.
+//   stg: this warp's private 8 KB buffer; sbias: bias of acc[0..NACC); cbase: channel of acc[0]
+// ---------------------------------------------------------------------------
+template <int NACC>
+__device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const float* __restrict__ sbias, bool relu,
+                                                uint8_t* __restrict__ stg, int lane, bool valid, int n, int y, int x,
+                                                __half* __restrict__ out, const ActGeom& go, int cbase) {
+    const int packed = valid ? ((y << 16) | x) : -1;
+#pragma unroll
+    for (int h = 0; h < NACC / 64; ++h) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = acc[h * 64 + q * 8 + j] + sbias[h * 64 + q * 8 + j];
+                v[j] = relu ? fmaxf(t, 0.f) : t;
+            }
+            Half8 hi, lo;
+            split8(v, hi, lo);
+            const int slot = q ^ (lane & 7);
+            *reinterpret_cast<Half8*>(stg + (lane * 8 + slot) * 16) = hi;
+            *reinterpret_cast<Half8*>(stg + 4096 + (lane * 8 + slot) * 16) = lo;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = j * 4 + (lane >> 3);
+            const int c = lane & 7;
+            const int info = __shfl_sync(0xffffffffu, packed, row);
+            const int nn = __shfl_sync(0xffffffffu, n, row);
+            const int slot = c ^ (row & 7);
+            const Half8 hi = *reinterpret_cast<const Half8*>(stg + (row * 8 + slot) * 16);
+            const Half8 lo = *reinterpret_cast<const Half8*>(stg + 4096 + (row * 8 + slot) * 16);
+            if (info >= 0) store8_with_halo(out, go, nn, info >> 16, info & 0xffff, cbase + h * 64 + c * 8, hi, lo);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier / TMA / tcgen05 (sm_100a)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -238,7 +238,8 @@ struct Conv2Cfg {
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int NACC = BN / (EPI_WARPS / 4);           // accumulators per epilogue thread (<= 128)
     static constexpr int AUX_BYTES = 256 + BN * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+    static constexpr int STG_BYTES = BN <= 128 ? 4 * 8192 : 0;  // per-epilogue-warp store staging (coalesced stores)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + STG_BYTES + 1024;
 };
 
 struct TileCoord {
@@ -432,7 +433,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 y = yy - 1;
                 x = xx - 1;
             }
-            if (valid && !*abort_flag) {
+            if (Cfg::STG_BYTES > 0) {
+                uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
+                store_tile_rows<Cfg::NACC>(acc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
+                                           tc.n0 + colbase);
+            } else if (valid && !*abort_flag) {
 #pragma unroll
                 for (int q = 0; q < Cfg::NACC / 8; ++q) {
                     float v[8];
@@ -529,7 +534,7 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
 }
 
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
-int g_conv_impl = 3;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu)
+int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu)
 
 int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
                        int flags, __half* out, int bn_override, cudaStream_t st);

@@ -92,9 +92,10 @@ struct Conv3Cfg {
     static constexpr int TMEM_COLS = NBUF * BN;
     static constexpr int CH = 4;
     static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
-    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int THREADS = 96 + 32 * EPI_WARPS;    // + TMA-A producer warp (last warp)
     static constexpr int NACC = BN / (EPI_WARPS / 4);
     static constexpr int AUX_BYTES = 512 + BN * 4;
+    static constexpr int STG_BYTES = 4 * 8192;              // per-epilogue-warp store staging
     static constexpr int MAX_B_STAGES = 6;
 };
 
@@ -185,8 +186,38 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int total_q = m_pairs * p.n_tiles;
 
     if (warp == 0) {
+        // ---- TMA producer, weights (B): one [BN x 64] tile pair per (slice, tap) ----
         if (lane == 0) {
-            uint32_t ia = 0, ib = 0;
+            uint32_t ib = 0;
+            for (int q = cid; q < total_q; q += num_clusters) {
+                const int n0 = (q % p.n_tiles) * BN;
+                for (int ks = 0; ks < ksl; ++ks) {
+                    for (int tap = 0; tap < 9; ++tap, ++ib) {
+                        const int sb = ib % p.nb_stages;
+                        mbar_wait(&emptyB[sb], ((ib / p.nb_stages) & 1) ^ 1u, abort_flag, p.err, 0x120u + sb);
+                        uint8_t* sbp = b_base + sb * Cfg::B_STAGE;
+                        mbar_arrive_expect_tx(&fullB[sb], Cfg::B_STAGE);
+                        const int kc = tap * p.Cin + ks * 64;
+                        if (p.cluster > 1) {
+                            // this CTA fetches rows [crank*BN/2, +BN/2) of the tile and multicasts them to both CTAs
+                            const int half = BN / 2;
+                            const int ro = (int)crank * half;
+                            tma_load_3d_mc(sbp + ro * 128, &mapB, &fullB[sb], kc, n0 + ro, 0, mc_mask);
+                            tma_load_3d_mc(sbp + Cfg::B_BYTES + ro * 128, &mapB, &fullB[sb], kc, n0 + ro, 1, mc_mask);
+                        } else {
+                            tma_load_3d(sbp, &mapB, &fullB[sb], kc, n0, 0);
+                            tma_load_3d(sbp + Cfg::B_BYTES, &mapB, &fullB[sb], kc, n0, 1);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2 + Cfg::EPI_WARPS) {
+        // ---- TMA producer, activations (A): its own warp so the next patch is requested as soon
+        //      as its stage is free instead of queueing behind nine weight loads ----
+        if (lane == 0) {
+            uint32_t ia = 0;
             for (int q = cid; q < total_q; q += num_clusters) {
                 const Tile3 t = tile3(p, (q / p.n_tiles) * p.cluster + (int)crank, q % p.n_tiles, BN);
                 for (int ks = 0; ks < ksl; ++ks, ++ia) {
@@ -204,23 +235,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         tma_load_3d(st + hb, &mapA, &fullA[sa], ks * 64, row + p.box_rows, 0);
                         tma_load_3d(st + p.a_plane_bytes, &mapA, &fullA[sa], ks * 64, row, 1);
                         tma_load_3d(st + p.a_plane_bytes + hb, &mapA, &fullA[sa], ks * 64, row + p.box_rows, 1);
-                    }
-                    for (int tap = 0; tap < 9; ++tap, ++ib) {
-                        const int sb = ib % p.nb_stages;
-                        mbar_wait(&emptyB[sb], ((ib / p.nb_stages) & 1) ^ 1u, abort_flag, p.err, 0x120u + sb);
-                        uint8_t* sbp = b_base + sb * Cfg::B_STAGE;
-                        mbar_arrive_expect_tx(&fullB[sb], Cfg::B_STAGE);
-                        const int kc = tap * p.Cin + ks * 64;
-                        if (p.cluster > 1) {
-                            // this CTA fetches rows [crank*BN/2, +BN/2) of the tile and multicasts them to both CTAs
-                            const int half = BN / 2;
-                            const int ro = (int)crank * half;
-                            tma_load_3d_mc(sbp + ro * 128, &mapB, &fullB[sb], kc, t.n0 + ro, 0, mc_mask);
-                            tma_load_3d_mc(sbp + Cfg::B_BYTES + ro * 128, &mapB, &fullB[sb], kc, t.n0 + ro, 1, mc_mask);
-                        } else {
-                            tma_load_3d(sbp, &mapB, &fullB[sb], kc, t.n0, 0);
-                            tma_load_3d(sbp + Cfg::B_BYTES, &mapB, &fullB[sb], kc, t.n0, 1);
-                        }
                     }
                 }
             }
@@ -333,20 +347,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     x = xx - 1;
                 }
             }
-            if (valid && !*abort_flag) {
-#pragma unroll
-                for (int qd = 0; qd < Cfg::NACC / 8; ++qd) {
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float tt = acc[qd * 8 + j] + sbias[colbase + qd * 8 + j];
-                        v[j] = relu ? fmaxf(tt, 0.f) : tt;
-                    }
-                    Half8 hi, lo;
-                    split8(v, hi, lo);
-                    store8_with_halo(p.out, go, n, y, x, t.n0 + colbase + qd * 8, hi, lo);
-                }
-            }
+            store_tile_rows<Cfg::NACC>(acc, sbias + colbase, relu, aux + Cfg::AUX_BYTES + e * 8192, lane, valid && !*abort_flag,
+                                       n, y, x, p.out, go, t.n0 + colbase);
         }
     }
     tc_fence_before();
@@ -442,6 +444,7 @@ int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __h
     p.bo_mode = g_conv3_bo_mode;
     int BN = Cout % 128 == 0 ? 128 : 64;
     if (bn_override && Cout % bn_override == 0 && bn_override <= 128) BN = bn_override;
+    else if (BN == 128 && W <= 64 && W > 40) BN = 64;   // big FLAT patch: 64-wide weight tiles keep >= 5 B stages in flight
     if (p.cluster > 1 && BN / 2 < 8) p.cluster = 1;
     p.n_tiles = Cout / BN;
 
@@ -487,7 +490,7 @@ int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __h
     }
     // shared memory: 2 A stages + as many B stages as fit (<= 6)
     const int b_stage = 2 * BN * 128;
-    const int aux = 512 + BN * 4 + 1024;
+    const int aux = 512 + BN * 4 + 4 * 8192 + 1024;
     const int budget = 227 * 1024 - aux - 2 * 2 * p.a_plane_bytes;
     int nb = budget / b_stage;
     if (nb > 6) nb = 6;
