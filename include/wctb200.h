@@ -119,6 +119,19 @@ WCTB200_API int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc,
                       const void* style, int Ns, int Hs, int Ws, int C,
                       float alpha, float eps_cov, float eps_eig, float thresh, int readd_content_mean,
                       void* out, int32_t* k_out, void* ws, size_t ws_bytes, void* stream);
+/* Split form of wctb200_wct_level (same arithmetic, same semantics flags): the style side --
+ * means, covariance, eigendecomposition and colouring matrix C_s = E_s D_s^1/2 E_s^T of
+ * ops.py:48-55,76 -- depends only on the style features, so a host can run it on a second
+ * stream (it overlaps the content convolutions) or cache it for a batch that shares one style.
+ * `state`: device buffer of wctb200_wct_style_state_bytes(C, Ns) bytes.  Workspace sizes:
+ * wctb200_wct_workspace_bytes(C, Nc, Ns) is enough for either call. */
+WCTB200_API size_t wctb200_wct_style_state_bytes(int C, int Ns);
+WCTB200_API int wctb200_wct_style_prepare(const void* style, int Ns, int Hs, int Ws, int C,
+                              float eps_cov, float eps_eig, float thresh,
+                              void* state, void* ws, size_t ws_bytes, void* stream);
+WCTB200_API int wctb200_wct_apply(const void* content, int Nc, int Hc, int Wc, int C, const void* state, int Ns,
+                      float alpha, float eps_cov, float eps_eig, float thresh, int readd_content_mean,
+                      void* out, int32_t* k_out, void* ws, size_t ws_bytes, void* stream);
 /* AdaIN (ops.py:282-294): biased per-channel moments of content and style,
  * y = (x-mc)*rsqrt(vc+eps)*sqrt(vs)+ms, out = alpha*y + (1-alpha)*x. */
 WCTB200_API int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc,

@@ -125,3 +125,27 @@ def test_adain_level(c, alpha):
     for i in range(2):
         ref = ref_ops.adain(U.split_repr(content[i:i + 1]), U.split_repr(style), alpha)
         assert np.abs(got[i:i + 1] - ref).max() <= 2e-5 * (1 + np.abs(ref).max())
+
+
+def test_split_style_prepare_and_apply_equals_combined_level():
+    """wctb200_wct_style_prepare + wctb200_wct_apply (two-stream form) == wctb200_wct_level."""
+    g = np.load(GOLDEN[3])
+    content = np.concatenate([g["content"], g["content"][:, ::-1]]).astype(np.float32)
+    style = g["style"].astype(np.float32)
+    nc, hc, wc, c = content.shape
+    ns, hs, ws_, _ = style.shape
+    ref, kref = _run_wct(content, style, 0.7, "tf")
+    lib = U.lib()
+    cin, sin = U.act_from_numpy(content), U.act_from_numpy(style)
+    out = U.act_alloc(nc, hc, wc, c)
+    ws = torch.empty(lib.wctb200_wct_workspace_bytes(c, nc, ns), dtype=torch.uint8, device="cuda")
+    state = torch.empty(lib.wctb200_wct_style_state_bytes(c, ns), dtype=torch.uint8, device="cuda")
+    kbuf = torch.zeros(2 * (nc + ns), dtype=torch.int32, device="cuda")
+    _capi.check(lib.wctb200_wct_style_prepare(sin.data_ptr(), ns, hs, ws_, c, 1e-8, 0.0, 1e-5, state.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), U.stream()))
+    _capi.check(lib.wctb200_wct_apply(cin.data_ptr(), nc, hc, wc, c, state.data_ptr(), ns, 0.7, 1e-8, 0.0, 1e-5, 1,
+                                      out.data_ptr(), kbuf.data_ptr(), ws.data_ptr(), ws.numel(), U.stream()))
+    U.check_device()
+    got = U.act_to_numpy(out, nc, hc, wc, c)
+    assert np.array_equal(kbuf.cpu().numpy()[: nc + ns], kref[: nc + ns])
+    assert np.abs(got - ref).max() <= 2e-5

@@ -34,6 +34,9 @@ SIGNATURES = {
     "wctb200_upsample2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "wctb200_wct_workspace_bytes": (_sz, [_i, _i, _i]),
     "wctb200_wct_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "wctb200_wct_style_state_bytes": (_sz, [_i, _i]),
+    "wctb200_wct_style_prepare": (_i, [_vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _sz, _vp]),
+    "wctb200_wct_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "wctb200_adain_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wctb200_debug_set_conv_bn": (_i, [_i]),

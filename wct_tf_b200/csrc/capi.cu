@@ -49,6 +49,10 @@ int launch_wct_level(const __half*, int, int, int, const __half*, int, int, int,
                      __half*, int32_t*, void*, size_t, cudaStream_t);
 int launch_adain_level(const __half*, int, int, int, const __half*, int, int, int, int, float, float, __half*, void*,
                        size_t, cudaStream_t);
+size_t wct_style_state_bytes(int, int);
+int launch_wct_style_prepare(const __half*, int, int, int, int, float, float, float, void*, void*, size_t, cudaStream_t);
+int launch_wct_apply(const __half*, int, int, int, int, const void*, int, float, float, float, float, int, __half*, int32_t*,
+                     void*, size_t, cudaStream_t);
 int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
 int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
@@ -167,6 +171,24 @@ int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc, const void* s
     WCTB_REQUIRE(geom_ok(Nc, Hc, Wc, C) && geom_ok(Ns, Hs, Ws, C), "wct_level: bad geometry");
     return launch_wct_level(HCP(content), Nc, Hc, Wc, HCP(style), Ns, Hs, Ws, C, alpha, eps_cov, eps_eig, thresh,
                             readd_content_mean, HP(out), k_out, ws, ws_bytes, ST(stream));
+}
+size_t wctb200_wct_style_state_bytes(int C, int Ns) {
+    if (C < 8 || Ns < 1) return 0;
+    return wct_style_state_bytes(C, Ns);
+}
+int wctb200_wct_style_prepare(const void* style, int Ns, int Hs, int Ws, int C, float eps_cov, float eps_eig, float thresh,
+                              void* state, void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(style && state && ws, "wct_style_prepare: null pointer");
+    WCTB_REQUIRE(geom_ok(Ns, Hs, Ws, C), "wct_style_prepare: bad geometry");
+    return launch_wct_style_prepare(HCP(style), Ns, Hs, Ws, C, eps_cov, eps_eig, thresh, state, ws, ws_bytes, ST(stream));
+}
+int wctb200_wct_apply(const void* content, int Nc, int Hc, int Wc, int C, const void* state, int Ns, float alpha,
+                      float eps_cov, float eps_eig, float thresh, int readd_content_mean, void* out, int32_t* k_out,
+                      void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(content && state && out && ws, "wct_apply: null pointer");
+    WCTB_REQUIRE(geom_ok(Nc, Hc, Wc, C), "wct_apply: bad geometry");
+    return launch_wct_apply(HCP(content), Nc, Hc, Wc, C, state, Ns, alpha, eps_cov, eps_eig, thresh, readd_content_mean,
+                            HP(out), k_out, ws, ws_bytes, ST(stream));
 }
 int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc, const void* style, int Ns, int Hs, int Ws, int C,
                         float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream) {

@@ -319,6 +319,70 @@ __device__ __forceinline__ void rot_regs(f32x2 (&x)[HP], f32x2 (&y)[HP], float& 
     b = fmaxf(fmaf(t, g, b), 0.f);
 }
 
+// Two INDEPENDENT rotations (x0,y0) and (x1,y1) fused and branch-free so their long
+// dependency chains (dot -> 5-step shuffle reduction -> MUFU chain -> rotation) interleave:
+// the kernel is latency bound (ncu: 38 % issue utilisation with 16 warps per SM), and the
+// early-exit branches of rot_regs() kept the compiler from overlapping the pair.
+__device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol, float& wmax, float& t, float& s,
+                                            float& cm1) {
+    const float ab = a * b;
+    const bool pos = ab > 0.f;
+    const float ratio = pos ? fabsf(g) * rsqrtf(ab) : 0.f;
+    wmax = fmaxf(wmax, ratio);
+    const bool rot = ratio > tol;
+    const float gs = rot ? g : 1.f;
+    const float zeta = __fdividef(b - a, 2.f * gs);
+    const float az = fabsf(zeta);
+    const float h2 = fmaf(zeta, zeta, 1.f);
+    float tt = __fdividef(copysignf(1.f, zeta), az + h2 * rsqrtf(h2));
+    if (az > 1e8f) tt = __fdividef(0.5f, zeta);            // asymptote; avoids zeta^2 overflow
+    tt = rot ? tt : 0.f;
+    const float h = fmaf(tt, tt, 1.f);
+    float r = rsqrtf(h);
+    r = r * fmaf(-0.5f * h, r * r, 1.5f);
+    t = tt;
+    s = tt * r;
+    cm1 = -__fdividef(tt * tt * r, fmaf(h, r, 1.f));
+}
+
+template <int HP>
+__device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], float& a0, float& b0, f32x2 (&x1)[HP],
+                                          f32x2 (&y1)[HP], float& a1, float& b1, float tol, float& wmax) {
+    f32x2 d00 = 0ull, d01 = 0ull, d10 = 0ull, d11 = 0ull;
+#pragma unroll
+    for (int i = 0; i < HP; ++i) {
+        if (i & 1) { d01 = fma2(x0[i], y0[i], d01); d11 = fma2(x1[i], y1[i], d11); }
+        else { d00 = fma2(x0[i], y0[i], d00); d10 = fma2(x1[i], y1[i], d10); }
+    }
+    float p0, p1, p2, p3, q0, q1, q2, q3;
+    unpack2(d00, p0, p1); unpack2(d01, p2, p3);
+    unpack2(d10, q0, q1); unpack2(d11, q2, q3);
+    float g0 = (p0 + p1) + (p2 + p3);
+    float g1 = (q0 + q1) + (q2 + q3);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    }
+    float t0, s0, c0, t1, s1, c1;
+    rot_scalars(g0, a0, b0, tol, wmax, t0, s0, c0);
+    rot_scalars(g1, a1, b1, tol, wmax, t1, s1, c1);
+    if (t0 != 0.f || t1 != 0.f) {          // warp-uniform: skip the FMAs only when BOTH pairs are already orthogonal
+        const f32x2 s20 = pack2(s0, s0), ns20 = pack2(-s0, -s0), c20 = pack2(c0, c0);
+        const f32x2 s21 = pack2(s1, s1), ns21 = pack2(-s1, -s1), c21 = pack2(c1, c1);
+#pragma unroll
+        for (int i = 0; i < HP; ++i) {
+            const f32x2 xa = x0[i], ya = y0[i], xb = x1[i], yb = y1[i];
+            x0[i] = fma2(c20, xa, fma2(ns20, ya, xa));
+            y0[i] = fma2(c20, ya, fma2(s20, xa, ya));
+            x1[i] = fma2(c21, xb, fma2(ns21, yb, xb));
+            y1[i] = fma2(c21, yb, fma2(s21, xb, yb));
+        }
+        a0 = fmaxf(fmaf(-t0, g0, a0), 0.f); b0 = fmaxf(fmaf(t0, g0, b0), 0.f);
+        a1 = fmaxf(fmaf(-t1, g1, a1), 0.f); b1 = fmaxf(fmaf(t1, g1, b1), 0.f);
+    }
+}
+
 template <int NN>
 __device__ __forceinline__ void load_col(const float* __restrict__ c, int lane, f32x2 (&r)[NN / 64]) {
     using Cfg = JacobiCfg<NN>;
@@ -429,10 +493,8 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                     load_col<NN>(cy0, lane, y0);
                     load_col<NN>(cy1, lane, y1);
                     float b0 = nrm[32 + 2 * j], b1 = nrm[32 + 2 * j + 1];
-                    rot_regs<HP>(x0, y0, a0, b0, tol, wmax);
-                    rot_regs<HP>(x1, y1, a1, b1, tol, wmax);
-                    rot_regs<HP>(x0, y1, a0, b1, tol, wmax);
-                    rot_regs<HP>(x1, y0, a1, b0, tol, wmax);
+                    rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol, wmax);
+                    rot_regs2<HP>(x0, y1, a0, b1, x1, y0, a1, b0, tol, wmax);
                     store_col<NN>(cy0, lane, y0);
                     store_col<NN>(cy1, lane, y1);
                     if (lane == 0) { nrm[32 + 2 * j] = b0; nrm[32 + 2 * j + 1] = b1; }
@@ -801,6 +863,119 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     rc = launch_conv3x3_tc(content, Nc, Hc, Wc, C, Msplit, 1, Nc, bias, C, 0, out, st);
     if (rc) return rc;
     if (k_out) WCTB_CUDA(cudaMemcpyAsync(k_out, kc, (size_t)np * 2 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Split form of the level transform: the style side (means, covariance, eigendecomposition,
+// colouring matrix C_s) depends only on the style features, so the host runs it on a second
+// stream where it overlaps the content encoder/decoder convolutions (the Jacobi kernel is
+// latency bound and leaves the tensor cores idle), and caches it when a batch shares a style.
+//   state layout: [Ns][C] mean_s | [Ns][C][C] C_s | [2*Ns] int32 (k_s, sweeps)
+// ---------------------------------------------------------------------------
+static size_t style_state_offsets(int C, int Ns, size_t* off_cs, size_t* off_k) {
+    size_t o = align_up((size_t)Ns * C * 4, 256);
+    *off_cs = o;
+    o = align_up(o + (size_t)Ns * C * C * 4, 256);
+    *off_k = o;
+    return align_up(o + (size_t)Ns * 2 * 4, 256);
+}
+size_t wct_style_state_bytes(int C, int Ns) {
+    size_t a, b;
+    return style_state_offsets(C, Ns, &a, &b);
+}
+
+int launch_wct_style_prepare(const __half* style, int Ns, int Hs, int Ws, int C, float eps_cov, float eps_eig, float thresh,
+                             void* state, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "wct_style_prepare: C=%d not in {64,128,256,512}", C);
+    const WctWs L = wct_layout(C, 0, Ns);
+    if (ws_bytes < L.total) {
+        set_error("wct_style_prepare: workspace %zu < %zu bytes", ws_bytes, L.total);
+        return WCTB200_EWS;
+    }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    size_t off_cs, off_k;
+    style_state_offsets(C, Ns, &off_cs, &off_k);
+    uint8_t* sp = static_cast<uint8_t*>(state);
+    float* mean_s = reinterpret_cast<float*>(sp);
+    float* Cs = reinterpret_cast<float*>(sp + off_cs);
+    int* kc = reinterpret_cast<int*>(sp + off_k);
+    double* sum = reinterpret_cast<double*>(w + L.sum);
+    double* cov = reinterpret_cast<double*>(w + L.cov);
+    float* G = reinterpret_cast<float*>(w + L.G);
+    float* sigma = reinterpret_cast<float*>(w + L.sigma);
+    float* dvec = reinterpret_cast<float*>(w + L.dvec);
+    float* conv = reinterpret_cast<float*>(w + L.conv);
+    const long long CC = (long long)C * C;
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
+    WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Ns * 2 * 4, st));
+    int rc = stats_and_cov(style, ActGeom(Ns, Hs, Ws, C), sum, cov, mean_s, G, eps_cov, st);
+    if (rc) return rc;
+    rc = launch_jacobi(G, C, Ns, conv, kc + Ns, st);
+    if (rc) return rc;
+    rc = launch_eig_post(G, C, Ns, thresh, eps_eig, /*n_content=*/0, sigma, dvec, kc, st);
+    if (rc) return rc;
+    dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Ns);
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Cs, CC, C);
+    WCTB_CHECK_LAUNCH("k_outer_gemm(Cs)");
+    return 0;
+}
+
+int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const void* state, int Ns, float alpha,
+                     float eps_cov, float eps_eig, float thresh, int readd, __half* out, int32_t* k_out, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+    WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "wct_apply: C=%d not in {64,128,256,512}", C);
+    WCTB_REQUIRE(Ns == 1 || Ns == Nc, "wct_apply: Ns must be 1 or Nc");
+    const WctWs L = wct_layout(C, Nc, 0);
+    if (ws_bytes < L.total) {
+        set_error("wct_apply: workspace %zu < %zu bytes", ws_bytes, L.total);
+        return WCTB200_EWS;
+    }
+    uint8_t* w = static_cast<uint8_t*>(ws);
+    size_t off_cs, off_k;
+    style_state_offsets(C, Ns, &off_cs, &off_k);
+    const uint8_t* sp = static_cast<const uint8_t*>(state);
+    const float* mean_s = reinterpret_cast<const float*>(sp);
+    const float* Cs = reinterpret_cast<const float*>(sp + off_cs);
+    const int* ks = reinterpret_cast<const int*>(sp + off_k);
+    double* sum = reinterpret_cast<double*>(w + L.sum);
+    double* cov = reinterpret_cast<double*>(w + L.cov);
+    float* mean = reinterpret_cast<float*>(w + L.mean);
+    float* G = reinterpret_cast<float*>(w + L.G);
+    float* sigma = reinterpret_cast<float*>(w + L.sigma);
+    float* dvec = reinterpret_cast<float*>(w + L.dvec);
+    float* Wcm = reinterpret_cast<float*>(w + L.Wc);
+    float* T = reinterpret_cast<float*>(w + L.T);
+    __half* Msplit = reinterpret_cast<__half*>(w + L.Msplit);
+    float* bias = reinterpret_cast<float*>(w + L.bias);
+    float* conv = reinterpret_cast<float*>(w + L.conv);
+    int* kc = reinterpret_cast<int*>(w + L.kcount);
+    const long long CC = (long long)C * C;
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
+    WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Nc * 2 * 4, st));
+    int rc = stats_and_cov(content, ActGeom(Nc, Hc, Wc, C), sum, cov, mean, G, eps_cov, st);
+    if (rc) return rc;
+    rc = launch_jacobi(G, C, Nc, conv, kc + Nc, st);
+    if (rc) return rc;
+    rc = launch_eig_post(G, C, Nc, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    if (rc) return rc;
+    dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Nc);
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C);
+    WCTB_CHECK_LAUNCH("k_outer_gemm(Wc)");
+    k_outer_gemm<<<gg, 256, 0, st>>>(Cs, Ns == 1 ? 0 : CC, Wcm, CC, nullptr, 0, T, CC, C);   // T = C_s W_c
+    WCTB_CHECK_LAUNCH("k_outer_gemm(T)");
+    dim3 gf((unsigned)cdiv(C, 8), (unsigned)Nc);
+    k_finalize_transform<<<gf, 256, 0, st>>>(T, C, Nc, Ns, alpha, readd, mean, mean_s, Msplit, bias);
+    WCTB_CHECK_LAUNCH("k_finalize_transform");
+    rc = launch_conv3x3_tc(content, Nc, Hc, Wc, C, Msplit, 1, Nc, bias, C, 0, out, st);
+    if (rc) return rc;
+    if (k_out) {
+        // k_out: [k_c x Nc | k_s x Ns | sweeps_c x Nc | sweeps_s x Ns]  (same order as wct_level)
+        WCTB_CUDA(cudaMemcpyAsync(k_out, kc, (size_t)Nc * 4, cudaMemcpyDeviceToDevice, st));
+        WCTB_CUDA(cudaMemcpyAsync(k_out + Nc, ks, (size_t)Ns * 4, cudaMemcpyDeviceToDevice, st));
+        WCTB_CUDA(cudaMemcpyAsync(k_out + Nc + Ns, kc + Nc, (size_t)Nc * 4, cudaMemcpyDeviceToDevice, st));
+        WCTB_CUDA(cudaMemcpyAsync(k_out + 2 * Nc + Ns, ks + Ns, (size_t)Ns * 4, cudaMemcpyDeviceToDevice, st));
+    }
     return 0;
 }
 

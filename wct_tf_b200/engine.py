@@ -43,6 +43,8 @@ class Engine(object):
         self.semantics = semantics
         self.last_info = None
         self._ws = {}
+        self.overlap_style = True  # run the style side (encode + per-level eigendecompositions) on a second stream
+        self._style_stream = None
         self.launches = 0          # kernels launched through the C-ABI (bench.py "gpu_launches")
         self.profile = None        # optional dict: key -> [torch.cuda.Event pairs, flops, bytes]
         with torch.cuda.device(self.device):
@@ -218,6 +220,34 @@ class Engine(object):
                    bytes_=4.0 * C * (2 * content.N * hwc + style.N * hws))
         return out, kbuf
 
+    def style_prepare(self, style):
+        """Style side of one level (ops.py:48-55,76): means, covariance, eigendecomposition, C_s.
+        Returns the device state buffer consumed by ``wct_apply``."""
+        st = self._stream()
+        sem = SEMANTICS[self.semantics]
+        C = style.C
+        state = torch.empty(self.lib.wctb200_wct_style_state_bytes(C, style.N), dtype=torch.uint8, device=self.device)
+        ws = self._workspace(C, 0, style.N)
+        hws = style.H * style.W
+        self._call("wct_style[C%d]" % C, 7, self.lib.wctb200_wct_style_prepare, style.ptr, style.N, style.H, style.W, C,
+                   sem["eps_cov"], sem["eps_eig"], sem["thresh"], state.data_ptr(), ws.data_ptr(), ws.numel(), st,
+                   flops=2.0 * C * C * style.N * hws, bytes_=4.0 * C * style.N * hws)
+        return state
+
+    def wct_apply(self, content, state, n_style, alpha, want_info=False):
+        st = self._stream()
+        sem = SEMANTICS[self.semantics]
+        C = content.C
+        out = self._act(content.N, content.H, content.W, C)
+        ws = self._workspace(C, content.N, 0)
+        kbuf = torch.empty(2 * (content.N + n_style), dtype=torch.int32, device=self.device) if want_info else None
+        hwc = content.H * content.W
+        self._call("wct_level[C%d]" % C, 9, self.lib.wctb200_wct_apply, content.ptr, content.N, content.H, content.W, C,
+                   state.data_ptr(), n_style, float(alpha), sem["eps_cov"], sem["eps_eig"], sem["thresh"], sem["readd"],
+                   out.ptr, kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st,
+                   flops=2.0 * C * C * 2 * content.N * hwc, bytes_=4.0 * C * 2 * content.N * hwc)
+        return out, kbuf
+
     # ------------------------------------------------------------------ pipeline
     def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None):
         """content_u8: cuda uint8 [N,H,W,3]; style_u8: cuda uint8 [Ns,Hs,Ws,3], Ns in {1, N}.
@@ -228,17 +258,41 @@ class Engine(object):
         assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
         assert style_u8.shape[0] in (1, N)
         content = torch.empty(content_u8.shape, dtype=torch.float32, device=self.device)
-        style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
         self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st)
-        self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(), st)
-        # model.py:70-72: one style pass emitting every target
-        _, style_feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
+        main = torch.cuda.current_stream(self.device)
+        split = not adain                      # WCT: style side on its own stream; AdaIN: cheap, keep it inline
+        side = main
+        if split and self.overlap_style:
+            if self._style_stream is None:
+                self._style_stream = torch.cuda.Stream(device=self.device)
+            side = self._style_stream
+            side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
+        style_states, style_events, style_feats = {}, {}, None
+        with torch.cuda.stream(side):
+            style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
+            self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(),
+                       self._stream())
+            # model.py:70-72: one style pass emitting every target
+            _, style_feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
+            if split:
+                for relu in self.model.style_taps:
+                    if relu not in style_states:
+                        style_states[relu] = self.style_prepare(style_feats[relu])
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        style_events[relu] = ev
         infos = []
         x = content
         nlev = len(self.model.levels)
+        n_style = style_u8.shape[0]
         for lvl in self.model.levels:
             cf, _ = self.encode(x, lvl.relu_target)
-            f, kbuf = self.transform(cf, style_feats[lvl.relu_target], alpha, adain, want_info)
+            if split:
+                if side is not main:
+                    main.wait_event(style_events[lvl.relu_target])
+                f, kbuf = self.wct_apply(cf, style_states[lvl.relu_target], n_style, alpha, want_info)
+            else:
+                f, kbuf = self.transform(cf, style_feats[lvl.relu_target], alpha, adain, want_info)
             infos.append(kbuf)
             if capture is not None:
                 capture.setdefault("level_input", []).append(x)
@@ -248,6 +302,9 @@ class Engine(object):
             x = self.decode(f, lvl.index, clip=(lvl.index < nlev - 1))
             if capture is not None:
                 capture.setdefault("level_output", []).append(x)
+        if side is not main:
+            side.wait_stream(main)             # buffers handed across streams may be recycled only after both are done
+            main.wait_stream(side)
         if want_info:
             self.last_info = infos
         return x
