@@ -161,7 +161,7 @@ int wctb200_upsample2(const void* act_in, int N, int H, int W, int C, void* act_
 }
 
 size_t wctb200_wct_workspace_bytes(int C, int Nc, int Ns) {
-    if (C < 8 || Nc < 1 || Ns < 1) return 0;
+    if (C < 8 || Nc < 0 || Ns < 0 || Nc + Ns < 1) return 0;     // Nc = 0 / Ns = 0: style-only / content-only calls
     return wct_workspace_bytes(C, Nc, Ns);
 }
 int wctb200_wct_level(const void* content, int Nc, int Hc, int Wc, const void* style, int Ns, int Hs, int Ws, int C,
