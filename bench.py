@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--adain", action="store_true", help="config 5: AdaIN instead of WCT")
+    ap.add_argument("--oversub", type=int, default=0, help="tuning: conv CTAs per SM (0 = library default)")
+    ap.add_argument("--no-overlap", action="store_true", help="tuning: run the style side on the main stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -194,6 +196,10 @@ def main():
     weights = make_synthetic_weights(42)
     wct = WCT(relu_targets=TARGETS, device="cuda:%d" % local, weights=weights, semantics=SEMANTICS)
     eng = wct.engine
+    if args.oversub:
+        eng.lib.wctb200_debug_set_conv_oversub(args.oversub)
+    if args.no_overlap:
+        eng.overlap_style = False
 
     # distinct frames per rank (frame-sharded batch); two input sets rotated between steps
     sets = []
@@ -258,7 +264,7 @@ def main():
     for i in range(2):
         step_resident(i)
     torch.cuda.synchronize(dev)
-    eng.overlap_style = True
+    eng.overlap_style = not args.no_overlap
     prof = {}
     for key, rec in eng.profile.items():
         ms = sum(a.elapsed_time(b) for a, b in rec["events"])

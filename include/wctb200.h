@@ -151,6 +151,8 @@ WCTB200_API int wctb200_debug_set_conv_bn(int bn);
  * accumulation, 3 = 2 + on-chip tap reuse of the activation patch and cluster-multicast weights.
  * Returns the implementation now selected. */
 WCTB200_API int wctb200_debug_set_conv_impl(int impl);
+/* impl 2: CTAs per SM in the persistent grid (default 4; 1 = exactly one CTA per SM). */
+WCTB200_API int wctb200_debug_set_conv_oversub(int k);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
 WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 

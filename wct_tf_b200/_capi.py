@@ -42,6 +42,7 @@ SIGNATURES = {
     "wctb200_debug_set_conv_bn": (_i, [_i]),
     "wctb200_debug_set_conv_impl": (_i, [_i]),
     "wctb200_debug_set_conv3": (_i, [_i, _i]),
+    "wctb200_debug_set_conv_oversub": (_i, [_i]),
 }
 
 _lib = None

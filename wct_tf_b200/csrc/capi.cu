@@ -59,6 +59,7 @@ extern int g_conv_bn_override;
 extern int g_conv_impl;
 extern int g_conv3_cluster;
 extern int g_conv3_bo_mode;
+extern int g_conv_oversub;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
 static bool geom_ok(int N, int H, int W, int C) {
@@ -217,6 +218,10 @@ int wctb200_debug_set_conv_bn(int bn) {
 int wctb200_debug_set_conv_impl(int impl) {
     if (impl >= 1 && impl <= 3) g_conv_impl = impl;
     return g_conv_impl;
+}
+int wctb200_debug_set_conv_oversub(int k) {
+    g_conv_oversub = k < 1 ? 1 : (k > 16 ? 16 : k);
+    return g_conv_oversub;
 }
 int wctb200_debug_set_conv3(int cluster, int bo_mode) {
     g_conv3_cluster = cluster == 1 ? 1 : 2;

@@ -514,6 +514,8 @@ static int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPar
     return 0;
 }
 
+int g_conv_oversub = 4;
+
 template <int BN>
 static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_tiles, int n_tiles,
                       cudaStream_t st) {
@@ -527,7 +529,12 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
         WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
-    const int grid = total_tiles < sms ? total_tiles : sms;
+    // Over-subscribed persistent grid: with g_conv_oversub x #SMs CTAs (1 resident per SM) the
+    // hardware block scheduler hands queued CTAs to whichever SMs are free, so a conv launched
+    // while the Jacobi clusters of the other stream hold half the SMs still balances its tiles
+    // (a grid of exactly #SMs would run as two unbalanced waves).
+    int grid = sms * (g_conv_oversub > 0 ? g_conv_oversub : 1);
+    if (grid > total_tiles) grid = total_tiles;
     conv_tc2_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p, total_tiles, n_tiles);
     WCTB_CHECK_LAUNCH("conv_tc2_kernel");
     return 0;
