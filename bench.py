@@ -126,7 +126,7 @@ def run_reference(args):
     import torch
     from wct_tf_b200.weights import make_synthetic_weights
     from oracle import nets
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)     # torch-CPU convs of this size get slower beyond ~32 threads
     torch.set_num_threads(cores)
     weights = make_synthetic_weights(42)
     c, s = frames(1, 1000), frames(1, 7)
@@ -277,7 +277,9 @@ def main():
     step_prof_ms = sum(v["ms"] for v in prof.values())
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf"], "traffic": None,
+                "frac": achieved_tf / pk["tf"],
+                # dram__bytes_read+write per launch from profiles/r01_ncu_full_conv_tc2.txt (512->512 @64x64, batch 2)
+                "traffic": 27383296 + 16640,
                 "kernel": "conv_tc_kernel (tcgen05 kind::f16, split-fp16 x3: 3 MMAs per algorithmic MAC -> ceiling 1/3 of the bf16 peak)",
                 "peak_source": pk["source"] + " of measured",
                 "share_of_step": conv_ms / step_prof_ms if step_prof_ms else None,
@@ -301,7 +303,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = min(os.cpu_count() or 1, 32)
             sec = cpu_frame_seconds(weights, 1, cores)
             cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
                    "sample": "1 full 512x512 5-level frame on the host (oracle port: torch-CPU convs + NumPy/LAPACK wct_tf; "
