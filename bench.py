@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--adain", action="store_true", help="config 5: AdaIN instead of WCT")
     ap.add_argument("--oversub", type=int, default=0, help="tuning: conv CTAs per SM (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the style side on the main stream")
+    ap.add_argument("--groups", type=int, default=2, help="sub-batches per step run as independent stream pairs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -200,6 +201,7 @@ def main():
         eng.lib.wctb200_debug_set_conv_oversub(args.oversub)
     if args.no_overlap:
         eng.overlap_style = False
+    eng.groups = max(1, args.groups)
 
     # distinct frames per rank (frame-sharded batch); two input sets rotated between steps
     sets = []
@@ -260,11 +262,13 @@ def main():
     # (style/content stream overlap is switched off for these two steps so that an event-bracketed
     #  duration is the kernel's own time, not its time while sharing SMs with the Jacobi kernels)
     eng.profile = {}
+    eng.groups = 1
     eng.overlap_style = False
     for i in range(2):
         step_resident(i)
     torch.cuda.synchronize(dev)
     eng.overlap_style = not args.no_overlap
+    eng.groups = max(1, args.groups)
     prof = {}
     for key, rec in eng.profile.items():
         ms = sum(a.elapsed_time(b) for a, b in rec["events"])
@@ -321,7 +325,7 @@ def main():
                        "style": "one distinct style per frame, re-encoded every step (no caching)",
                        "l2": "two input sets alternate; per-step activation working set (>5 GB) >> 126 MB L2",
                        "precision": "fp32 semantics: split-fp16 x3 on tcgen05, fp32 accumulate",
-                       "streams": "style side (encode + eigendecompositions) on a second CUDA stream"},
+                       "streams": "%d sub-batch group(s) per step, each a (content, style) stream pair" % eng.groups},
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(2 * B * SIZE * SIZE * 3), "d2h_bytes_per_step": int(B * SIZE * SIZE * 3)},
             "gpu_launches": int(launches),

@@ -44,7 +44,10 @@ class Engine(object):
         self.last_info = None
         self._ws = {}
         self.overlap_style = True  # run the style side (encode + per-level eigendecompositions) on a second stream
-        self._style_stream = None
+        self.groups = 1            # >1: split a batch into sub-batches that run as independent stream-pairs
+        self._group = 0
+        self._style_streams = {}
+        self._group_streams = {}
         self.launches = 0          # kernels launched through the C-ABI (bench.py "gpu_launches")
         self.profile = None        # optional dict: key -> [torch.cuda.Event pairs, flops, bytes]
         with torch.cuda.device(self.device):
@@ -129,7 +132,7 @@ class Engine(object):
         return Act(torch.empty(nbytes, dtype=torch.uint8, device=self.device), N, H, W, C)
 
     def _workspace(self, C, Nc, Ns):
-        key = (C, Nc, Ns)
+        key = (self._group, C, Nc, Ns)    # concurrent groups (streams) must not share scratch
         ws = self._ws.get(key)
         if ws is None:
             ws = torch.empty(self.lib.wctb200_wct_workspace_bytes(C, Nc, Ns), dtype=torch.uint8, device=self.device)
@@ -252,7 +255,40 @@ class Engine(object):
     def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None):
         """content_u8: cuda uint8 [N,H,W,3]; style_u8: cuda uint8 [Ns,Hs,Ws,3], Ns in {1, N}.
         Returns the float32 ``decoded_output`` [N,H',W',3] (unclipped, model.py:94).
-        ``capture`` (dict) receives every level's input image / features for parity tests."""
+        ``capture`` (dict) receives every level's input image / features for parity tests.
+
+        With ``self.groups`` = G > 1 the batch is cut into G sub-batches whose level chains are
+        enqueued on G independent stream pairs: frames are independent (wct.py:97-103), and the
+        eigendecompositions are latency bound on a few SMs, so one group's Jacobi clusters overlap the
+        other groups' convolutions (same arithmetic per frame; only the schedule changes)."""
+        N = content_u8.shape[0]
+        G = min(self.groups, N) if (capture is None and not want_info) else 1
+        if G > 1:
+            main = torch.cuda.current_stream(self.device)
+            bounds = [(g * N) // G for g in range(G + 1)]
+            outs = []
+            for g in range(G):
+                lo, hi = bounds[g], bounds[g + 1]
+                if g not in self._group_streams:
+                    self._group_streams[g] = torch.cuda.Stream(device=self.device)
+                gs = self._group_streams[g]
+                gs.wait_stream(main)
+                self._group = g + 1
+                try:
+                    with torch.cuda.stream(gs):
+                        sg = style_u8 if style_u8.shape[0] == 1 else style_u8[lo:hi]
+                        outs.append(self._stylize_one(content_u8[lo:hi], sg, alpha, adain, False, None))
+                finally:
+                    self._group = 0
+            for g in range(G):
+                main.wait_stream(self._group_streams[g])
+            out = torch.cat(outs, dim=0)
+            for g in range(G):                      # sub-batch buffers die here: their streams wait for the cat
+                self._group_streams[g].wait_stream(main)
+            return out
+        return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture)
+
+    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture):
         lib, st = self.lib, self._stream()
         N = content_u8.shape[0]
         assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
@@ -263,9 +299,9 @@ class Engine(object):
         split = not adain                      # WCT: style side on its own stream; AdaIN: cheap, keep it inline
         side = main
         if split and self.overlap_style:
-            if self._style_stream is None:
-                self._style_stream = torch.cuda.Stream(device=self.device)
-            side = self._style_stream
+            if self._group not in self._style_streams:
+                self._style_streams[self._group] = torch.cuda.Stream(device=self.device)
+            side = self._style_streams[self._group]
             side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
         style_states, style_events, style_feats = {}, {}, None
         with torch.cuda.stream(side):
