@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--oversub", type=int, default=0, help="tuning: conv CTAs per SM (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the style side on the main stream")
     ap.add_argument("--groups", type=int, default=2, help="sub-batches per step run as independent stream pairs")
+    ap.add_argument("--no-prio", action="store_true", help="tuning: all streams at the same priority")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -202,6 +203,7 @@ def main():
     if args.no_overlap:
         eng.overlap_style = False
     eng.groups = max(1, args.groups)
+    eng.group_priorities = not args.no_prio
 
     # distinct frames per rank (frame-sharded batch); two input sets rotated between steps
     sets = []

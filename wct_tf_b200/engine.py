@@ -45,6 +45,7 @@ class Engine(object):
         self._ws = {}
         self.overlap_style = True  # run the style side (encode + per-level eigendecompositions) on a second stream
         self.groups = 1            # >1: split a batch into sub-batches that run as independent stream-pairs
+        self.group_priorities = False
         self._group = 0
         self._style_streams = {}
         self._group_streams = {}
@@ -270,7 +271,10 @@ class Engine(object):
             for g in range(G):
                 lo, hi = bounds[g], bounds[g + 1]
                 if g not in self._group_streams:
-                    self._group_streams[g] = torch.cuda.Stream(device=self.device)
+                    # descending priority: group 0 runs "in the foreground", later groups fill the SMs it
+                    # leaves idle while its eigendecompositions are latency bound (self.group_priorities)
+                    prio = -1 if (self.group_priorities and g == 0) else 0
+                    self._group_streams[g] = torch.cuda.Stream(device=self.device, priority=prio)
                 gs = self._group_streams[g]
                 gs.wait_stream(main)
                 self._group = g + 1
@@ -300,7 +304,8 @@ class Engine(object):
         side = main
         if split and self.overlap_style:
             if self._group not in self._style_streams:
-                self._style_streams[self._group] = torch.cuda.Stream(device=self.device)
+                prio = -1 if (self.group_priorities and self._group <= 1) else 0
+                self._style_streams[self._group] = torch.cuda.Stream(device=self.device, priority=prio)
             side = self._style_streams[self._group]
             side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
         style_states, style_events, style_feats = {}, {}, None

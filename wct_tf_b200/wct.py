@@ -45,6 +45,8 @@ class WCT(object):
             from .weights import load_weights
             weights = load_weights(vgg_path, checkpoints, relu_targets)   # pairs checkpoints[i] <-> relu_targets[i] (wct.py:47)
         self.engine = Engine(weights, relu_targets, device=_torch_device(device), semantics=semantics)
+        self.engine.groups = 2                  # batches >= 2 frames run as two interleaved stream pairs
+        self.engine.group_priorities = True
         self.model = self.engine.model
 
     @staticmethod
