@@ -226,12 +226,9 @@ def main():
         return eng.to_u8(out)
 
     def step_e2e(i):
+        # the public API call a user makes: host (pinned) uint8 in, host (pinned) uint8 out, synchronous
         c, s = pin_sets[i % 2]
-        cd = c.to(dev, non_blocking=True)
-        sd = s.to(dev, non_blocking=True)
-        out = eng.to_u8(eng.stylize(cd, sd, alpha=ALPHA, adain=args.adain))
-        out_pin.copy_(out, non_blocking=True)
-        return out
+        return wct.predict_batch(c, s, alpha=ALPHA, adain=args.adain, out=out_pin)
 
     def timed(fn, steps, warmup):
         for i in range(warmup):

@@ -61,9 +61,11 @@ class WCT(object):
         """wct.py:66-68"""
         return np.uint8(np.clip(image, 0, 1) * 255)
 
-    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False):
-        """contents: uint8 [N,H,W,3]; styles: uint8 [1|N,Hs,Ws,3] (numpy or torch, host or device).
-        Returns uint8 [N,H',W',3] numpy (and the float image if return_float)."""
+    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False, out=None):
+        """contents: uint8 [N,H,W,3]; styles: uint8 [1|N,Hs,Ws,3] (numpy or torch; host buffers --
+        ideally pinned -- or device tensors).  Returns uint8 [N,H',W',3] on the host: a numpy array,
+        or ``out`` (a pinned uint8 torch tensor of the right shape) filled in place.  The call is
+        synchronous like the reference's ``sess.run`` (wct.py:97)."""
         eng = self.engine
         dev = eng.device
 
@@ -80,7 +82,13 @@ class WCT(object):
             c = to_dev(contents)
             s = to_dev(styles)
             out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
-            out_u8 = eng.to_u8(out_f).cpu().numpy()
+            out_dev = eng.to_u8(out_f)
+            if out is not None:
+                out.copy_(out_dev, non_blocking=True)
+                torch.cuda.current_stream(dev).synchronize()
+                out_u8 = out
+            else:
+                out_u8 = out_dev.cpu().numpy()
         if return_float:
             return out_u8, out_f.cpu().numpy()
         return out_u8
