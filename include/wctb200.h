@@ -139,6 +139,11 @@ WCTB200_API int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc,
                         float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Stand-alone pieces of the transform, exposed for parity tests and profiling:
+ * per-channel mean [N][C] and covariance [N][C][C] = fc fc^T/(HW-1) + eps_cov*I of a feature batch
+ * (ops.py:43-45,105-108), fp32 outputs. */
+WCTB200_API int wctb200_covariance(const void* act, int N, int H, int W, int C, float eps_cov, float* mean, float* cov,
+                       void* stream);
+/*
  * symmetric eigen-decomposition of `count` CxC fp32 matrices by one-sided Jacobi.
  * a: [count][C][C] symmetric (overwritten: column i becomes sigma_i * u_i),
  * sigma: [count][C] = |lambda_i|, sweeps: [count] (may be NULL). */
@@ -153,6 +158,9 @@ WCTB200_API int wctb200_debug_set_conv_bn(int bn);
 WCTB200_API int wctb200_debug_set_conv_impl(int impl);
 /* impl 2: CTAs per SM in the persistent grid (default 4; 1 = exactly one CTA per SM). */
 WCTB200_API int wctb200_debug_set_conv_oversub(int k);
+/* covariance: impl 1 = fp32 FFMA (centred), 2 = tcgen05 (uncentred sums, fp64 centring; default);
+ * lbo/sbo: MN-major descriptor strides in bytes (probe; negative keeps the current value). */
+WCTB200_API int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
 WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 

@@ -149,3 +149,30 @@ def test_split_style_prepare_and_apply_equals_combined_level():
     got = U.act_to_numpy(out, nc, hc, wc, c)
     assert np.array_equal(kbuf.cpu().numpy()[: nc + ns], kref[: nc + ns])
     assert np.abs(got - ref).max() <= 2e-5
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("shape", [(1, 8, 32, 64), (2, 9, 40, 64), (1, 16, 33, 128), (1, 12, 20, 256), (2, 8, 8, 512)])
+def test_covariance_kernels(shape, impl):
+    """Stage A of the transform (ops.py:43-45,105-108): per-channel mean and fc fc^T/(HW-1).
+    impl 2 = tcgen05 (MN-major operands, uncentred sums, fp64 centring), impl 1 = fp32 FFMA (centred)."""
+    rng = np.random.default_rng(3)
+    n, h, w, c = shape
+    x = np.maximum(rng.standard_normal(shape) @ (rng.standard_normal((c, c)) / np.sqrt(c)) + 0.3, 0).astype(np.float32)
+    lib = U.lib()
+    lib.wctb200_debug_set_cov(impl, -1, -1)
+    try:
+        buf = U.act_from_numpy(x)
+        mean = torch.empty((n, c), dtype=torch.float32, device="cuda")
+        cov = torch.empty((n, c, c), dtype=torch.float32, device="cuda")
+        _capi.check(lib.wctb200_covariance(buf.data_ptr(), n, h, w, c, 1e-8, mean.data_ptr(), cov.data_ptr(), U.stream()))
+        U.check_device()
+    finally:
+        lib.wctb200_debug_set_cov(2, -1, -1)
+    xs = U.split_repr(x).reshape(n, -1, c)
+    for i in range(n):
+        ref = np.cov(xs[i].T) + 1e-8 * np.eye(c)
+        got = cov[i].cpu().numpy()
+        assert np.abs(mean[i].cpu().numpy() - xs[i].mean(0)).max() <= 1e-6
+        assert np.abs(got - ref).max() <= 4e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+        assert np.array_equal(got, got.T)

@@ -38,11 +38,13 @@ SIGNATURES = {
     "wctb200_wct_style_prepare": (_i, [_vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _sz, _vp]),
     "wctb200_wct_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "wctb200_adain_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
+    "wctb200_covariance": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wctb200_debug_set_conv_bn": (_i, [_i]),
     "wctb200_debug_set_conv_impl": (_i, [_i]),
     "wctb200_debug_set_conv3": (_i, [_i, _i]),
     "wctb200_debug_set_conv_oversub": (_i, [_i]),
+    "wctb200_debug_set_cov": (_i, [_i, _i, _i]),
 }
 
 _lib = None

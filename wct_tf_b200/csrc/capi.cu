@@ -53,6 +53,7 @@ size_t wct_style_state_bytes(int, int);
 int launch_wct_style_prepare(const __half*, int, int, int, int, float, float, float, void*, void*, size_t, cudaStream_t);
 int launch_wct_apply(const __half*, int, int, int, int, const void*, int, float, float, float, float, int, __half*, int32_t*,
                      void*, size_t, cudaStream_t);
+int launch_covariance(const __half*, int, int, int, int, float, float*, float*, cudaStream_t);
 int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
 int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
@@ -60,6 +61,9 @@ extern int g_conv_impl;
 extern int g_conv3_cluster;
 extern int g_conv3_bo_mode;
 extern int g_conv_oversub;
+extern int g_cov_impl;
+extern int g_cov_lbo;
+extern int g_cov_sbo;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
 static bool geom_ok(int N, int H, int W, int C) {
@@ -199,6 +203,11 @@ int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc, const void*
                               ST(stream));
 }
 
+int wctb200_covariance(const void* act, int N, int H, int W, int C, float eps_cov, float* mean, float* cov, void* stream) {
+    WCTB_REQUIRE(act && mean && cov && geom_ok(N, H, W, C), "covariance: bad arguments");
+    return launch_covariance(HCP(act), N, H, W, C, eps_cov, mean, cov, ST(stream));
+}
+
 int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream) {
     WCTB_REQUIRE(a && sigma && count >= 1, "jacobi_eigh: bad arguments");
     // convergence scratch: 16 floats per matrix
@@ -222,6 +231,12 @@ int wctb200_debug_set_conv_impl(int impl) {
 int wctb200_debug_set_conv_oversub(int k) {
     g_conv_oversub = k < 1 ? 1 : (k > 16 ? 16 : k);
     return g_conv_oversub;
+}
+int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes) {
+    if (impl == 1 || impl == 2) g_cov_impl = impl;
+    if (lbo_bytes >= 0) g_cov_lbo = lbo_bytes;
+    if (sbo_bytes >= 0) g_cov_sbo = sbo_bytes;
+    return g_cov_impl;
 }
 int wctb200_debug_set_conv3(int cluster, int bo_mode) {
     g_conv3_cluster = cluster == 1 ? 1 : 2;

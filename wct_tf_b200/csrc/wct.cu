@@ -159,15 +159,16 @@ k_cov_partial(const __half* __restrict__ act, ActGeom g, const float* __restrict
 }
 
 // cov64 (upper blocks) -> full symmetric fp32 matrix, /(HW-1), + eps_cov*I   (ops.py:45,50,108,121)
-__global__ void k_cov_finalize(const double* __restrict__ cov, int C, long long HW, float eps_cov, int count,
-                               float* __restrict__ G) {
+__global__ void k_cov_finalize(const double* __restrict__ cov, const double* __restrict__ sum, int C, long long HW,
+                               float eps_cov, int count, float* __restrict__ G) {
     const long long total = (long long)count * C * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(t % C);
         const int i = (int)((t / C) % C);
         const long long n = t / ((long long)C * C);
         const double* cv = cov + n * C * C;
-        const double v = (i / 64 <= j / 64) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
+        double v = (i / 64 <= j / 64) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
+        if (sum) v -= sum[n * C + i] * sum[n * C + j] / (double)HW;    // uncentred sums: remove HW*m_i*m_j in fp64
         float r = (float)(v / (double)(HW - 1));
         if (i == j) r += eps_cov;
         G[t] = r;
@@ -792,6 +793,9 @@ int launch_eig_post(const float* G, int C, int count, float thresh, float eps_ei
     return 0;
 }
 
+int g_cov_impl = 2;   // 1 = fp32 FFMA centred covariance, 2 = tcgen05 uncentred covariance (default)
+int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st);
+
 static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float eps_cov,
                          cudaStream_t st) {
     const long long HW = (long long)g.H * g.W;
@@ -799,13 +803,20 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
     if (rc) return rc;
     k_mean_finalize<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(sum, nullptr, HW, g.N * g.C, mean, nullptr);
     WCTB_CHECK_LAUNCH("k_mean_finalize");
-    const int nb = g.C / 64;
-    const int chunk = pick_chunk(HW, nb * (nb + 1) / 2, g.N);
-    dim3 grid((unsigned)(nb * (nb + 1) / 2), (unsigned)cdiv(HW, chunk), (unsigned)g.N);
-    k_cov_partial<<<grid, 256, 0, st>>>(act, g, mean, chunk, cov);
-    WCTB_CHECK_LAUNCH("k_cov_partial");
+    const bool tc = g_cov_impl == 2 && (g.C == 64 || g.C % 128 == 0);
+    if (tc) {
+        // tensor-core path: uncentred sums S = sum x x^T (cov_tc.cu); centring removed in fp64 below
+        int rc2 = launch_cov_tc(act, g, cov, st);
+        if (rc2) return rc2;
+    } else {
+        const int nb = g.C / 64;
+        const int chunk = pick_chunk(HW, nb * (nb + 1) / 2, g.N);
+        dim3 grid((unsigned)(nb * (nb + 1) / 2), (unsigned)cdiv(HW, chunk), (unsigned)g.N);
+        k_cov_partial<<<grid, 256, 0, st>>>(act, g, mean, chunk, cov);
+        WCTB_CHECK_LAUNCH("k_cov_partial");
+    }
     k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
-        cov, g.C, HW, eps_cov, g.N, G);
+        cov, tc ? sum : nullptr, g.C, HW, eps_cov, g.N, G);
     WCTB_CHECK_LAUNCH("k_cov_finalize");
     return 0;
 }
@@ -977,6 +988,20 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
         WCTB_CUDA(cudaMemcpyAsync(k_out + 2 * Nc + Ns, ks + Ns, (size_t)Ns * 4, cudaMemcpyDeviceToDevice, st));
     }
     return 0;
+}
+
+// test / profiling hook: means and covariance of a feature batch (stage A of the transform)
+int launch_covariance(const __half* act, int N, int H, int W, int C, float eps_cov, float* mean_out, float* cov_out,
+                      cudaStream_t st) {
+    WCTB_REQUIRE(C % 64 == 0 && C >= 64, "covariance: C=%d must be a multiple of 64", C);
+    double *sum = nullptr, *cov = nullptr;
+    const size_t nsum = (size_t)N * C, ncov = (size_t)N * C * C;
+    WCTB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st));
+    cov = sum + nsum;
+    WCTB_CUDA(cudaMemsetAsync(sum, 0, (nsum + ncov) * sizeof(double), st));
+    int rc = stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, eps_cov, st);
+    cudaFreeAsync(sum, st);
+    return rc;
 }
 
 int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
