@@ -158,7 +158,7 @@ WCTB200_API int wctb200_debug_set_conv_bn(int bn);
 WCTB200_API int wctb200_debug_set_conv_impl(int impl);
 /* impl 2: CTAs per SM in the persistent grid (default 4; 1 = exactly one CTA per SM). */
 WCTB200_API int wctb200_debug_set_conv_oversub(int k);
-/* covariance: impl 1 = fp32 FFMA (centred), 2 = tcgen05 (uncentred sums, fp64 centring; default);
+/* covariance: impl 1 = fp32 FFMA, 2 = tcgen05 on a centred split-fp16 copy (default);
  * lbo/sbo: MN-major descriptor strides in bytes (probe; negative keeps the current value). */
 WCTB200_API int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */

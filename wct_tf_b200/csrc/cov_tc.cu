@@ -8,10 +8,12 @@
 // reflect-padded plane (base pointer at pixel (0,0), padded strides, dims W x H): boxes that stick
 // out at a ragged edge are zero-filled by TMA and add nothing to the sums, halo cells are never read.
 //
-//   uncentred sums in fp32 (split-fp16 x3 products), drained from TMEM every 256 pixels into
-//   registers (the tensor core accumulates with truncation and x x^T diagonals are all-positive
-//   sums), per-CTA partials combined with fp64 atomics; the centring term HW m m^T is removed in
-//   fp64 by k_cov_finalize.
+//   The input is the CENTRED feature copy fc = x - mean written by k_center (wct.cu): products
+//   in fp32 (split-fp16 x3), drained from TMEM every 256 pixels into registers (the tensor core
+//   accumulates with truncation and the diagonals are all-positive sums), per-CTA partials
+//   combined with fp64 atomics.  (An uncentred variant with the HW m m^T term removed in fp64 was
+//   measured first: it cancels in fp32 and produced a spurious eigenvalue above the 1e-5 cut on a
+//   rank-deficient map, so centring happens before the product, like ops.py:44-45.)
 //
 // One CTA = one 128 x 128 block pair (bi <= bj) of the C x C matrix x one range of pixel tiles.
 #include "common.cuh"

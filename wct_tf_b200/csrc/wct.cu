@@ -687,6 +687,33 @@ __global__ void k_affine_apply(const __half* __restrict__ in, ActGeom g, const f
     }
 }
 
+// centred copy fc = x - mean (ops.py:44,49,106) as SPF16, interior cells only: the operand of the
+// tensor-core covariance.  Centring BEFORE the product matters: the uncentred form
+// sum x x^T - HW m m^T cancels in fp32 (measured: a rank-deficient 64-pixel map produced a
+// spurious eigenvalue above the 1e-5 cut).
+__global__ void k_center(const __half* __restrict__ in, ActGeom g, const float* __restrict__ mean, __half* __restrict__ out) {
+    const int cgs = g.C / 8;
+    const long long total = (long long)g.N * g.H * g.W * cgs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % (unsigned)cgs) * 8;
+        unsigned pix = i / (unsigned)cgs;
+        const int x = (int)(pix % (unsigned)g.W); pix /= (unsigned)g.W;
+        const int y = (int)(pix % (unsigned)g.H);
+        const int n = (int)(pix / (unsigned)g.H);
+        const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
+        float v[8];
+        load8(in, g, pos, c0, v);
+        const float* m = mean + (long long)n * g.C + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] -= m[j];
+        Half8 hi, lo;
+        split8(v, hi, lo);
+        const long long off = pos * g.C + c0;
+        *reinterpret_cast<Half8*>(out + off) = hi;
+        *reinterpret_cast<Half8*>(out + g.plane + off) = lo;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -805,8 +832,16 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
     WCTB_CHECK_LAUNCH("k_mean_finalize");
     const bool tc = g_cov_impl == 2 && (g.C == 64 || g.C % 128 == 0);
     if (tc) {
-        // tensor-core path: uncentred sums S = sum x x^T (cov_tc.cu); centring removed in fp64 below
-        int rc2 = launch_cov_tc(act, g, cov, st);
+        // tensor-core path (cov_tc.cu) on a centred SPF16 copy of the features (stream-ordered scratch)
+        __half* centred = nullptr;
+        WCTB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&centred), (size_t)g.plane * 2 * sizeof(__half), st));
+        const long long total = (long long)g.N * g.H * g.W * (g.C / 8);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_center<<<(unsigned)blocks, 256, 0, st>>>(act, g, mean, centred);
+        cudaError_t le = cudaGetLastError();
+        int rc2 = le == cudaSuccess ? launch_cov_tc(centred, g, cov, st) : cuda_fail(le, "k_center");
+        cudaFreeAsync(centred, st);
         if (rc2) return rc2;
     } else {
         const int nb = g.C / 64;
@@ -816,7 +851,7 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
         WCTB_CHECK_LAUNCH("k_cov_partial");
     }
     k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
-        cov, tc ? sum : nullptr, g.C, HW, eps_cov, g.N, G);
+        cov, nullptr, g.C, HW, eps_cov, g.N, G);
     WCTB_CHECK_LAUNCH("k_cov_finalize");
     return 0;
 }
