@@ -174,5 +174,6 @@ def test_covariance_kernels(shape, impl):
         ref = np.cov(xs[i].T) + 1e-8 * np.eye(c)
         got = cov[i].cpu().numpy()
         assert np.abs(mean[i].cpu().numpy() - xs[i].mean(0)).max() <= 1e-6
-        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+        # tensor-core chunks add with truncation: ~24 adds x 2^-24 on the all-positive diagonal sums
+        assert np.abs(got - ref).max() <= 1.5e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
         assert np.array_equal(got, got.T)

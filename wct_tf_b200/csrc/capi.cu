@@ -19,6 +19,22 @@ int cuda_fail(cudaError_t e, const char* what) {
     return WCTB200_ECUDA;
 }
 
+int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready[dev] = true;
+    }
+    WCTB_CUDA(cudaMallocAsync(ptr, bytes, st));
+    return 0;
+}
+
 __device__ unsigned int g_device_error = 0;
 
 unsigned int* device_error_word() {
@@ -212,7 +228,7 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     WCTB_REQUIRE(a && sigma && count >= 1, "jacobi_eigh: bad arguments");
     // convergence scratch: 16 floats per matrix
     float* conv = nullptr;
-    WCTB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&conv), (size_t)count * 16 * sizeof(float), ST(stream)));
+    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&conv), (size_t)count * 16 * sizeof(float), ST(stream)); if (rc0) return rc0; }
     int rc = launch_jacobi(a, C, count, conv, sweeps, ST(stream));
     if (!rc) rc = launch_eig_post(a, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
     cudaFreeAsync(conv, ST(stream));

@@ -301,6 +301,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 #endif  // __CUDACC__
 
+// stream-ordered scratch (cudaMallocAsync) with the pool's release threshold raised once, so that
+// scratch freed before a synchronisation point is NOT handed back to the OS every step
+int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
+
 // ---------------------------------------------------------------------------
 // kernel launchers implemented in the .cu files (host API used by capi.cu)
 // ---------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 // out at a ragged edge are zero-filled by TMA and add nothing to the sums, halo cells are never read.
 //
 //   The input is the CENTRED feature copy fc = x - mean written by k_center (wct.cu): products
-//   in fp32 (split-fp16 x3), drained from TMEM every 256 pixels into registers (the tensor core
+//   in fp32 (split-fp16 x3), drained from TMEM every 128 pixels into registers (the tensor core
 //   accumulates with truncation and the diagonals are all-positive sums), per-CTA partials
 //   combined with fp64 atomics.  (An uncentred variant with the HW m m^T term removed in fp64 was
 //   measured first: it cancels in fp32 and produced a spurious eigenvalue above the 1e-5 cut on a
@@ -36,7 +36,7 @@ struct CovCfg {
     static constexpr int STAGE = 2 * OPER;                  // A + B
     static constexpr int STAGES = 3;
     static constexpr int NBUF = 4;
-    static constexpr int CH = 4;                            // 64-pixel tiles per TMEM accumulation chunk
+    static constexpr int CH = 2;                            // 64-pixel tiles per TMEM accumulation chunk (24 truncating adds)
     static constexpr int THREADS = 192;
     static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + 1024;
 };
