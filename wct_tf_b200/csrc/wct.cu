@@ -167,7 +167,8 @@ __global__ void k_cov_finalize(const double* __restrict__ cov, const double* __r
         const int i = (int)((t / C) % C);
         const long long n = t / ((long long)C * C);
         const double* cv = cov + n * C * C;
-        double v = (i / 64 <= j / 64) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
+        // every (min,max) entry lies in a stored upper block: reading it for both (i,j) and (j,i) makes G exactly symmetric
+        double v = (i <= j) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
         if (sum) v -= sum[n * C + i] * sum[n * C + j] / (double)HW;    // uncentred sums: remove HW*m_i*m_j in fp64
         float r = (float)(v / (double)(HW - 1));
         if (i == j) r += eps_cov;
