@@ -234,8 +234,9 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
     p.nb = g.C == 64 ? 1 : g.C / 128;
     const int npairs = p.nb * (p.nb + 1) / 2;
     const int tiles_img = p.tiles_x * p.tiles_y;
-    // aim for ~4 CTAs per SM in total, at least 8 tiles (512 pixels) per CTA
-    int ksplit = (148 * 4 + npairs * g.N - 1) / (npairs * g.N);
+    // aim for ~2 CTAs per SM in total (each CTA pays ~5 us of TMEM/barrier set-up and final atomics),
+    // at least 8 tiles (512 pixels) per CTA
+    int ksplit = (148 * 2 + npairs * g.N - 1) / (npairs * g.N);
     if (ksplit < 1) ksplit = 1;
     int tps = (tiles_img + ksplit - 1) / ksplit;
     if (tps < 8) tps = 8;
