@@ -145,3 +145,50 @@ def test_grouped_streams_equal_single_stream(weights):
     eng.check_device()
     assert got2.shape == ref.shape and np.abs(got2 - ref).max() <= 2e-4
     assert np.abs(got4 - ref4).max() <= 2e-4
+
+
+@pytest.mark.parametrize("hw,shw", [((70, 130), (50, 66)), ((33, 47), (128, 40)), ((16, 16), (16, 20))])
+def test_odd_sizes_full_pipeline_vs_oracle(weights, hw, shw):
+    """Sizes that are not multiples of 16: MaxPooling2D(padding='same') rounds up and UpSampling2D doubles,
+    so the output grows like the reference graph's (vgg_normalised.py:42, model.py:293)."""
+    targets = ["relu4_1", "relu2_1", "relu1_1"]
+    rng = np.random.default_rng(hw[0])
+    content = rng.integers(0, 256, (1, hw[0], hw[1], 3), dtype=np.uint8)
+    style = rng.integers(0, 256, (1, shw[0], shw[1], 3), dtype=np.uint8)
+    eng = Engine(weights, targets, semantics="tf")
+    cap = {}
+    out = eng.stylize(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), alpha=0.6, want_info=True, capture=cap)
+    eng.check_device()
+    sfe = nets.encode(nets.preprocess(style).astype(np.float64), weights, targets, np.float64)
+    for i, relu in enumerate(targets):
+        x = cap["level_input"][i].cpu().numpy().astype(np.float64)
+        cf = nets.encode(x, weights, [relu], np.float64)[relu]
+        f, info = ref_ops.wct_tf(cf, sfe[relu], 0.6, return_info=True)
+        if not (ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"])):
+            pytest.skip("ill-posed vector (eigenvalue near the 1e-5 cut)")
+        k = eng.last_info[i].cpu().numpy()
+        assert (k[0], k[1]) == (info["k_c"], info["k_s"])
+        y = nets.decode(f, weights, relu, np.float64)
+        if i < len(targets) - 1:
+            y = np.clip(y, 0, 1)
+        got = cap["level_output"][i].cpu().numpy()
+        assert got.shape == y.shape
+        assert np.abs(got - y).max() <= 1e-3
+    ref_shape = nets.pipeline(content[0], style[0], weights, targets, alpha=0.6, semantics="tf", dtype=np.float32).shape
+    assert tuple(out.shape) == tuple(ref_shape)
+
+
+def test_cli_end_to_end(tmp_path):
+    """stylize.py with the reference's flags on real image files (synthetic weights)."""
+    from PIL import Image
+    import stylize
+    rng = np.random.default_rng(0)
+    cdir, sdir, odir = tmp_path / "c", tmp_path / "s", tmp_path / "o"
+    cdir.mkdir(); sdir.mkdir()
+    Image.fromarray(rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)).save(cdir / "a.png")
+    Image.fromarray(rng.integers(0, 256, (64, 48, 3), dtype=np.uint8)).save(sdir / "st.png")
+    stylize.main(["--synthetic-weights", "42", "--relu-targets", "relu2_1", "relu1_1", "--content-path", str(cdir),
+                  "--style-path", str(sdir / "st.png"), "--out-path", str(odir), "--alpha", "0.7", "--style-size", "32",
+                  "--passes", "2", "--concat"])
+    out = np.asarray(Image.open(odir / "a_st.png"))      # {content}_{style}{ext}, stylize.py:114
+    assert out.shape == (40, 40 + 56, 3) and out.dtype == np.uint8
