@@ -164,8 +164,12 @@ def test_odd_sizes_full_pipeline_vs_oracle(weights, hw, shw):
         x = cap["level_input"][i].cpu().numpy().astype(np.float64)
         cf = nets.encode(x, weights, [relu], np.float64)[relu]
         f, info = ref_ops.wct_tf(cf, sfe[relu], 0.6, return_info=True)
-        if not (ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"])):
-            pytest.skip("ill-posed vector (eigenvalue near the 1e-5 cut)")
+        _, info32 = ref_ops.wct_tf(cf.astype(np.float32), sfe[relu].astype(np.float32), 0.6, return_info=True)
+        if not (ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"])) or \
+                (info32["k_c"], info32["k_s"]) != (info["k_c"], info["k_s"]):
+            # rank-deficient map (HW < C): the null eigenvalues sit at the fp32 noise floor eps*lambda_max*sqrt(C)
+            # ~ 1e-5, so the reference's OWN fp32 arithmetic does not agree with its fp64 run on k
+            pytest.skip("ill-posed vector for any fp32 implementation (reference fp32 k != fp64 k)")
         k = eng.last_info[i].cpu().numpy()
         assert (k[0], k[1]) == (info["k_c"], info["k_s"])
         y = nets.decode(f, weights, relu, np.float64)
