@@ -177,3 +177,25 @@ def test_covariance_kernels(shape, impl):
         # tensor-core chunks add with truncation: ~24 adds x 2^-24 on the all-positive diagonal sums
         assert np.abs(got - ref).max() <= 1.5e-6 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
         assert np.array_equal(got, got.T)
+
+
+def test_jacobi_rank_deficient_null_space_stays_below_threshold():
+    """HW < C (e.g. relu5_1 of a 256x256 image): 483 of 512 eigenvalues are exactly zero.  The count
+    k = #(sigma > 1e-5) (ops.py:68,112) must equal what LAPACK finds on the same fp32 matrix."""
+    rng = np.random.default_rng(1)
+    C, hw = 512, 30
+    x = np.maximum(rng.standard_normal((hw, C)) @ (rng.standard_normal((C, C)) / np.sqrt(C)) * 1.5 + 0.8, 0)
+    xc = (x - x.mean(0)).astype(np.float32)
+    cov = (xc.T @ xc / np.float32(hw - 1)).astype(np.float32)
+    k_ref = int((np.linalg.svd(cov, compute_uv=False) > 1e-5).sum())
+    assert k_ref == hw - 1
+    d = U.dev(cov[None].copy())
+    sigma = torch.empty((1, C), dtype=torch.float32, device="cuda")
+    sweeps = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _capi.check(U.lib().wctb200_jacobi_eigh(d.data_ptr(), C, 1, sigma.data_ptr(), sweeps.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    sg = np.sort(sigma.cpu().numpy()[0])[::-1]
+    w = np.linalg.eigvalsh(cov.astype(np.float64))[::-1]
+    print("lambda_max %.1f, k %d (ref %d), largest null value %.2e, sweeps %d" % (w[0], (sg > 1e-5).sum(), k_ref, sg[k_ref], int(sweeps.item())))
+    assert int((sg > 1e-5).sum()) == k_ref
+    assert np.abs(sg[:k_ref] - w[:k_ref]).max() <= 4e-5 * w[0]
