@@ -71,7 +71,7 @@ int launch_wct_apply(const __half*, int, int, int, int, const void*, int, float,
                      void*, size_t, cudaStream_t);
 int launch_covariance(const __half*, int, int, int, int, float, float*, float*, cudaStream_t);
 int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
-int launch_eig_post(const float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
+int launch_eig_post(const float*, const float*, float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
 extern int g_conv_impl;
 extern int g_conv3_cluster;
@@ -226,12 +226,21 @@ int wctb200_covariance(const void* act, int N, int H, int W, int C, float eps_co
 
 int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream) {
     WCTB_REQUIRE(a && sigma && count >= 1, "jacobi_eigh: bad arguments");
-    // convergence scratch: 16 floats per matrix
-    float* conv = nullptr;
-    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&conv), (size_t)count * 16 * sizeof(float), ST(stream)); if (rc0) return rc0; }
-    int rc = launch_jacobi(a, C, count, conv, sweeps, ST(stream));
-    if (!rc) rc = launch_eig_post(a, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
-    cudaFreeAsync(conv, ST(stream));
+    WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "jacobi_eigh: C=%d not in {64,128,256,512}", C);
+    // scratch: convergence words (16 floats per matrix), a pristine copy of the input (Rayleigh quotients), lambda
+    const size_t nmat = (size_t)count * C * C;
+    float* scratch = nullptr;
+    {
+        int rc0 = scratch_alloc(reinterpret_cast<void**>(&scratch), ((size_t)count * 16 + nmat + (size_t)count * C) * sizeof(float), ST(stream));
+        if (rc0) return rc0;
+    }
+    float* conv = scratch;
+    float* a0 = scratch + (size_t)count * 16;
+    float* lam = a0 + nmat;
+    cudaError_t ce = cudaMemcpyAsync(a0, a, nmat * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream));
+    int rc = ce == cudaSuccess ? launch_jacobi(a, C, count, conv, sweeps, ST(stream)) : cuda_fail(ce, "cudaMemcpyAsync");
+    if (!rc) rc = launch_eig_post(a, a0, lam, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
+    cudaFreeAsync(scratch, ST(stream));
     return rc;
 }
 

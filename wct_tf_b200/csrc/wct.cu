@@ -160,7 +160,7 @@ k_cov_partial(const __half* __restrict__ act, ActGeom g, const float* __restrict
 
 // cov64 (upper blocks) -> full symmetric fp32 matrix, /(HW-1), + eps_cov*I   (ops.py:45,50,108,121)
 __global__ void k_cov_finalize(const double* __restrict__ cov, const double* __restrict__ sum, int C, long long HW,
-                               float eps_cov, int count, float* __restrict__ G) {
+                               float eps_cov, int count, float* __restrict__ G, float* __restrict__ A0) {
     const long long total = (long long)count * C * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(t % C);
@@ -173,6 +173,7 @@ __global__ void k_cov_finalize(const double* __restrict__ cov, const double* __r
         float r = (float)(v / (double)(HW - 1));
         if (i == j) r += eps_cov;
         G[t] = r;
+        if (A0) A0[t] = r;          // pristine copy: the Jacobi kernel overwrites G, the Rayleigh quotients need A
     }
 }
 
@@ -580,12 +581,60 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     if (rank == 0 && threadIdx.x == 0 && sweeps_out) sweeps_out[prob] = sweep;
 }
 
-// sigma_i = |column i|; per-problem kept count; scaling d_i of the rank-k reconstruction
+// Rayleigh quotients  lambda_i = g_i^T A g_i / |g_i|^2  of the converged columns against the ORIGINAL matrix.
+// The column norm |g_i| is a first-order eigenvalue estimate: on a rank-deficient map the null columns
+// keep the rounding noise of the cancellations that created them (measured 4e-7*lambda_max, i.e. above
+// the 1e-5 cut for lambda_max > 25; LAPACK: 4e-8*lambda_max).  The Rayleigh quotient is second order in
+// that noise: the same null columns give ~1e-8.   grid (C/16, problems), C threads.
+__global__ void __launch_bounds__(512)
+k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int C, float* __restrict__ lam) {
+    __shared__ __align__(16) float gs[512 * 16];
+    __shared__ float red_q[16], red_s[16];
+    const int prob = blockIdx.y, j0 = blockIdx.x * 16, r = threadIdx.x;
+    const float* A0 = A0all + (long long)prob * C * C;
+    const float* G = Gall + (long long)prob * C * C;
+    if (r < 16) { red_q[r] = 0.f; red_s[r] = 0.f; }
+    float mine[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        mine[jj] = G[(long long)(j0 + jj) * C + r];          // column j0+jj, row r (coalesced over r)
+        gs[r * 16 + jj] = mine[jj];
+    }
+    __syncthreads();
+    float acc[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.f;
+    for (int k = 0; k < C; ++k) {
+        const float a = A0[(long long)k * C + r];             // A symmetric: row k read as column k, coalesced over r
+        const float4* g4 = reinterpret_cast<const float4*>(gs + k * 16);
+        const float4 g0 = g4[0], g1 = g4[1], g2 = g4[2], g3 = g4[3];
+        acc[0] = fmaf(a, g0.x, acc[0]); acc[1] = fmaf(a, g0.y, acc[1]); acc[2] = fmaf(a, g0.z, acc[2]); acc[3] = fmaf(a, g0.w, acc[3]);
+        acc[4] = fmaf(a, g1.x, acc[4]); acc[5] = fmaf(a, g1.y, acc[5]); acc[6] = fmaf(a, g1.z, acc[6]); acc[7] = fmaf(a, g1.w, acc[7]);
+        acc[8] = fmaf(a, g2.x, acc[8]); acc[9] = fmaf(a, g2.y, acc[9]); acc[10] = fmaf(a, g2.z, acc[10]); acc[11] = fmaf(a, g2.w, acc[11]);
+        acc[12] = fmaf(a, g3.x, acc[12]); acc[13] = fmaf(a, g3.y, acc[13]); acc[14] = fmaf(a, g3.z, acc[14]); acc[15] = fmaf(a, g3.w, acc[15]);
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+        float q = mine[jj] * acc[jj], ss = mine[jj] * mine[jj];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) { atomicAdd(&red_q[jj], q); atomicAdd(&red_s[jj], ss); }
+    }
+    __syncthreads();
+    if (r < 16) lam[(long long)prob * C + j0 + r] = red_s[r] > 0.f ? red_q[r] / red_s[r] : 0.f;
+}
+
+// eigenvalue estimate (Rayleigh quotient when `lam` is given, else |column i|); per-problem kept count;
+// scaling d_i of the rank-k reconstruction
 //   mode 0 (content, whitening): d = (sigma+eps_eig)^-1/2 / sigma^2
 //   mode 1 (style, colouring)  : d = (sigma+eps_eig)^+1/2 / sigma^2
 //   so that  E_k f(S_k) E_k^T = G diag(d) G^T  with G's columns = sigma_i u_i.
-__global__ void k_eig_post(const float* __restrict__ Gall, int C, float thresh, float eps_eig, int n_content,
-                           float* __restrict__ sigma, float* __restrict__ dvec, int* __restrict__ kcount) {
+__global__ void k_eig_post(const float* __restrict__ Gall, const float* __restrict__ lam, int C, float thresh, float eps_eig,
+                           int n_content, float* __restrict__ sigma, float* __restrict__ dvec, int* __restrict__ kcount) {
     const int prob = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -596,7 +645,7 @@ __global__ void k_eig_post(const float* __restrict__ Gall, int C, float thresh, 
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if (lane == 0) {
-        const float sg = sqrtf(ss);
+        const float sg = lam ? fabsf(lam[(long long)prob * C + col]) : sqrtf(ss);   // |lambda| like the SVD of ops.py:54,110
         sigma[(long long)prob * C + col] = sg;
         float d = 0.f;
         if (sg > thresh) {                                       // ops.py:68-69,112,125
@@ -758,7 +807,7 @@ __global__ void k_center(const __half* __restrict__ in, ActGeom g, const float* 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WctWs {
-    size_t sum, sumsq, mean, var, cov, G, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
+    size_t sum, sumsq, mean, var, cov, G, A0, lam, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
 };
 static WctWs wct_layout(int C, int Nc, int Ns) {
     WctWs w;
@@ -771,6 +820,8 @@ static WctWs wct_layout(int C, int Nc, int Ns) {
     w.mean = take(np * C * 4);
     w.var = take(np * C * 4);
     w.G = take(np * C * C * 4);
+    w.A0 = take(np * C * C * 4);
+    w.lam = take(np * C * 4);
     w.sigma = take(np * C * 4);
     w.dvec = take(np * C * 4);
     w.Wc = take((size_t)Nc * C * C * 4);
@@ -850,10 +901,17 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
     return 0;
 }
 
-int launch_eig_post(const float* G, int C, int count, float thresh, float eps_eig, int n_content, float* sigma,
-                    float* dvec, int* kcount, cudaStream_t st) {
+int launch_eig_post(const float* G, const float* A0, float* lam, int C, int count, float thresh, float eps_eig,
+                    int n_content, float* sigma, float* dvec, int* kcount, cudaStream_t st) {
+    if (A0 && lam) {
+        dim3 gr((unsigned)(C / 16), (unsigned)count);
+        k_rayleigh<<<gr, C, 0, st>>>(A0, G, C, lam);
+        WCTB_CHECK_LAUNCH("k_rayleigh");
+    } else {
+        lam = nullptr;
+    }
     dim3 grid((unsigned)cdiv(C, 8), (unsigned)count);
-    k_eig_post<<<grid, 256, 0, st>>>(G, C, thresh, eps_eig, n_content, sigma, dvec, kcount);
+    k_eig_post<<<grid, 256, 0, st>>>(G, lam, C, thresh, eps_eig, n_content, sigma, dvec, kcount);
     WCTB_CHECK_LAUNCH("k_eig_post");
     return 0;
 }
@@ -861,8 +919,8 @@ int launch_eig_post(const float* G, int C, int count, float thresh, float eps_ei
 int g_cov_impl = 2;   // 1 = fp32 FFMA centred covariance, 2 = tcgen05 uncentred covariance (default)
 int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st);
 
-static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float eps_cov,
-                         cudaStream_t st) {
+static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float* A0,
+                         float eps_cov, cudaStream_t st) {
     const long long HW = (long long)g.H * g.W;
     int rc = launch_sums<false>(act, g, sum, nullptr, st);
     if (rc) return rc;
@@ -889,7 +947,7 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
         WCTB_CHECK_LAUNCH("k_cov_partial");
     }
     k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
-        cov, nullptr, g.C, HW, eps_cov, g.N, G);
+        cov, nullptr, g.C, HW, eps_cov, g.N, G, A0);
     WCTB_CHECK_LAUNCH("k_cov_finalize");
     return 0;
 }
@@ -925,13 +983,16 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));          // sum, sumsq, cov
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)np * 2 * 4, st));
     ActGeom gc(Nc, Hc, Wc, C), gs(Ns, Hs, Ws, C);
-    int rc = stats_and_cov(content, gc, sum, cov, mean, G, eps_cov, st);
+    float* A0 = reinterpret_cast<float*>(w + L.A0);
+    float* lam = reinterpret_cast<float*>(w + L.lam);
+    int rc = stats_and_cov(content, gc, sum, cov, mean, G, A0, eps_cov, st);
     if (rc) return rc;
-    rc = stats_and_cov(style, gs, sum + (long long)Nc * C, cov + Nc * CC, mean + (long long)Nc * C, G + Nc * CC, eps_cov, st);
+    rc = stats_and_cov(style, gs, sum + (long long)Nc * C, cov + Nc * CC, mean + (long long)Nc * C, G + Nc * CC, A0 + Nc * CC,
+                       eps_cov, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, np, conv, kc + np, st);
     if (rc) return rc;
-    rc = launch_eig_post(G, C, np, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, np, thresh, eps_eig, Nc, sigma, dvec, kc, st);
     if (rc) return rc;
     // W_c (whitening) per content frame, C_s (colouring) per style
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)np);
@@ -993,11 +1054,13 @@ int launch_wct_style_prepare(const __half* style, int Ns, int Hs, int Ws, int C,
     const long long CC = (long long)C * C;
     WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Ns * 2 * 4, st));
-    int rc = stats_and_cov(style, ActGeom(Ns, Hs, Ws, C), sum, cov, mean_s, G, eps_cov, st);
+    float* A0 = reinterpret_cast<float*>(w + L.A0);
+    float* lam = reinterpret_cast<float*>(w + L.lam);
+    int rc = stats_and_cov(style, ActGeom(Ns, Hs, Ws, C), sum, cov, mean_s, G, A0, eps_cov, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, Ns, conv, kc + Ns, st);
     if (rc) return rc;
-    rc = launch_eig_post(G, C, Ns, thresh, eps_eig, /*n_content=*/0, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, Ns, thresh, eps_eig, /*n_content=*/0, sigma, dvec, kc, st);
     if (rc) return rc;
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Ns);
     k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Cs, CC, C);
@@ -1037,11 +1100,13 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
     const long long CC = (long long)C * C;
     WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Nc * 2 * 4, st));
-    int rc = stats_and_cov(content, ActGeom(Nc, Hc, Wc, C), sum, cov, mean, G, eps_cov, st);
+    float* A0 = reinterpret_cast<float*>(w + L.A0);
+    float* lam = reinterpret_cast<float*>(w + L.lam);
+    int rc = stats_and_cov(content, ActGeom(Nc, Hc, Wc, C), sum, cov, mean, G, A0, eps_cov, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, Nc, conv, kc + Nc, st);
     if (rc) return rc;
-    rc = launch_eig_post(G, C, Nc, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, Nc, thresh, eps_eig, Nc, sigma, dvec, kc, st);
     if (rc) return rc;
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Nc);
     k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C);
@@ -1072,7 +1137,7 @@ int launch_covariance(const __half* act, int N, int H, int W, int C, float eps_c
     { int rc0 = scratch_alloc(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st); if (rc0) return rc0; }
     cov = sum + nsum;
     WCTB_CUDA(cudaMemsetAsync(sum, 0, (nsum + ncov) * sizeof(double), st));
-    int rc = stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, eps_cov, st);
+    int rc = stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, nullptr, eps_cov, st);
     cudaFreeAsync(sum, st);
     return rc;
 }
