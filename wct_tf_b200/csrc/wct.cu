@@ -436,41 +436,11 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     cg::cluster_group cluster = cg::this_cluster();
 
-    // ---- fp32 noise floor: columns whose norm drops below 4*eps*(largest initial column norm) are
-    // numerically null.  Rotating them against the large columns only re-injects the rounding noise the
-    // large columns have accumulated (measured: null eigenvalues came out at 4e-7*lambda_max, LAPACK
-    // gives 4e-8*lambda_max, and a rank-deficient map got k too large once lambda_max > 25), and
-    // noise-vs-noise pairs never converge.  Such columns are left alone; their eigenvalue estimate stays
-    // below the noise floor, far under the 1e-5 cut of ops.py:112 for any lambda_max < 40.
-    float null2;
-    {
-        float cmax = 0.f;
-        const float* mine = G + (long long)rank * 64 * NN;           // this CTA's 64 columns of the initial matrix
-        for (int c = warp * 4; c < warp * 4 + 4; ++c) {
-            float ss = 0.f;
-            for (int i = lane; i < NN; i += 32) { const float v = __ldcg(mine + (long long)c * NN + i); ss = fmaf(v, v, ss); }
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            cmax = fmaxf(cmax, ss);
-        }
-        if (threadIdx.x == 0) s_max = 0u;
-        __syncthreads();
-        if (lane == 0) atomicMax(&s_max, __float_as_uint(cmax));
-        __syncthreads();
-        cmax = __uint_as_float(s_max);
-        if (P > 1) {
-            if (threadIdx.x == 0) {
-                reinterpret_cast<volatile float*>(cw)[8 + rank] = cmax;
-                __threadfence();
-            }
-            cluster.sync();
-            cmax = 0.f;
-            for (int i = 0; i < P; ++i) cmax = fmaxf(cmax, reinterpret_cast<volatile float*>(cw)[8 + i]);
-        }
-        __syncthreads();
-        const float ne = 4.f * 5.96e-8f;
-        null2 = ne * ne * cmax;                                      // compared with squared norms
-    }
+    // Every pair is rotated, including columns that have collapsed to rounding noise: keeping the noise
+    // columns orthogonal to the large ones is what makes their Rayleigh quotients (k_rayleigh) second-order
+    // small.  (A variant that left columns below 4*eps*max|column| alone was measured: the untouched columns
+    // keep large range-space components and their Rayleigh quotients are O(lambda).)
+    const float null2 = 0.f;
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
