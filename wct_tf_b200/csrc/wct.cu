@@ -559,11 +559,10 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
 __global__ void __launch_bounds__(512)
 k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int C, float* __restrict__ lam) {
     __shared__ __align__(16) float gs[512 * 16];
-    __shared__ float red_q[16], red_s[16];
+    __shared__ float red_q[16][17], red_s[16][17];     // [warp][column]: fixed-order (deterministic) reduction
     const int prob = blockIdx.y, j0 = blockIdx.x * 16, r = threadIdx.x;
     const float* A0 = A0all + (long long)prob * C * C;
     const float* G = Gall + (long long)prob * C * C;
-    if (r < 16) { red_q[r] = 0.f; red_s[r] = 0.f; }
     float mine[16];
 #pragma unroll
     for (int jj = 0; jj < 16; ++jj) {
@@ -592,10 +591,14 @@ k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int 
             q += __shfl_xor_sync(0xffffffffu, q, o);
             ss += __shfl_xor_sync(0xffffffffu, ss, o);
         }
-        if (lane == 0) { atomicAdd(&red_q[jj], q); atomicAdd(&red_s[jj], ss); }
+        if (lane == 0) { red_q[threadIdx.x >> 5][jj] = q; red_s[threadIdx.x >> 5][jj] = ss; }
     }
     __syncthreads();
-    if (r < 16) lam[(long long)prob * C + j0 + r] = red_s[r] > 0.f ? red_q[r] / red_s[r] : 0.f;
+    if (r < 16) {
+        float q = 0.f, ss = 0.f;
+        for (int w = 0; w < (C >> 5); ++w) { q += red_q[w][r]; ss += red_s[w][r]; }
+        lam[(long long)prob * C + j0 + r] = ss > 0.f ? q / ss : 0.f;
+    }
 }
 
 // eigenvalue estimate (Rayleigh quotient when `lam` is given, else |column i|); per-problem kept count;
