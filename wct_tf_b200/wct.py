@@ -71,7 +71,7 @@ class WCT(object):
 
         def to_dev(a):
             if isinstance(a, np.ndarray):
-                a = torch.from_numpy(np.ascontiguousarray(a))
+                a = torch.from_numpy(np.array(a, copy=True, order="C"))    # own, writable, contiguous
             if a.dim() == 3:
                 a = a.unsqueeze(0)
             if a.dtype != torch.uint8:
