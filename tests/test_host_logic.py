@@ -163,3 +163,37 @@ def test_frame_sharding_world2_gloo(B, tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_t7_reader_against_reference_torchfile(tmp_path):
+    """A VGG .t7 written by tests/t7_writer.py is read identically by the reference's own
+    torchfile.py (vgg_normalised.py:16, force_8bytes_long=True) and by wct_tf_b200.t7."""
+    from tests.t7_writer import write_vgg_t7
+    from wct_tf_b200 import t7, weights as W
+    w = W.make_synthetic_weights(5, relu_targets=["relu3_1"])
+    path = str(tmp_path / "vgg_normalised.t7")
+    write_vgg_t7(path, w["vgg"])
+    ours = t7.load_vgg_t7(path, deepest="relu5_1")
+    assert [l["name"] for l in ours] == [l["name"] for l in w["vgg"]]
+    for a, b in zip(ours, w["vgg"]):
+        assert np.array_equal(a["weight"], b["weight"]) and np.array_equal(a["bias"], b["bias"])
+    assert [l["name"] for l in t7.load_vgg_t7(path, deepest="relu2_1")][-1] == "conv2_1"    # stops at the target (vgg_normalised.py:48)
+    ref_path = "/root/reference/torchfile.py"
+    if os.path.exists(ref_path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_torchfile", ref_path)
+        tf = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(tf)
+        net = tf.load(path, force_8bytes_long=True)
+        convs = [m for m in net.modules if m._typename == b"nn.SpatialConvolution"]
+        assert len(convs) == len(ours)
+        for m, o in zip(convs, ours):
+            assert np.array_equal(np.asarray(m.weight), o["weight"]) and np.array_equal(np.asarray(m.bias), o["bias"])
+        names = [m.name.decode() for m in net.modules[1:] if m._typename == b"nn.SpatialConvolution"]
+        assert names == [l["name"] for l in ours[1:]]
+    # and through the public loader: checkpoints stay .npz
+    ck = str(tmp_path / "dec.npz")
+    W.save_weights(ck, w)
+    w2 = W.load_weights(path, [ck], ["relu3_1"])
+    assert np.array_equal(w2["vgg"][3]["weight"], w["vgg"][3]["weight"])
+    assert [l["name"] for l in w2["vgg"]][-1] == "conv3_1"

@@ -102,15 +102,19 @@ def load_weights(vgg_path, checkpoints, relu_targets):
     """Mirror of the reference's loading protocol (wct.py:47-58): ``checkpoints[i]``
     pairs with ``relu_targets[i]``; a target without a checkpoint raises.
 
-    Supported here: ``.npz`` bundles written by ``save_weights`` (``vgg_path`` holds the
-    encoder; each checkpoint holds at least its own decoder).  The reference's own
-    formats (Torch7 ``vgg_normalised.t7`` via torchfile.py, TF1 Saver checkpoints) are the
-    next scope row: those files do not exist offline."""
+    Encoder: the reference's own Torch7 ``vgg_normalised.t7`` (read by ``t7.py``) or an ``.npz``
+    bundle.  Decoders: ``.npz`` bundles written by ``save_weights`` (each checkpoint holds at least
+    its own decoder).  TF1 Saver checkpoints (wct.py:51-56) are NOT readable offline (no
+    TensorFlow; the files do not exist here) -- convert them once with TF and ``save_weights``."""
     if vgg_path is None or checkpoints is None:
         raise ValueError("vgg_path and checkpoints are required when no weights dict is given")
-    if not str(vgg_path).endswith(".npz"):
-        raise NotImplementedError("only .npz weight bundles are readable offline; .t7 import is scope row 8f-1")
-    vgg = _load_npz(vgg_path)["vgg"]
+    if str(vgg_path).endswith(".t7"):
+        from .t7 import load_vgg_t7                      # the reference's own encoder format (vgg_normalised.py:16)
+        vgg = load_vgg_t7(vgg_path, deepest=sorted(relu_targets)[-1])
+    elif str(vgg_path).endswith(".npz"):
+        vgg = _load_npz(vgg_path)["vgg"]
+    else:
+        raise NotImplementedError("encoder weights must be a Torch7 .t7 file or an .npz bundle")
     decoders = {}
     for relu, ck in zip(relu_targets, checkpoints):     # wct.py:47 zip pairing
         d = _load_npz(ck)["decoders"] if str(ck).endswith(".npz") else {}
