@@ -13,8 +13,12 @@ Pinning status (see DESIGN.md "Oracle"):
     in the build container (``tests/golden/make_golden.py`` imports
     ``/root/reference/ops.py`` with TensorFlow/Keras stubbed and commits the
     outputs as ``tests/golden/wct_np_*.npz``).
-  * ``wct_tf``, ``adain``, encoder, decoder, level wiring -- PARITY UNPINNED:
-    TensorFlow/Keras are not installable here and the reference ships no
-    tests / golden vectors / weights, so these are restatements of the
-    reference source only (file:line cited on every function).
+  * ``wct_tf``, ``adain``, encoder, decoder, level wiring -- PINNED AT SOURCE LEVEL:
+    ``tests/golden/make_pipeline_golden.py`` imports the reference's own model.py /
+    ops.py / vgg_normalised.py / torchfile.py unmodified and evaluates them over
+    ``tests/golden/np_tf1.py`` (an eager NumPy stand-in for the TensorFlow/Keras calls
+    they make); the outputs are ``tests/golden/pipeline_*.npz`` and the oracle matches
+    them to 1e-9 in float64.  TensorFlow's own kernels (conv, svd) are NOT exercised --
+    TensorFlow is not installable offline -- and no trained weights exist on disk, so
+    real-TF / real-weight parity stays unverified (file:line cited on every function).
 """

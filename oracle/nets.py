@@ -1,5 +1,11 @@
 """CPU restatement of the reference encoder / decoders / level wiring
-(TEST INFRASTRUCTURE; parity UNPINNED -- TensorFlow/Keras absent, no weights on disk).
+(TEST INFRASTRUCTURE).
+
+Pinned by tests/golden/pipeline_*.npz: outputs of the reference's OWN model.py / ops.py /
+vgg_normalised.py / torchfile.py, imported unmodified and evaluated over a NumPy stand-in for the
+TensorFlow/Keras calls they make (tests/golden/np_tf1.py; TensorFlow itself is not installable
+offline, so the tensor primitives conv/svd/pad/pool are numpy, the algorithm statement is the
+reference's).  tests/test_oracle.py: this module == that code to 1e-9 in float64.
 
 Follows:
   vgg_from_t7      /root/reference/vgg_normalised.py:10-55  (+ ops.py:12-15 pad_reflect)

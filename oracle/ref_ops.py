@@ -2,8 +2,9 @@
 
 Follows /root/reference/ops.py:
   wct_np   ops.py:92-140   (the named oracle; pinned by tests/golden/wct_np_*.npz)
-  wct_tf   ops.py:24-90    (what the reference graph really executes; unpinned)
-  adain    ops.py:282-294  (unpinned)
+  wct_tf   ops.py:24-90    (what the reference graph really executes; pinned by tests/golden/pipeline_*.npz:
+                            the reference's own wct_tf source evaluated over the NumPy TF stand-in np_tf1.py)
+  adain    ops.py:282-294  (pinned the same way, pipeline_adain4_a07.npz)
 
 All functions take features shaped 1xHxWxC (or HxWxC) like the reference and
 are dtype-polymorphic: float64 inputs give an fp64 "truth" run of the same

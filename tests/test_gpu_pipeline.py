@@ -7,11 +7,14 @@ Two statements (DESIGN.md "Parity"):
     oracle's fp32-vs-fp64 distance (the chained levels amplify rounding noise ~1e3x with
     random weights, so this bound is stated relative to that noise floor).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import nets, ref_ops
+from tests.test_oracle import PIPE_GOLDEN, load_pipeline_fixture
 from wct_tf_b200.engine import Engine
 from wct_tf_b200.weights import make_synthetic_weights
 from wct_tf_b200.wct import WCT
@@ -97,6 +100,32 @@ def test_free_running_five_levels_vs_oracle(weights):
     for lvl, inf in zip(eng.last_info, info):
         k = lvl.cpu().numpy()
         assert (k[0], k[1]) == (inf["k_c"], inf["k_s"])
+    assert err <= max(1e-3, FREE_RUN_NOISE_FACTOR * noise)
+
+
+@pytest.mark.parametrize("path", PIPE_GOLDEN, ids=[os.path.basename(p)[9:-4] for p in PIPE_GOLDEN])
+def test_engine_vs_reference_code_golden(path):
+    """Engine vs fixtures computed by the reference's own model.py/ops.py/vgg_normalised.py (tests/golden/make_pipeline_golden.py)."""
+    g, targets, w = load_pipeline_fixture(path)
+    alpha, adain = float(g["alpha"]), bool(g["adain"])
+    eng = Engine(w, targets, semantics="tf")
+    cap = {}
+    out = eng.stylize(torch.from_numpy(g["content"][None]).cuda(), torch.from_numpy(g["style"][None]).cuda(), alpha=alpha,
+                      adain=adain, want_info=True, capture=cap)
+    eng.check_device()
+    got = out.cpu().numpy()
+    assert got.shape == g["out_ref_fp64"].shape
+    # level 0 has no chained amplification: the transformed feature (decoder input, model.py:150-158) must meet 1e-3
+    t0 = eng.act_to_f32(cap["transformed"][0]).cpu().numpy()
+    e0 = np.abs(t0 - g["lvl0_decoder_input"]).max()
+    d0 = np.abs(cap["level_output"][0].cpu().numpy() - (np.clip(g["lvl0_decoded"], 0, 1) if len(targets) > 1 else g["lvl0_decoded"])).max()
+    if not adain:
+        ks = [tuple(int(v) for v in lvl.cpu().numpy()[:2]) for lvl in eng.last_info]
+        assert ks == [tuple(r) for r in g["k"].tolist()]
+    noise = np.abs(g["out_ref_fp32"] - g["out_ref_fp64"]).max()
+    err = np.abs(got - g["out_ref_fp64"]).max()
+    print("level-0 transform %.2e  level-0 decoded %.2e  final %.2e (reference fp32-vs-fp64 %.2e)" % (e0, d0, err, noise))
+    assert e0 <= 1e-3 and d0 <= 1e-3
     assert err <= max(1e-3, FREE_RUN_NOISE_FACTOR * noise)
 
 

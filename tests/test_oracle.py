@@ -84,3 +84,55 @@ def test_encoder_shapes_and_pool_same():
     assert f["relu5_1"].shape == (1, 2, 2, 512)
     y = nets.decode(f["relu3_1"], w, "relu3_1")
     assert y.shape == (1, 24, 20, 3)
+
+
+# ---- whole-path fixtures produced by the reference's OWN model.py / ops.py / vgg_normalised.py / torchfile.py
+# (imported unmodified, evaluated over tests/golden/np_tf1.py; see tests/golden/make_pipeline_golden.py)
+PIPE_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pipeline_*.npz")))
+
+
+def load_pipeline_fixture(path):
+    from tests.golden.make_pipeline_golden import weight_checksum
+    from wct_tf_b200.weights import make_synthetic_weights
+    g = np.load(path)
+    targets = [str(t) for t in g["relu_targets"]]
+    w = make_synthetic_weights(int(g["seed"]), relu_targets=targets)
+    assert abs(weight_checksum(w) - float(g["wsum"])) <= 1e-9 * float(g["wsum"]), "synthetic weight generator drifted"
+    return g, targets, w
+
+
+def test_pipeline_golden_present():
+    assert len(PIPE_GOLDEN) >= 4
+
+
+@pytest.mark.parametrize("path", PIPE_GOLDEN, ids=[os.path.basename(p)[9:-4] for p in PIPE_GOLDEN])
+def test_oracle_pipeline_matches_reference_code_fixture(path):
+    """oracle.nets.pipeline (encoder + wct_tf | adain + decoder + level wiring) == the reference's WCTModel code."""
+    g, targets, w = load_pipeline_fixture(path)
+    alpha, adain = float(g["alpha"]), bool(g["adain"])
+    o64, info = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf",
+                              dtype=np.float64, return_info=True)
+    assert o64.shape == g["out_ref_fp64"].shape
+    assert np.abs(o64 - g["out_ref_fp64"]).max() <= 1e-9          # same algorithm in exact arithmetic
+    if not adain:
+        assert [(i["k_c"], i["k_s"]) for i in info] == [tuple(r) for r in g["k"].tolist()]
+    o32 = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf", dtype=np.float32)
+    noise = np.abs(g["out_ref_fp32"] - g["out_ref_fp64"]).max()     # the reference code's own fp32 rounding (chained levels amplify it)
+    assert np.abs(o32 - g["out_ref_fp32"]).max() <= max(1e-4, 4 * noise)
+
+
+def test_reference_code_live_reproduces_fixture_if_present(tmp_path):
+    if not os.path.exists("/root/reference/model.py"):
+        pytest.skip("reference tree not mounted")
+    from tests.golden import np_tf1
+    from tests.t7_writer import write_vgg_t7
+    path = [p for p in PIPE_GOLDEN if "wct_31_11_odd" in p][0]
+    g, targets, w = load_pipeline_fixture(path)
+    t7 = str(tmp_path / "vgg.t7")
+    write_vgg_t7(t7, w["vgg"])
+    dec = {l["name"]: (l["kernel"], l["bias"]) for t in targets for l in w["decoders"][t]}
+    with np_tf1.reference_modules() as ref:
+        out, levels = np_tf1.run_reference(ref, g["content"][None] / 255.0, g["style"][None] / 255.0, t7, dec, targets,
+                                           float(g["alpha"]), bool(g["adain"]), np.float64)
+    assert np.abs(out - g["out_ref_fp64"]).max() <= 1e-12
+    assert "tensorflow" not in __import__("sys").modules or not hasattr(__import__("sys").modules["tensorflow"], "placeholder_with_default")
