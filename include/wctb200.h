@@ -153,14 +153,21 @@ WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, in
  * (64/128/256; 0 = built-in heuristic).  Used by bench/profiling scripts. */
 WCTB200_API int wctb200_debug_set_conv_bn(int bn);
 /* 1 = one tile per CTA with all-TMEM accumulation, 2 = persistent CTAs with chunked register
- * accumulation, 3 = 2 + on-chip tap reuse of the activation patch and cluster-multicast weights.
- * Returns the implementation now selected. */
+ * accumulation with the Cin <= 64 layers on v4 (default), 3 = 2 + on-chip tap reuse through row-shifted
+ * descriptors and cluster-multicast weights (experiment), 4 = v4 everywhere (8x16 tiles, three kx-shifted
+ * patches, aligned ky reuse), 5 = v2 everywhere.  Returns the implementation now selected. */
 WCTB200_API int wctb200_debug_set_conv_impl(int impl);
 /* impl 2: CTAs per SM in the persistent grid (default 4; 1 = exactly one CTA per SM). */
 WCTB200_API int wctb200_debug_set_conv_oversub(int k);
 /* covariance: impl 1 = fp32 FFMA, 2 = tcgen05 on a centred split-fp16 copy (default);
  * lbo/sbo: MN-major descriptor strides in bytes (probe; negative keeps the current value). */
 WCTB200_API int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes);
+/* conv v4 (aligned tap reuse): cluster 1|2 (weight multicast), largest Cin the default dispatch sends to v4; <0 keeps. */
+WCTB200_API int wctb200_debug_set_conv4(int cluster, int cin_max);
+/* conv v4 timeline probe: device buffer of 1024 int64 receiving clock64 samples of CTA 0 (NULL = off). */
+WCTB200_API int wctb200_debug_conv4_trace(void* dev_buf_1024_i64);
+/* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = keep.  Returns lg. */
+WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
 WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 

@@ -102,6 +102,9 @@ CONV_CASES = [
     (1, 8, 130, 64, 64, True),         # 2-D tiles (4 x 30), ragged right edge
     (2, 9, 128, 128, 128, True),       # 2-D tiles, ragged bottom edge, batch
     (1, 37, 260, 64, 64, False),
+    (1, 13, 40, 64, 64, True),         # v4 tiles (8 x 16), ragged in both directions (edge tiles shift inwards)
+    (3, 16, 48, 64, 128, True),        # v4, odd number of M tiles per cluster pair, two cout tiles at BN=64
+    (1, 24, 16, 192, 64, True),        # v4, three 64-channel slices
 ]
 
 
@@ -128,7 +131,7 @@ def test_conv3x3_ref_kernel(case):
     assert_close(got, ref, name="conv_ref_%d_%d" % (cin, cout))
 
 
-@pytest.mark.parametrize("impl", [3, 2, 1])
+@pytest.mark.parametrize("impl", [4, 41, 3, 2, 5, 1])     # 41 = impl 4 without the CTA-pair weight multicast
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
 def test_conv3x3_tensor_core(case, bn, impl):
@@ -141,10 +144,12 @@ def test_conv3x3_tensor_core(case, bn, impl):
     d_k, d_b = U.dev(k), U.dev(b)
     _capi.check(U.lib().wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
     out = U.act_alloc(n, h, w, cout)
+    if impl in (3, 4, 41) and bn == 256:
+        pytest.skip("impl 3/4 tiles are 64 or 128 wide")
     U.lib().wctb200_debug_set_conv_bn(bn)
+    U.lib().wctb200_debug_set_conv4(1 if impl == 41 else 2, -1)
+    impl = 4 if impl == 41 else impl
     U.lib().wctb200_debug_set_conv_impl(impl)
-    if impl == 3 and bn == 256:
-        pytest.skip("impl 3 tiles are 64 or 128 wide")
     try:
         _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,
                                             _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
@@ -152,6 +157,7 @@ def test_conv3x3_tensor_core(case, bn, impl):
     finally:
         U.lib().wctb200_debug_set_conv_bn(0)
         U.lib().wctb200_debug_set_conv_impl(2)
+        U.lib().wctb200_debug_set_conv4(2, -1)
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
     # impl 1 accumulates the whole K loop in TMEM: the tensor core adds into its fp32 accumulator
@@ -190,7 +196,8 @@ def test_maxpool_same_and_upsample(shape):
 
 
 @pytest.mark.parametrize("clip", [False, True])
-@pytest.mark.parametrize("shape", [(1, 8, 8, 64), (2, 5, 7, 64), (1, 33, 3, 64)])
+@pytest.mark.parametrize("shape", [(1, 8, 8, 64), (2, 5, 7, 64), (1, 33, 3, 64),
+                                   (1, 32, 32, 64), (2, 37, 45, 64), (1, 64, 96, 64), (1, 40, 33, 128)])   # >= 32x32: tiled kernel
 def test_conv_tail(shape, clip):
     n, h, w, c = shape
     rng = np.random.default_rng(11)

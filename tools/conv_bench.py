@@ -1,4 +1,4 @@
-"""Per-layer conv micro-benchmark: every 3x3 layer shape of the 512x512 pipeline, impl 2 vs 3."""
+"""Per-layer conv micro-benchmark: every 3x3 layer shape of the 512x512 pipeline, v2 vs v4."""
 import os, sys, itertools
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,7 @@ from tests import gpu_util as U
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 SHAPES = [(512, 64, 64), (512, 64, 128), (256, 128, 128), (256, 128, 64), (256, 64, 128), (128, 128, 256), (128, 256, 256),
           (128, 256, 128), (64, 256, 512), (64, 512, 512), (64, 512, 256), (32, 512, 512)]
-CFGS = [("v2", 2, 0, 0), ("v3 c2", 3, 2, 0), ("v3 c1", 3, 1, 0), ("v3 c2 bn64", 3, 2, 64)]
+CFGS = [("v2", 5, 0, 0), ("v4 c2", 4, 2, 0), ("v4 c1", 4, 1, 0), ("v4 c2 bn64", 4, 2, 64), ("v4 c1 bn64", 4, 1, 64)]
 if os.environ.get("CONV_BENCH_ONLY"):
     idx = [int(v) for v in os.environ["CONV_BENCH_ONLY"].split(",")]
     SHAPES = [SHAPES[i] for i in idx]
@@ -29,7 +29,7 @@ for hw, cin, cout in SHAPES:
     row = "%-18s" % ("%dx%d %d->%d" % (hw, hw, cin, cout))
     for name, impl, cl, bn in CFGS:
         lib.wctb200_debug_set_conv_impl(impl)
-        lib.wctb200_debug_set_conv3(cl if cl else 2, 0)
+        lib.wctb200_debug_set_conv4(cl if cl else 2, -1)
         lib.wctb200_debug_set_conv_bn(bn)
         def run():
             _capi.check(lib.wctb200_conv3x3(xin.data_ptr(), B, hw, hw, cin, ws.data_ptr(), bias.data_ptr(), cout, 1, out.data_ptr(), U.stream()))
@@ -41,5 +41,5 @@ for hw, cin, cout in SHAPES:
         ms = e0.elapsed_time(e1) / 10
         row += "%9.0f (%4.0fus)" % (flops / ms / 1e9, ms * 1e3)
     print(row, flush=True)
-lib.wctb200_debug_set_conv_impl(2); lib.wctb200_debug_set_conv3(2, 0); lib.wctb200_debug_set_conv_bn(0)
+lib.wctb200_debug_set_conv_impl(2); lib.wctb200_debug_set_conv4(2, -1); lib.wctb200_debug_set_conv_bn(0)
 _capi.check(lib.wctb200_check_device(U.stream()))

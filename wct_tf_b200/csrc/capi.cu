@@ -79,6 +79,12 @@ extern int g_conv3_bo_mode;
 extern int g_conv_oversub;
 extern int g_cov_impl;
 extern int g_cov_lbo;
+extern int g_conv4_cluster;
+extern int g_conv4_cin_max;
+extern int g_conv4_dbg;
+extern long long* g_conv4_trace;
+extern int g_jacobi_lg;
+extern int g_jacobi_stagger;
 extern int g_cov_sbo;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
@@ -250,7 +256,7 @@ int wctb200_debug_set_conv_bn(int bn) {
     return 0;
 }
 int wctb200_debug_set_conv_impl(int impl) {
-    if (impl >= 1 && impl <= 3) g_conv_impl = impl;
+    if (impl >= 1 && impl <= 5) g_conv_impl = impl;
     return g_conv_impl;
 }
 int wctb200_debug_set_conv_oversub(int k) {
@@ -262,6 +268,21 @@ int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes) {
     if (lbo_bytes >= 0) g_cov_lbo = lbo_bytes;
     if (sbo_bytes >= 0) g_cov_sbo = sbo_bytes;
     return g_cov_impl;
+}
+int wctb200_debug_set_conv4(int cluster, int cin_max) {
+    if (cluster == 1 || cluster == 2) g_conv4_cluster = cluster;
+    if (cin_max >= 0 && cin_max < 100000) g_conv4_cin_max = cin_max;
+    if (cin_max >= 100000) g_conv4_dbg = cin_max - 100000;      // timing probes (conv_tc4.cu: Conv4Params::dbg)
+    return g_conv4_cluster;
+}
+int wctb200_debug_conv4_trace(void* dev_buf_1024_i64) {
+    g_conv4_trace = static_cast<long long*>(dev_buf_1024_i64);
+    return 0;
+}
+int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
+    if (lg_groups >= 0 && lg_groups <= 4) g_jacobi_lg = lg_groups;
+    if (stagger_cycles >= 0) g_jacobi_stagger = stagger_cycles;
+    return g_jacobi_lg;
 }
 int wctb200_debug_set_conv3(int cluster, int bo_mode) {
     g_conv3_cluster = cluster == 1 ? 1 : 2;

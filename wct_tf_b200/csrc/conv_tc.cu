@@ -541,10 +541,13 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
 }
 
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
-int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu)
+int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu); 4 = aligned tap reuse (conv_tc4.cu); 5 = v2 only
 
 int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
                        int flags, __half* out, int bn_override, cudaStream_t st);
+int launch_conv3x3_tc4(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
+                       int flags, __half* out, int bn_override, cudaStream_t st);
+extern int g_conv4_cin_max;
 
 int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __half* w_split, int taps, int nsets,
                       const float* bias, int Cout, int flags, __half* out, cudaStream_t st) {
@@ -558,6 +561,11 @@ int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __ha
     if (g_conv_impl == 3 && taps == 9 && nsets == 1) {
         const int r = launch_conv3x3_tc3(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
         if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v3 -> v2 below
+    }
+    // impl 4 = v4 for every shape it covers; impl 2 (default) sends only the L2-operand-bound layers (Cin <= 64) to v4
+    if ((g_conv_impl == 4 || (g_conv_impl == 2 && Cin <= g_conv4_cin_max)) && taps == 9 && nsets == 1) {
+        const int r = launch_conv3x3_tc4(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
+        if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v4 -> v2 below
     }
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     if (BN == 256) BN = 128;  // v1 default: 3-stage pipeline beats the 2-stage 256-wide tile until 2-CTA lands

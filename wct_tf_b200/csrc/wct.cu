@@ -193,74 +193,7 @@ struct JacobiCfg {
     static constexpr int SMEM_BYTES = 64 * NN * 4 + 64;
 };
 
-template <int NN>
-__device__ __forceinline__ float jacobi_pair(float* __restrict__ cx, float* __restrict__ cy, int lane, float tol,
-                                             float null2) {
-    using Cfg = JacobiCfg<NN>;
-    float x[Cfg::NV * Cfg::VEC], y[Cfg::NV * Cfg::VEC];
-#pragma unroll
-    for (int v = 0; v < Cfg::NV; ++v) {
-        const int off = (v * 32 + lane) * Cfg::VEC;
-        if (Cfg::VEC == 4) {
-            const float4 a = *reinterpret_cast<const float4*>(cx + off);
-            const float4 b = *reinterpret_cast<const float4*>(cy + off);
-            x[v * 4] = a.x; x[v * 4 + 1] = a.y; x[v * 4 + 2] = a.z; x[v * 4 + 3] = a.w;
-            y[v * 4] = b.x; y[v * 4 + 1] = b.y; y[v * 4 + 2] = b.z; y[v * 4 + 3] = b.w;
-        } else {
-            const float2 a = *reinterpret_cast<const float2*>(cx + off);
-            const float2 b = *reinterpret_cast<const float2*>(cy + off);
-            x[v * 2] = a.x; x[v * 2 + 1] = a.y;
-            y[v * 2] = b.x; y[v * 2 + 1] = b.y;
-        }
-    }
-    float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-    for (int i = 0; i < Cfg::NV * Cfg::VEC; ++i) {
-        al = fmaf(x[i], x[i], al);
-        be = fmaf(y[i], y[i], be);
-        ga = fmaf(x[i], y[i], ga);
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        al += __shfl_xor_sync(0xffffffffu, al, o);
-        be += __shfl_xor_sync(0xffffffffu, be, o);
-        ga += __shfl_xor_sync(0xffffffffu, ga, o);
-    }
-    const float nrm = sqrtf(al) * sqrtf(be);
-    if (!(nrm > 0.f) || fminf(al, be) <= null2) return 0.f;      // numerically null column: leave it alone
-    const float ratio = fabsf(ga) / nrm;
-    if (ratio <= tol) return ratio;
-    // rotation that makes the two columns orthogonal (Hestenes)
-    const float zeta = (be - al) / (2.f * ga);
-    const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
-    // c = 1 + cm1 with cm1 = -t^2/(sqrt(h)(1+sqrt(h))): for small angles c rounds to exactly 1 and
-    // [[1,-s],[s,1]] would GROW the columns by t^2/2 per rotation (eigenvalue bias ~ #rotations)
-    const float h = 1.f + t * t;
-    const float rh = sqrtf(h);
-    const float s = t / rh;
-    const float cm1 = -(t * t) / (rh * (1.f + rh));
-#pragma unroll
-    for (int v = 0; v < Cfg::NV; ++v) {
-        const int off = (v * 32 + lane) * Cfg::VEC;
-        float nx[Cfg::VEC], ny[Cfg::VEC];
-#pragma unroll
-        for (int e = 0; e < Cfg::VEC; ++e) {
-            const float xv = x[v * Cfg::VEC + e], yv = y[v * Cfg::VEC + e];
-            nx[e] = fmaf(cm1, xv, fmaf(-s, yv, xv));
-            ny[e] = fmaf(cm1, yv, fmaf(s, xv, yv));
-        }
-        if (Cfg::VEC == 4) {
-            *reinterpret_cast<float4*>(cx + off) = make_float4(nx[0], nx[1], nx[2], nx[3]);
-            *reinterpret_cast<float4*>(cy + off) = make_float4(ny[0], ny[1], ny[2], ny[3]);
-        } else {
-            *reinterpret_cast<float2*>(cx + off) = make_float2(nx[0], nx[1]);
-            *reinterpret_cast<float2*>(cy + off) = make_float2(ny[0], ny[1]);
-        }
-    }
-    return ratio;
-}
-
-// ---- register-blocked cross-pair rotation: operands live in registers as PACKED fp32 pairs
+// ---- register-blocked pair rotation: operands live in registers as PACKED fp32 pairs
 // (fma.rn.f32x2: two FMAs per instruction on sm_100), column norms are cached ----
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) {
@@ -274,84 +207,52 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// single-MUFU approximations (the CUDA intrinsics wrap these in range/denormal fix-ups: measured 25 FMUL +
+// 12 FSETP + 7 MUFU per rotation in the SASS of the previous version)
+__device__ __forceinline__ float rsqrt_ap(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ap(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-template <int HP>   // HP = packed pairs per lane per column = NN/64
-__device__ __forceinline__ void rot_regs(f32x2 (&x)[HP], f32x2 (&y)[HP], float& a, float& b, float tol, float& wmax) {
-    f32x2 d0 = 0ull, d1 = 0ull;                     // +0.0f pairs
-#pragma unroll
-    for (int i = 0; i < HP; ++i) {
-        if (i & 1) d1 = fma2(x[i], y[i], d1);
-        else d0 = fma2(x[i], y[i], d0);
-    }
-    float p0, p1, p2, p3;
-    unpack2(d0, p0, p1);
-    unpack2(d1, p2, p3);
-    float g = (p0 + p1) + (p2 + p3);
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-    const float ab = a * b;
-    if (!(ab > 0.f)) return;
-    const float ratio = fabsf(g) * rsqrtf(ab);
-    wmax = fmaxf(wmax, ratio);
-    if (ratio <= tol) return;
-    // Rotation angle: approximate (MUFU) arithmetic is fine for t -- any t yields an exact
-    // rotation as long as (c,s) is orthonormal; a slightly-off t only leaves a residual for the
-    // next sweep.  (c,s) come from r = h^-1/2 refined by one Newton step, and c is applied as
-    // 1 + cm1 so that small angles neither shrink nor grow the columns (no eigenvalue bias).
-    const float zeta = __fdividef(b - a, 2.f * g);
-    const float az = fabsf(zeta);
-    float t;
-    if (az > 1e8f) {
-        t = __fdividef(0.5f, zeta);                       // asymptote; avoids zeta^2 overflow
-    } else {
-        const float h2 = fmaf(zeta, zeta, 1.f);
-        t = __fdividef(copysignf(1.f, zeta), az + h2 * rsqrtf(h2));
-    }
-    const float h = fmaf(t, t, 1.f);
-    float r = rsqrtf(h);
+// Rotation parameters of one Hestenes step from g = x.y, a = |x|^2, b = |y|^2.
+//   * convergence test without a division:  |g| > tol*sqrt(ab)  <=>  g^2 > tol^2 * ab ; `flag` collects
+//     1 (some pair above tol: a further sweep is needed to VERIFY) and 2 (some pair above tol_q, the level
+//     from which one more quadratically convergent sweep cannot be trusted to land below tol);
+//   * t = tan(theta) = sgn(d) 2g / (|d| + sqrt(d^2 + 4g^2)),  d = b - a  (no zeta = d/2g, so nothing overflows
+//     for tiny g).  Approximate MUFU arithmetic is fine for t: ANY t gives an exact rotation as long as (c,s)
+//     is orthonormal, an inexact t only leaves a residual for the next sweep;
+//   * (c,s): r = h^-1/2 refined by one Newton step, s = t r, and c is applied as 1 + cm1 with
+//     cm1 = -s^2/(1+r), so that small angles neither shrink nor grow the columns (no eigenvalue bias).
+__device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol2, float tolq2, float& flag, float& t,
+                                            float& s, float& cm1) {
+    const float ab = a * b, gg = g * g;
+    const bool rot = gg > tol2 * ab;
+    flag = fmaxf(flag, gg > tolq2 * ab ? 2.f : (rot ? 1.f : 0.f));
+    const float d = b - a, g2 = g + g;
+    const float w2 = fmaf(d, d, g2 * g2);
+    const float w = w2 * rsqrt_ap(w2);
+    float tt = (d < 0.f ? -g2 : g2) * rcp_ap(fabsf(d) + w);
+    tt = rot ? tt : 0.f;                                   // (select, not arithmetic: discards the NaN of d = g = 0)
+    const float h = fmaf(tt, tt, 1.f);
+    float r = rsqrt_ap(h);
     r = r * fmaf(-0.5f * h, r * r, 1.5f);
-    const float s = t * r;
-    const float cm1 = -__fdividef(t * t * r, fmaf(h, r, 1.f));
-    const f32x2 s2 = pack2(s, s), ns2 = pack2(-s, -s), c2 = pack2(cm1, cm1);
-#pragma unroll
-    for (int i = 0; i < HP; ++i) {
-        const f32x2 xv = x[i], yv = y[i];
-        x[i] = fma2(c2, xv, fma2(ns2, yv, xv));       // x' = x + cm1*x - s*y
-        y[i] = fma2(c2, yv, fma2(s2, xv, yv));        // y' = y + cm1*y + s*x
-    }
-    a = fmaxf(fmaf(-t, g, a), 0.f);      // |x'|^2 = |x|^2 - t*g ,  |y'|^2 = |y|^2 + t*g
-    b = fmaxf(fmaf(t, g, b), 0.f);
+    t = tt;
+    s = tt * r;
+    cm1 = -(s * s) * rcp_ap(1.f + r);
 }
 
 // Two INDEPENDENT rotations (x0,y0) and (x1,y1) fused and branch-free so their long
 // dependency chains (dot -> 5-step shuffle reduction -> MUFU chain -> rotation) interleave:
-// the kernel is latency bound (ncu: 38 % issue utilisation with 16 warps per SM), and the
-// early-exit branches of rot_regs() kept the compiler from overlapping the pair.
-__device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol, float null2, float& wmax, float& t,
-                                            float& s, float& cm1) {
-    const float ab = a * b;
-    const bool pos = ab > 0.f && fminf(a, b) > null2;     // a column below the fp32 noise floor is left alone
-    const float ratio = pos ? fabsf(g) * rsqrtf(ab) : 0.f;
-    wmax = fmaxf(wmax, ratio);
-    const bool rot = ratio > tol;
-    const float gs = rot ? g : 1.f;
-    const float zeta = __fdividef(b - a, 2.f * gs);
-    const float az = fabsf(zeta);
-    const float h2 = fmaf(zeta, zeta, 1.f);
-    float tt = __fdividef(copysignf(1.f, zeta), az + h2 * rsqrtf(h2));
-    if (az > 1e8f) tt = __fdividef(0.5f, zeta);            // asymptote; avoids zeta^2 overflow
-    tt = rot ? tt : 0.f;
-    const float h = fmaf(tt, tt, 1.f);
-    float r = rsqrtf(h);
-    r = r * fmaf(-0.5f * h, r * r, 1.5f);
-    t = tt;
-    s = tt * r;
-    cm1 = -__fdividef(tt * tt * r, fmaf(h, r, 1.f));
-}
-
+// the kernel is latency bound (ncu: 38 % issue utilisation with 16 warps per SM).
 template <int HP>
 __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], float& a0, float& b0, f32x2 (&x1)[HP],
-                                          f32x2 (&y1)[HP], float& a1, float& b1, float tol, float null2, float& wmax) {
+                                          f32x2 (&y1)[HP], float& a1, float& b1, float tol2, float tolq2, float& flag) {
     f32x2 d00 = 0ull, d01 = 0ull, d10 = 0ull, d11 = 0ull;
 #pragma unroll
     for (int i = 0; i < HP; ++i) {
@@ -369,20 +270,20 @@ __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], floa
         g1 += __shfl_xor_sync(0xffffffffu, g1, o);
     }
     float t0, s0, c0, t1, s1, c1;
-    rot_scalars(g0, a0, b0, tol, null2, wmax, t0, s0, c0);
-    rot_scalars(g1, a1, b1, tol, null2, wmax, t1, s1, c1);
+    rot_scalars(g0, a0, b0, tol2, tolq2, flag, t0, s0, c0);
+    rot_scalars(g1, a1, b1, tol2, tolq2, flag, t1, s1, c1);
     if (t0 != 0.f || t1 != 0.f) {          // warp-uniform: skip the FMAs only when BOTH pairs are already orthogonal
         const f32x2 s20 = pack2(s0, s0), ns20 = pack2(-s0, -s0), c20 = pack2(c0, c0);
         const f32x2 s21 = pack2(s1, s1), ns21 = pack2(-s1, -s1), c21 = pack2(c1, c1);
 #pragma unroll
         for (int i = 0; i < HP; ++i) {
             const f32x2 xa = x0[i], ya = y0[i], xb = x1[i], yb = y1[i];
-            x0[i] = fma2(c20, xa, fma2(ns20, ya, xa));
-            y0[i] = fma2(c20, ya, fma2(s20, xa, ya));
+            x0[i] = fma2(c20, xa, fma2(ns20, ya, xa));       // x' = x + cm1*x - s*y
+            y0[i] = fma2(c20, ya, fma2(s20, xa, ya));        // y' = y + cm1*y + s*x
             x1[i] = fma2(c21, xb, fma2(ns21, yb, xb));
             y1[i] = fma2(c21, yb, fma2(s21, xb, yb));
         }
-        a0 = fmaxf(fmaf(-t0, g0, a0), 0.f); b0 = fmaxf(fmaf(t0, g0, b0), 0.f);
+        a0 = fmaxf(fmaf(-t0, g0, a0), 0.f); b0 = fmaxf(fmaf(t0, g0, b0), 0.f);   // |x'|^2 = |x|^2 - t g , |y'|^2 = |y|^2 + t g
         a1 = fmaxf(fmaf(-t1, g1, a1), 0.f); b1 = fmaxf(fmaf(t1, g1, b1), 0.f);
     }
 }
@@ -413,13 +314,64 @@ __device__ __forceinline__ void store_col(float* __restrict__ c, int lane, const
     }
 }
 
-// 512 threads = 16 warps.  Cross phase: warp w keeps top columns 2w,2w+1 in REGISTERS for the
-// whole round and walks over the 16 bottom column pairs; each bottom pair is loaded/stored once
-// per 4 rotations (shared-memory traffic /4 vs one pair per warp), column norms are cached and
-// updated analytically, so a rotation costs one dot product instead of three.
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// All pairs between the two columns x0,x1 held in REGISTERS by this warp (cached squared norms a0,a1) and the
+// `npairs` column pairs of the shared-memory sub-block starting at bot0: npairs steps x 4 rotations.  Each bottom
+// pair is loaded/stored once per 4 rotations, column norms are cached in nrm[] and updated analytically, so a
+// rotation costs one dot product instead of three.  The `npairs` warps that share the sub-block form a ring
+// (warp wsub starts at pair wsub) and synchronise on their own named barrier `bar` (32*npairs threads): groups
+// working on disjoint sub-blocks run out of phase, so one group's FMA bursts fill the other's latency chains.
+template <int NN>
+__device__ __forceinline__ void ring_steps(float* cols, float* nrm, f32x2 (&x0)[NN / 64], f32x2 (&x1)[NN / 64], float& a0,
+                                           float& a1, int bot0, int npairs, int wsub, int bar, int lane, float tol2,
+                                           float tolq2, float& flag) {
+    constexpr int HP = NN / 64;
+    for (int s = 0; s < npairs; ++s) {
+        const int j = bot0 + 2 * ((wsub + s) & (npairs - 1));
+        float* cy0 = cols + j * NN;
+        float* cy1 = cy0 + NN;
+        f32x2 y0[HP], y1[HP];
+        load_col<NN>(cy0, lane, y0);
+        load_col<NN>(cy1, lane, y1);
+        float b0 = nrm[j], b1 = nrm[j + 1];
+        rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, flag);
+        rot_regs2<HP>(x0, y1, a0, b1, x1, y0, a1, b0, tol2, tolq2, flag);
+        store_col<NN>(cy0, lane, y0);
+        store_col<NN>(cy1, lane, y1);
+        if (lane == 0) { nrm[j] = b0; nrm[j + 1] = b1; }
+        if (npairs > 1) group_bar(bar, 32 * npairs);
+        else __syncwarp();
+    }
+}
+
+// tops (top, top+1) from shared memory, one ring pass, tops back to shared memory (the pairs INSIDE a block)
+template <int NN>
+__device__ __forceinline__ void cross_steps(float* cols, float* nrm, int top, int bot0, int npairs, int wsub, int bar,
+                                            int lane, float tol2, float tolq2, float& flag) {
+    constexpr int HP = NN / 64;
+    f32x2 x0[HP], x1[HP];
+    load_col<NN>(cols + top * NN, lane, x0);
+    load_col<NN>(cols + (top + 1) * NN, lane, x1);
+    float a0 = nrm[top], a1 = nrm[top + 1];
+    ring_steps<NN>(cols, nrm, x0, x1, a0, a1, bot0, npairs, wsub, bar, lane, tol2, tolq2, flag);
+    store_col<NN>(cols + top * NN, lane, x0);
+    store_col<NN>(cols + (top + 1) * NN, lane, x1);
+    if (lane == 0) { nrm[top] = a0; nrm[top + 1] = a1; }
+}
+
+// 512 threads = 16 warps, 64 columns (a "top" and a "bottom" block of 32) in shared memory.
+//   every round : the 32x32 cross pairs: warp w keeps top columns 2w,2w+1 in registers; the warps split into
+//                 2^lg groups, group g walks bottom sub-block g^h in sub-round h (ring of 16>>lg warps on a named
+//                 barrier), groups start `stagger` cycles apart so that they stay out of phase;
+//   round 0     : additionally the pairs INSIDE both blocks, by recursive halving with the same register-blocked
+//                 step (16|16 -> 8|8 -> 4|4 -> 2|2 -> 1|1 : 8+4+2+1+1 steps instead of 62 one-pair-per-warp steps).
 template <int NN>
 __global__ void __launch_bounds__(512, 1)
-k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol) {
+k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol,
+         int lg, int stagger) {
     using Cfg = JacobiCfg<NN>;
     constexpr int P = Cfg::P;
     constexpr int NB = 2 * P;
@@ -440,12 +392,16 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     // columns orthogonal to the large ones is what makes their Rayleigh quotients (k_rayleigh) second-order
     // small.  (A variant that left columns below 4*eps*max|column| alone was measured: the untouched columns
     // keep large range-space components and their Rayleigh quotients are O(lambda).)
-    const float null2 = 0.f;
+    const float tol2 = tol * tol;
+    // Quadratic convergence: a sweep whose largest cosine was rho leaves ~rho^2 behind.  When a sweep saw
+    // nothing above tol_q = 1e-4 (rho^2 = 1e-8 << tol ~ 2.7e-6) its own rotations already finished the job and
+    // the verification sweep (no rotations, ~60 % of a sweep's cost) is skipped.
+    const float tolq2 = 1e-4f * 1e-4f;
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
         if (threadIdx.x == 0) s_max = 0u;
-        float wmax = 0.f;
+        float flag = 0.f;
         for (int r = 0; r < (P == 1 ? 1 : M); ++r) {
             int bt, bb;
             if (P == 1) { bt = 0; bb = 1; }
@@ -461,19 +417,6 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                 }
             }
             __syncthreads();
-            // ---- pairs inside each 32-column block: once per sweep, plain one-pair-per-warp steps
-            if (r == 0) {
-                for (int half = 0; half < 2; ++half) {
-                    float* base = cols + half * 32 * NN;
-                    for (int s = 0; s < 31; ++s) {
-                        int a, b;
-                        if (warp == 0) { a = 31; b = s; }
-                        else { a = (s + warp) % 31; b = (s - warp + 31) % 31; }
-                        wmax = fmaxf(wmax, jacobi_pair<NN>(base + a * NN, base + b * NN, lane, tol, null2));
-                        __syncthreads();
-                    }
-                }
-            }
             // ---- column norms (fresh every round: the cached values never drift far)
             for (int c = warp * 4; c < warp * 4 + 4; ++c) {
                 f32x2 v[HP];
@@ -489,31 +432,53 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                 if (lane == 0) nrm[c] = ss;
             }
             __syncthreads();
+            // ---- pairs inside each 32-column block: once per sweep
+            if (r == 0) {
+                for (int lv = 3; lv >= 0; --lv) {          // sub-block halves of 16, 8, 4, 2 columns
+                    const int wpg = 1 << lv;               // warps per sub-block pair = column pairs per half
+                    const int base = (warp >> lv) * (4 << lv);
+                    cross_steps<NN>(cols, nrm, base + 2 * (warp & (wpg - 1)), base + (2 << lv), wpg, warp & (wpg - 1),
+                                    1 + (warp >> lv), lane, tol2, tolq2, flag);
+                    __syncthreads();
+                }
+                {   // 1|1 : columns (4w,4w+1) and (4w+2,4w+3)
+                    f32x2 x0[HP], y0[HP], x1[HP], y1[HP];
+                    float* c0 = cols + 4 * warp * NN;
+                    load_col<NN>(c0, lane, x0);
+                    load_col<NN>(c0 + NN, lane, y0);
+                    load_col<NN>(c0 + 2 * NN, lane, x1);
+                    load_col<NN>(c0 + 3 * NN, lane, y1);
+                    float a0 = nrm[4 * warp], b0 = nrm[4 * warp + 1], a1 = nrm[4 * warp + 2], b1 = nrm[4 * warp + 3];
+                    rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, flag);
+                    store_col<NN>(c0, lane, x0);
+                    store_col<NN>(c0 + NN, lane, y0);
+                    store_col<NN>(c0 + 2 * NN, lane, x1);
+                    store_col<NN>(c0 + 3 * NN, lane, y1);
+                    if (lane == 0) { nrm[4 * warp] = a0; nrm[4 * warp + 1] = b0; nrm[4 * warp + 2] = a1; nrm[4 * warp + 3] = b1; }
+                    __syncthreads();
+                }
+            }
             // ---- cross pairs: 16 steps x 4 rotations per warp
             {
                 f32x2 x0[HP], x1[HP];
-                load_col<NN>(cols + (2 * warp) * NN, lane, x0);
+                load_col<NN>(cols + 2 * warp * NN, lane, x0);
                 load_col<NN>(cols + (2 * warp + 1) * NN, lane, x1);
                 float a0 = nrm[2 * warp], a1 = nrm[2 * warp + 1];
-                for (int s = 0; s < 16; ++s) {
-                    const int j = (warp + s) & 15;
-                    float* cy0 = cols + (32 + 2 * j) * NN;
-                    float* cy1 = cy0 + NN;
-                    f32x2 y0[HP], y1[HP];
-                    load_col<NN>(cy0, lane, y0);
-                    load_col<NN>(cy1, lane, y1);
-                    float b0 = nrm[32 + 2 * j], b1 = nrm[32 + 2 * j + 1];
-                    rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol, null2, wmax);
-                    rot_regs2<HP>(x0, y1, a0, b1, x1, y0, a1, b0, tol, null2, wmax);
-                    store_col<NN>(cy0, lane, y0);
-                    store_col<NN>(cy1, lane, y1);
-                    if (lane == 0) { nrm[32 + 2 * j] = b0; nrm[32 + 2 * j + 1] = b1; }
+                const int ring = 16 >> lg;                         // warps per group = bottom pairs per sub-block
+                const int grp = warp / ring, wsub = warp & (ring - 1);
+                for (int h = 0; h < (1 << lg); ++h) {
+                    if (stagger > 0 && grp > 0) {
+                        const long long t0 = clock64();
+                        while (clock64() - t0 < (long long)grp * stagger) {}
+                    }
+                    ring_steps<NN>(cols, nrm, x0, x1, a0, a1, 32 + 2 * ring * (grp ^ h), ring, wsub, 1 + grp, lane, tol2,
+                                   tolq2, flag);
                     __syncthreads();
                 }
-                store_col<NN>(cols + (2 * warp) * NN, lane, x0);
+                store_col<NN>(cols + 2 * warp * NN, lane, x0);
                 store_col<NN>(cols + (2 * warp + 1) * NN, lane, x1);
+                __syncthreads();
             }
-            __syncthreads();
             if (P > 1) {
                 float4* d0 = reinterpret_cast<float4*>(G + (long long)bt * 32 * NN);
                 float4* d1 = reinterpret_cast<float4*>(G + (long long)bb * 32 * NN);
@@ -526,8 +491,8 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                 cluster.sync();   // release/acquire: next round reads what the peers just wrote
             }
         }
-        // ---- convergence: largest |x.y| / (|x||y|) seen in this sweep, agreed across the cluster
-        if (lane == 0) atomicMax(&s_max, __float_as_uint(wmax));
+        // ---- convergence: worst pair class seen in this sweep (0 / 1 / 2), agreed across the cluster
+        if (lane == 0) atomicMax(&s_max, __float_as_uint(flag));
         __syncthreads();
         float gmax = __uint_as_float(s_max);
         if (P > 1) {
@@ -541,7 +506,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             cluster.sync();   // everyone has read before the next sweep overwrites
         }
         __syncthreads();
-        if (gmax <= tol) { ++sweep; break; }
+        if (gmax < 2.f) { ++sweep; break; }
     }
     if (P == 1) {
         float4* d = reinterpret_cast<float4*>(G);
@@ -835,6 +800,10 @@ static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq,
     return 0;
 }
 
+// cross-phase schedule of k_jacobi: 2^lg warp groups, started `stagger` cycles apart (wctb200_debug_set_jacobi)
+int g_jacobi_lg = 1;
+int g_jacobi_stagger = 600;
+
 int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
     const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
     const int max_sweeps = 40;
@@ -858,7 +827,8 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
             done = true;                                                                                             \
         }                                                                                                            \
         cfg.dynamicSmemBytes = JacobiCfg<NN>::SMEM_BYTES;                                                            \
-        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol));                      \
+        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, g_jacobi_lg,           \
+                                     g_jacobi_stagger));                                                            \
         break;                                                                                                       \
     }
     switch (C) {
