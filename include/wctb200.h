@@ -162,11 +162,13 @@ WCTB200_API int wctb200_debug_set_conv_oversub(int k);
 /* covariance: impl 1 = fp32 FFMA, 2 = tcgen05 on a centred split-fp16 copy (default);
  * lbo/sbo: MN-major descriptor strides in bytes (probe; negative keeps the current value). */
 WCTB200_API int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes);
+/* conv v2: fuse the a_hi*b_hi and a_hi*b_lo products into one N = 2*tile MMA: -1 auto (default), 0 never, 1 always. */
+WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
 /* conv v4 (aligned tap reuse): cluster 1|2 (weight multicast), largest Cin the default dispatch sends to v4; <0 keeps. */
 WCTB200_API int wctb200_debug_set_conv4(int cluster, int cin_max);
 /* conv v4 timeline probe: device buffer of 1024 int64 receiving clock64 samples of CTA 0 (NULL = off). */
 WCTB200_API int wctb200_debug_conv4_trace(void* dev_buf_1024_i64);
-/* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = keep.  Returns lg. */
+/* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = per-size default. */
 WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
 WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);

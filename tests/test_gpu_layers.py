@@ -131,7 +131,7 @@ def test_conv3x3_ref_kernel(case):
     assert_close(got, ref, name="conv_ref_%d_%d" % (cin, cout))
 
 
-@pytest.mark.parametrize("impl", [4, 41, 3, 2, 5, 1])     # 41 = impl 4 without the CTA-pair weight multicast
+@pytest.mark.parametrize("impl", [4, 41, 3, 2, 50, 51, 1])     # 41 = impl 4 without the CTA-pair weight multicast; 50/51 = v2 with the fused [b_hi|b_lo] MMA off/on
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
 def test_conv3x3_tensor_core(case, bn, impl):
@@ -148,7 +148,8 @@ def test_conv3x3_tensor_core(case, bn, impl):
         pytest.skip("impl 3/4 tiles are 64 or 128 wide")
     U.lib().wctb200_debug_set_conv_bn(bn)
     U.lib().wctb200_debug_set_conv4(1 if impl == 41 else 2, -1)
-    impl = 4 if impl == 41 else impl
+    U.lib().wctb200_debug_set_conv_fuse({50: 0, 51: 1}.get(impl, -1))
+    impl = {41: 4, 50: 5, 51: 5}.get(impl, impl)
     U.lib().wctb200_debug_set_conv_impl(impl)
     try:
         _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,
@@ -158,6 +159,7 @@ def test_conv3x3_tensor_core(case, bn, impl):
         U.lib().wctb200_debug_set_conv_bn(0)
         U.lib().wctb200_debug_set_conv_impl(2)
         U.lib().wctb200_debug_set_conv4(2, -1)
+        U.lib().wctb200_debug_set_conv_fuse(-1)
     got = U.act_to_numpy(out, n, h, w, cout)
     ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
     # impl 1 accumulates the whole K loop in TMEM: the tensor core adds into its fp32 accumulator

@@ -47,6 +47,7 @@ SIGNATURES = {
     "wctb200_debug_set_cov": (_i, [_i, _i, _i]),
     "wctb200_debug_set_jacobi": (_i, [_i, _i]),
     "wctb200_debug_set_conv4": (_i, [_i, _i]),
+    "wctb200_debug_set_conv_fuse": (_i, [_i]),
     "wctb200_debug_conv4_trace": (_i, [_vp]),
 }
 

@@ -79,6 +79,7 @@ extern int g_conv3_bo_mode;
 extern int g_conv_oversub;
 extern int g_cov_impl;
 extern int g_cov_lbo;
+extern int g_conv_fuse;
 extern int g_conv4_cluster;
 extern int g_conv4_cin_max;
 extern int g_conv4_dbg;
@@ -269,6 +270,10 @@ int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes) {
     if (sbo_bytes >= 0) g_cov_sbo = sbo_bytes;
     return g_cov_impl;
 }
+int wctb200_debug_set_conv_fuse(int mode) {
+    g_conv_fuse = mode < 0 ? -1 : (mode ? 1 : 0);
+    return g_conv_fuse;
+}
 int wctb200_debug_set_conv4(int cluster, int cin_max) {
     if (cluster == 1 || cluster == 2) g_conv4_cluster = cluster;
     if (cin_max >= 0 && cin_max < 100000) g_conv4_cin_max = cin_max;
@@ -280,8 +285,8 @@ int wctb200_debug_conv4_trace(void* dev_buf_1024_i64) {
     return 0;
 }
 int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
-    if (lg_groups >= 0 && lg_groups <= 4) g_jacobi_lg = lg_groups;
-    if (stagger_cycles >= 0) g_jacobi_stagger = stagger_cycles;
+    if (lg_groups <= 4) g_jacobi_lg = lg_groups < 0 ? -1 : lg_groups;              // negative: back to the per-size default
+    g_jacobi_stagger = stagger_cycles < 0 ? -1 : stagger_cycles;
     return g_jacobi_lg;
 }
 int wctb200_debug_set_conv3(int cluster, int bo_mode) {

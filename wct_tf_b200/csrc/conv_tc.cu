@@ -223,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //     overlaps the MMAs of chunk i+1 (also across tiles: the epilogue of tile t overlaps
 //     the main loop of tile t+1).
 // ===========================================================================
-template <int BN>
+template <int BN, bool FUSE_>
 struct Conv2Cfg {
     static constexpr int BM = 128;
     static constexpr int BK = 64;
@@ -231,8 +231,14 @@ struct Conv2Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int STAGES = BN == 64 ? 4 : (BN == 128 ? 3 : 2);
-    static constexpr int NBUF = BN == 256 ? 2 : 4;
-    static constexpr int TMEM_COLS = NBUF * BN;                 // 256 / 512 / 512
+    // FUSE: the products a_hi*b_hi and a_hi*b_lo share the A operand, and the two weight planes sit back to back in a
+    // stage, so ONE tcgen05.mma with N = 2*BN computes both into adjacent accumulator column ranges (summed when the
+    // chunk is drained); a_lo*b_hi follows with N = BN into the first range.  8 instead of 12 MMAs per k-iteration and
+    // half the A-operand shared-memory reads per flop (timeline probe: ~80 cycles per MMA regardless of N <= 128).
+    static constexpr bool FUSE = FUSE_ && BN <= 128;
+    static constexpr int ACC_COLS = FUSE ? 2 * BN : BN;         // TMEM columns of one accumulation buffer
+    static constexpr int NBUF = 512 / ACC_COLS >= 4 ? 4 : 2;
+    static constexpr int TMEM_COLS = NBUF * ACC_COLS;           // 512 / 512 / 512
     static constexpr int CH = 4;                                // k-iterations per accumulation chunk
     static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
@@ -267,11 +273,11 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
     return t;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(Conv2Cfg<BN>::THREADS, 1)
+template <int BN, bool FUSE_>
+__global__ void __launch_bounds__(Conv2Cfg<BN, FUSE_>::THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvParams p,
                 const int total_tiles, const int n_tiles) {
-    using Cfg = Conv2Cfg<BN>;
+    using Cfg = Conv2Cfg<BN, FUSE_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -342,6 +348,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, BN);
+            constexpr uint32_t idesc2 = umma_idesc_f16(Cfg::BM, Cfg::FUSE ? 2 * BN : BN);
             uint32_t itg = 0, cg_ = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 for (int c = 0; c < nchunks; ++c, ++cg_) {
@@ -349,7 +356,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const uint32_t bph = (cg_ / Cfg::NBUF) & 1;
                     mbar_wait(&tempty[b], bph ^ 1u, abort_flag, p.err, 0x400u + b);   // epilogue drained this buffer
                     tc_fence_after();
-                    const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
+                    const uint32_t tacc = tmem_base + (uint32_t)(b * Cfg::ACC_COLS);
                     const int it_end = min(kiters, (c + 1) * Cfg::CH);
                     for (int it = c * Cfg::CH; it < it_end; ++it, ++itg) {
                         const int s = itg % Cfg::STAGES;
@@ -365,9 +372,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < Cfg::BK / 16; ++k) {
                             const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                            umma_f16(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
-                            umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
-                            umma_f16(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
+                            if (Cfg::FUSE) {
+                                // [b_hi | b_lo] is one 2*BN-row K-major tile: columns [0,BN) += a_hi b_hi, [BN,2BN) += a_hi b_lo
+                                umma_f16(tacc, a_hi + ko, b_hi + ko, idesc2, (first && k == 0) ? 0u : 1u);
+                                umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                            } else {
+                                umma_f16(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
+                                umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                                umma_f16(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
+                            }
                         }
                         umma_commit(&empty[s]);
                     }
@@ -402,18 +415,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const uint32_t bph = (cg_ / Cfg::NBUF) & 1;
                 mbar_wait(&tfull[b], bph, abort_flag, p.err, 0x300u + b);
                 tc_fence_after();
-                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * BN + colbase);
+                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * Cfg::ACC_COLS + colbase);
+                if (Cfg::FUSE) {
 #pragma unroll
-                for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tsrc + c0, r0);
-                    if (c0 + 32 < Cfg::NACC) tmem_ld32(tsrc + c0 + 32, r1);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < Cfg::NACC; c0 += 32) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tsrc + c0, r0);               // a_hi b_hi + a_lo b_hi
+                        tmem_ld32(tsrc + BN + c0, r1);          // a_hi b_lo
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
-                    if (c0 + 32 < Cfg::NACC) {
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    }
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                    for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tsrc + c0, r0);
+                        if (c0 + 32 < Cfg::NACC) tmem_ld32(tsrc + c0 + 32, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+                        if (c0 + 32 < Cfg::NACC) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -516,14 +541,14 @@ static int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPar
 
 int g_conv_oversub = 4;
 
-template <int BN>
+template <int BN, bool FUSE_>
 static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_tiles, int n_tiles,
                       cudaStream_t st) {
-    using Cfg = Conv2Cfg<BN>;
+    using Cfg = Conv2Cfg<BN, FUSE_>;
     static bool attr_done = false;
     static int sms = 0;
     if (!attr_done) {
-        WCTB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        WCTB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         int dev = 0;
         WCTB_CUDA(cudaGetDevice(&dev));
         WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -535,11 +560,12 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
     // (a grid of exactly #SMs would run as two unbalanced waves).
     int grid = sms * (g_conv_oversub > 0 ? g_conv_oversub : 1);
     if (grid > total_tiles) grid = total_tiles;
-    conv_tc2_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p, total_tiles, n_tiles);
+    conv_tc2_kernel<BN, FUSE_><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p, total_tiles, n_tiles);
     WCTB_CHECK_LAUNCH("conv_tc2_kernel");
     return 0;
 }
 
+int g_conv_fuse = -1;        // -1 auto, 0 never, 1 whenever the tile allows (wctb200_debug_set_conv_fuse)
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
 int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu); 4 = aligned tap reuse (conv_tc4.cu); 5 = v2 only
 
@@ -593,9 +619,14 @@ int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __ha
         const int n_tiles = Cout / BN;
         const int total = (int)grid.x * n_tiles;
         switch (BN) {
-            case 64: return launch2_bn<64>(mA, mB, p, total, n_tiles, st);
-            case 128: return launch2_bn<128>(mA, mB, p, total, n_tiles, st);
-            default: return launch2_bn<256>(mA, mB, p, total, n_tiles, st);
+            // fused [b_hi|b_lo] MMAs (Conv2Cfg::FUSE): always at BN=64 (4 TMEM buffers stay); at BN=128 the ring shrinks to 2
+            // buffers, which only pays for long K loops (measured: Cin=128 -9 %, Cin>=256 +3..5 %)
+            case 64: return g_conv_fuse == 0 ? launch2_bn<64, false>(mA, mB, p, total, n_tiles, st)
+                                             : launch2_bn<64, true>(mA, mB, p, total, n_tiles, st);
+            case 128: return (g_conv_fuse == 1 || (g_conv_fuse < 0 && (long long)taps * Cin >= 9 * 256))
+                                 ? launch2_bn<128, true>(mA, mB, p, total, n_tiles, st)
+                                 : launch2_bn<128, false>(mA, mB, p, total, n_tiles, st);
+            default: return launch2_bn<256, false>(mA, mB, p, total, n_tiles, st);
         }
     }
     switch (BN) {

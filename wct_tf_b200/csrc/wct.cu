@@ -801,12 +801,16 @@ static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq,
 }
 
 // cross-phase schedule of k_jacobi: 2^lg warp groups, started `stagger` cycles apart (wctb200_debug_set_jacobi)
-int g_jacobi_lg = 1;
-int g_jacobi_stagger = 600;
+// -1 = auto: measured best on B200 (tools/jacobi_bench.py): C=512 -> 4 groups 300 cycles apart (6.76 ms vs 7.80 ms for
+// one group), smaller matrices -> 2 groups 600 cycles apart.
+int g_jacobi_lg = -1;
+int g_jacobi_stagger = -1;
 
 int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
     const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
     const int max_sweeps = 40;
+    const int lg = g_jacobi_lg >= 0 ? g_jacobi_lg : (C >= 512 ? 2 : 1);
+    const int stagger = g_jacobi_stagger >= 0 ? g_jacobi_stagger : (C >= 512 ? 300 : 600);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(C / 64), (unsigned)count, 1);
     cfg.blockDim = dim3(512, 1, 1);
@@ -827,8 +831,7 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
             done = true;                                                                                             \
         }                                                                                                            \
         cfg.dynamicSmemBytes = JacobiCfg<NN>::SMEM_BYTES;                                                            \
-        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, g_jacobi_lg,           \
-                                     g_jacobi_stagger));                                                            \
+        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, lg, stagger));         \
         break;                                                                                                       \
     }
     switch (C) {
