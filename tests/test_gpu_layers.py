@@ -1,5 +1,7 @@
 """GPU parity: encoder/decoder layers through the C-ABI vs the CPU oracle.
 Tolerances are on fp32-class arithmetic: 2e-5 * (1 + |ref|)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -131,7 +133,11 @@ def test_conv3x3_ref_kernel(case):
     assert_close(got, ref, name="conv_ref_%d_%d" % (cin, cout))
 
 
-@pytest.mark.parametrize("impl", [4, 41, 3, 2, 50, 51, 1])     # 41 = impl 4 without the CTA-pair weight multicast; 50/51 = v2 with the fused [b_hi|b_lo] MMA off/on
+# 6 = v2 on CTA pairs (tcgen05 cta_group::2); WCTB_TEST_CONV_IMPLS narrows the list while developing a kernel
+CONV_IMPLS = [int(v) for v in os.environ.get("WCTB_TEST_CONV_IMPLS", "6,4,41,42,3,2,50,51,1").split(",")]
+
+
+@pytest.mark.parametrize("impl", CONV_IMPLS)     # 41 = impl 4 without the CTA-pair weight multicast; 50/51 = v2 with the fused [b_hi|b_lo] MMA off/on
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
 def test_conv3x3_tensor_core(case, bn, impl):
@@ -144,12 +150,12 @@ def test_conv3x3_tensor_core(case, bn, impl):
     d_k, d_b = U.dev(k), U.dev(b)
     _capi.check(U.lib().wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
     out = U.act_alloc(n, h, w, cout)
-    if impl in (3, 4, 41) and bn == 256:
+    if impl in (3, 4, 41, 42, 6) and bn == 256:
         pytest.skip("impl 3/4 tiles are 64 or 128 wide")
     U.lib().wctb200_debug_set_conv_bn(bn)
     U.lib().wctb200_debug_set_conv4(1 if impl == 41 else 2, -1)
-    U.lib().wctb200_debug_set_conv_fuse({50: 0, 51: 1}.get(impl, -1))
-    impl = {41: 4, 50: 5, 51: 5}.get(impl, impl)
+    U.lib().wctb200_debug_set_conv_fuse({50: 0, 51: 1, 42: 1}.get(impl, -1))      # 42 = impl 4 with the fused MMA forced on
+    impl = {41: 4, 42: 4, 50: 5, 51: 5}.get(impl, impl)
     U.lib().wctb200_debug_set_conv_impl(impl)
     try:
         _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,

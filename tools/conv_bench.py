@@ -8,7 +8,7 @@ from tests import gpu_util as U
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 SHAPES = [(512, 64, 64), (512, 64, 128), (256, 128, 128), (256, 128, 64), (256, 64, 128), (128, 128, 256), (128, 256, 256),
           (128, 256, 128), (64, 256, 512), (64, 512, 512), (64, 512, 256), (32, 512, 512)]
-CFGS = [("v2", 5, 0, 0), ("v4 c2", 4, 2, 0), ("v4 c1", 4, 1, 0), ("v4 c2 bn64", 4, 2, 64), ("v4 c1 bn64", 4, 1, 64)]
+CFGS = [("v2", 5, 0, 0, -1), ("v2 nofuse", 5, 0, 0, 0), ("pairs", 6, 0, 0, -1), ("pairs bn64", 6, 0, 64, -1), ("v4 c2", 4, 2, 0, -1)]
 if os.environ.get("CONV_BENCH_ONLY"):
     idx = [int(v) for v in os.environ["CONV_BENCH_ONLY"].split(",")]
     SHAPES = [SHAPES[i] for i in idx]
@@ -27,7 +27,8 @@ for hw, cin, cout in SHAPES:
     out = torch.empty(lib.wctb200_act_bytes(B, hw, hw, cout), dtype=torch.uint8, device="cuda")
     flops = 2.0 * 9 * cin * cout * B * hw * hw
     row = "%-18s" % ("%dx%d %d->%d" % (hw, hw, cin, cout))
-    for name, impl, cl, bn in CFGS:
+    for name, impl, cl, bn, fuse in CFGS:
+        lib.wctb200_debug_set_conv_fuse(fuse)
         lib.wctb200_debug_set_conv_impl(impl)
         lib.wctb200_debug_set_conv4(cl if cl else 2, -1)
         lib.wctb200_debug_set_conv_bn(bn)
@@ -41,5 +42,5 @@ for hw, cin, cout in SHAPES:
         ms = e0.elapsed_time(e1) / 10
         row += "%9.0f (%4.0fus)" % (flops / ms / 1e9, ms * 1e3)
     print(row, flush=True)
-lib.wctb200_debug_set_conv_impl(2); lib.wctb200_debug_set_conv4(2, -1); lib.wctb200_debug_set_conv_bn(0)
+lib.wctb200_debug_set_conv_fuse(-1); lib.wctb200_debug_set_conv_impl(2); lib.wctb200_debug_set_conv4(2, -1); lib.wctb200_debug_set_conv_bn(0)
 _capi.check(lib.wctb200_check_device(U.stream()))

@@ -37,3 +37,23 @@ for ms, k, n, fl, by in rows:
     if fl: extra = " %.0f TFLOP/s" % (fl / ms / 1e9)
     elif by: extra = " %.0f GB/s" % (by / ms / 1e6)
     print("%-28s n=%3d %8.3f ms %5.1f%%%s" % (k, n, ms, 100 * ms / acc, extra))
+
+# ---- overlapped schedule: host enqueue time vs device time
+import time
+eng.profile = None
+eng.overlap_style = True
+eng.groups = 4
+for _ in range(2):
+    eng.to_u8(eng.stylize(c, s, alpha=0.8))
+torch.cuda.synchronize()
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    out = eng.to_u8(eng.stylize(c, s, alpha=0.8))
+    e1.record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print("overlapped step: host enqueue %.1f ms, host until done %.1f ms, device %.1f ms, launches %d" % (
+        (t1 - t0) * 1e3, (t2 - t0) * 1e3, e0.elapsed_time(e1), getattr(eng, "launches", -1)))

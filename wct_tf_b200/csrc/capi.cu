@@ -257,7 +257,7 @@ int wctb200_debug_set_conv_bn(int bn) {
     return 0;
 }
 int wctb200_debug_set_conv_impl(int impl) {
-    if (impl >= 1 && impl <= 5) g_conv_impl = impl;
+    if (impl >= 1 && impl <= 6) g_conv_impl = impl;
     return g_conv_impl;
 }
 int wctb200_debug_set_conv_oversub(int k) {

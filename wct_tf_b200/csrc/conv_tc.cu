@@ -483,6 +483,257 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ===========================================================================
+// v5: v2 on CTA PAIRS (tcgen05 cta_group::2).  A timeline probe of the MMA-issuing thread showed every
+// single-CTA tcgen05.mma (M=128, K=16) occupying the tensor pipe for >= 80 cycles (N=64) .. ~115 cycles (N=128):
+// 40-55 % of the nominal rate.  A pair of CTAs on the two SMs of a TPC executes ONE M=256 instruction: each CTA
+// supplies its own 128 activation rows and HALF of the weight tile (N/2 rows), accumulators stay in each CTA's own
+// TMEM.  Per CTA the weight traffic halves and the operand shared-memory reads per flop drop by a third.
+//   * both CTAs run the TMA producer (own A tile + own half of B); every load completes on the LEADER's `full`
+//     barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address mapped with mapa);
+//   * only the leader's elected thread issues tcgen05.mma.cta_group::2; stage release (`empty`) and chunk completion
+//     (`tfull`) are multicast commits to both CTAs;
+//   * both CTAs' epilogue warps drain their own TMEM and arrive on the leader's `tempty` (remote mbarrier arrive).
+// Everything else is v2 (persistent pairs, 4-k-iteration chunks summed in registers with RN adds, coalesced store).
+// ===========================================================================
+template <int BN>
+struct Conv5Cfg {
+    static constexpr int BM = 128;                              // rows per CTA (the MMA is M = 256)
+    static constexpr int BK = 64;
+    static constexpr int A_BYTES = BM * BK * 2;                 // one plane of this CTA's A tile
+    static constexpr int BH_BYTES = (BN / 2) * BK * 2;          // one plane of this CTA's HALF of the weight tile
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
+    static constexpr int STAGES = 4;
+    static constexpr int NBUF = 4;
+    static constexpr int TMEM_COLS = NBUF * BN;
+    static constexpr int CH = 4;
+    static constexpr int EPI_WARPS = 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int NACC = BN;
+    static constexpr int AUX_BYTES = 256 + BN * 4;
+    static constexpr int STG_BYTES = 4 * 8192;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + STG_BYTES + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(Conv5Cfg<BN>::THREADS, 1)
+conv_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvParams p,
+                const int total_q, const int n_tiles) {
+    using Cfg = Conv5Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tfull = empty + Cfg::STAGES;
+    uint64_t* tempty = tfull + Cfg::NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NBUF);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* sbias = reinterpret_cast<float*>(aux + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();                     // 0 = leader (issues the MMAs)
+    // NOTE: no early exit on a previous error: both CTAs of a pair must take the same path
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full[s], 1);                            // leader's copy is the live one: 1 arrive (leader producer) + tx bytes of both CTAs
+            mbar_init(&empty[s], 1);                           // multicast commit
+        }
+        for (int b = 0; b < Cfg::NBUF; ++b) {
+            mbar_init(&tfull[b], 1);                           // multicast commit
+            mbar_init(&tempty[b], 2 * Cfg::EPI_WARPS);         // leader's copy: epilogue warps of both CTAs
+        }
+        *abort_flag = 0;
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();                                         // peer barriers initialised before any remote arrive / multicast
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ksl = p.Cin / Cfg::BK;
+    const int kiters = p.taps * ksl;
+    const int nchunks = (kiters + Cfg::CH - 1) / Cfg::CH;
+    const int num_pairs = gridDim.x >> 1;
+    const int pid = blockIdx.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int q = pid; q < total_q; q += num_pairs) {
+                const int n0 = (q % n_tiles) * BN;
+                const long long p0 = (long long)(q / n_tiles) * 256 + rank * 128;
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&empty[s], ph ^ 1u, abort_flag, p.err, 0x500u + s);
+                    const int tap = it / ksl;
+                    const int ks = it - tap * ksl;
+                    const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
+                    const int row = (int)(p0 + off);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0u);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+                    const int kc = tap * p.Cin + ks * Cfg::BK;
+                    const int nrow = n0 + (int)rank * (BN / 2);
+                    tma_load_3d_2sm(st, &mapA, lbar, ks * Cfg::BK, row, 0);
+                    tma_load_3d_2sm(st + Cfg::A_BYTES, &mapA, lbar, ks * Cfg::BK, row, 1);
+                    tma_load_3d_2sm(st + 2 * Cfg::A_BYTES, &mapB, lbar, kc, nrow, 0);
+                    tma_load_3d_2sm(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &mapB, lbar, kc, nrow, 1);
+                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(256, BN);
+            int s = 0, b = 0;
+            uint32_t ph = 0, pht = 0;
+            for (int q = pid; q < total_q; q += num_pairs) {
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(&tempty[b], pht ^ 1u, abort_flag, p.err, 0x800u + b);   // both epilogues drained this buffer
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
+                    const int it_end = min(kiters, (c + 1) * Cfg::CH);
+                    for (int it = c * Cfg::CH; it < it_end; ++it) {
+                        mbar_wait(&full[s], ph, abort_flag, p.err, 0x600u + s);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                        const uint64_t a_hi = umma_desc_sw128(st);
+                        const uint64_t a_lo = umma_desc_sw128(st + Cfg::A_BYTES);
+                        const uint64_t b_hi = umma_desc_sw128(st + 2 * Cfg::A_BYTES);
+                        const uint64_t b_lo = umma_desc_sw128(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES);
+                        const bool first = (it == c * Cfg::CH);
+#pragma unroll
+                        for (int k = 0; k < Cfg::BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                            umma_f16_2sm(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
+                            umma_f16_2sm(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                            umma_f16_2sm(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
+                        }
+                        umma_commit_2sm(&empty[s]);
+                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
+                    }
+                    umma_commit_2sm(&tfull[b]);
+                    if (++b == Cfg::NBUF) { b = 0; pht ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int g = warp & 3;
+        const int et = threadIdx.x - 64;
+        constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
+        const long long HpWp = (long long)p.Hp * p.Wp;
+        const ActGeom go(p.N, p.H, p.W, p.Cout);
+        const bool relu = (p.flags & WCTB200_RELU) != 0;
+        int b = 0;
+        uint32_t pht = 0;
+        for (int q = pid; q < total_q; q += num_pairs) {
+            const int n0 = (q % n_tiles) * BN;
+            const long long p0 = (long long)(q / n_tiles) * 256 + rank * 128;
+            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+            for (int i = et; i < BN; i += ETHREADS) sbias[i] = p.bias ? p.bias[n0 + i] : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+
+            float acc[Cfg::NACC];
+#pragma unroll
+            for (int i = 0; i < Cfg::NACC; ++i) acc[i] = 0.f;
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(&tfull[b], pht, abort_flag, p.err, 0x700u + b);
+                tc_fence_after();
+                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * BN);
+#pragma unroll
+                for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tsrc + c0, r0);
+                    tmem_ld32(tsrc + c0 + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty[b]), 0u));   // the leader's barrier counts both CTAs
+                if (++b == Cfg::NBUF) { b = 0; pht ^= 1u; }
+            }
+            const long long pos = p0 + g * 32 + lane;
+            bool valid = pos < p.P;
+            int n = 0, y = 0, x = 0;
+            if (valid) {
+                n = (int)(pos / HpWp);
+                const int r = (int)(pos - n * HpWp);
+                const int yy = r / p.Wp;
+                const int xx = r - yy * p.Wp;
+                valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
+                y = yy - 1;
+                x = xx - 1;
+            }
+            uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
+            store_tile_rows<Cfg::NACC>(acc, sbias, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go, n0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_barrier();                                          // no CTA exits (or frees TMEM) while its peer may still signal it
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -565,9 +816,40 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
     return 0;
 }
 
+template <int BN>
+static int launch5_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_q, int n_tiles,
+                      cudaStream_t st) {
+    using Cfg = Conv5Cfg<BN>;
+    static bool attr_done = false;
+    static int sms = 0;
+    if (!attr_done) {
+        WCTB_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        int dev = 0;
+        WCTB_CUDA(cudaGetDevice(&dev));
+        WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_done = true;
+    }
+    int pairs = (sms / 2) * (g_conv_oversub > 0 ? g_conv_oversub : 1);
+    if (pairs > total_q) pairs = total_q;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    WCTB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc5_kernel<BN>, mA, mB, p, total_q, n_tiles));
+    return 0;
+}
+
 int g_conv_fuse = -1;        // -1 auto, 0 never, 1 whenever the tile allows (wctb200_debug_set_conv_fuse)
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
-int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu); 4 = aligned tap reuse (conv_tc4.cu); 5 = v2 only
+int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu); 4 = aligned tap reuse (conv_tc4.cu); 5 = v2 only; 6 = v2 on CTA pairs (cta_group::2)
 
 int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
                        int flags, __half* out, int bn_override, cudaStream_t st);
@@ -592,6 +874,23 @@ int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __ha
     if ((g_conv_impl == 4 || (g_conv_impl == 2 && Cin <= g_conv4_cin_max)) && taps == 9 && nsets == 1) {
         const int r = launch_conv3x3_tc4(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
         if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v4 -> v2 below
+    }
+    if (g_conv_impl == 6 && taps == 9 && nsets == 1) {   // CTA pairs (cta_group::2)
+        int BN5 = Cout % 128 == 0 ? 128 : 64;
+        if (g_conv_bn_override == 64) BN5 = 64;
+        CUtensorMap mA5, mB5;
+        int rc5 = make_map(&mA5, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
+        if (rc5) return rc5;
+        const uint64_t K5 = (uint64_t)9 * Cin;
+        rc5 = make_map(&mB5, w_split, K5, (uint64_t)Cout, 2, K5 * 2, K5 * Cout * 2, (uint32_t)(BN5 / 2));
+        if (rc5) return rc5;
+        ConvParams p5;
+        p5.N = N; p5.H = H; p5.W = W; p5.Cin = Cin; p5.Cout = Cout; p5.Hp = gi.Hp; p5.Wp = gi.Wp; p5.P = gi.P;
+        p5.taps = 9; p5.nsets = 1; p5.per_image = 0; p5.tiles_per_image = 0;
+        p5.flags = flags; p5.bias = bias; p5.out = out; p5.err = device_error_word();
+        const int n_tiles5 = Cout / BN5;
+        const int total_q = (int)cdiv(gi.P, 256) * n_tiles5;
+        return BN5 == 128 ? launch5_bn<128>(mA5, mB5, p5, total_q, n_tiles5, st) : launch5_bn<64>(mA5, mB5, p5, total_q, n_tiles5, st);
     }
     int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
     if (BN == 256) BN = 128;  // v1 default: 3-stage pipeline beats the 2-stage 256-wide tile until 2-CTA lands

@@ -66,12 +66,16 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-template <int BN>
+template <int BN, bool FUSE_>
 struct Conv4Cfg {
     static constexpr int B_BYTES = BN * 64 * 2;             // one plane of one weight tile
     static constexpr int B_STAGE = 2 * B_BYTES;
-    static constexpr int NBUF = BN == 256 ? 2 : 4;
-    static constexpr int TMEM_COLS = NBUF * BN;
+    // FUSE: a_hi*[b_hi|b_lo] as ONE MMA with N = 2*BN (the planes are adjacent in a stage), a_lo*b_hi with N = BN into
+    // the first column range; the epilogue adds the two ranges (same scheme as conv_tc2, see Conv2Cfg::FUSE)
+    static constexpr bool FUSE = FUSE_ && BN <= 128;
+    static constexpr int ACC_COLS = FUSE ? 2 * BN : BN;
+    static constexpr int NBUF = 512 / ACC_COLS >= 4 ? 4 : 2;
+    static constexpr int TMEM_COLS = NBUF * ACC_COLS;
     static constexpr int CH = 4;
     static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
     static constexpr int THREADS = 96 + 32 * EPI_WARPS;    // + TMA-A producer warp (last warp)
@@ -106,10 +110,10 @@ __device__ __forceinline__ Tile4 tile4(const Conv4Params& p, int m_tile, int n_i
     return t;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(Conv4Cfg<BN>::THREADS, 1)
+template <int BN, bool FUSE_>
+__global__ void __launch_bounds__(Conv4Cfg<BN, FUSE_>::THREADS, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Conv4Params p) {
-    using Cfg = Conv4Cfg<BN>;
+    using Cfg = Conv4Cfg<BN, FUSE_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_base = smem;
@@ -219,47 +223,57 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(128, BN);
-            uint32_t ia = 0, ib = 0, cg_ = 0;
+            constexpr uint32_t idesc2 = umma_idesc_f16(128, Cfg::FUSE ? 2 * BN : BN);
+            // ring positions as running counters (a timeline probe showed ~600 cycles per k-iteration of bookkeeping in
+            // this single thread with runtime % and / on the stage counts -- as much as issuing the MMAs)
+            const uint32_t a0 = smem_u32(a_base), b0 = smem_u32(b_base);
+            int sa = 0, sb = 0, b = 0;
+            uint32_t pha = 0, phb = 0, pht = 0, ib = 0;
             for (int q = cid; q < total_q; q += num_clusters) {
-                int it = 0;
-                for (int c = 0; c < nchunks; ++c, ++cg_) {
-                    const int b = cg_ % Cfg::NBUF;
-                    mbar_wait(&tempty[b], ((cg_ / Cfg::NBUF) & 1) ^ 1u, abort_flag, p.err, 0x400u + b);
+                int it = 0, ky = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    mbar_wait(&tempty[b], pht ^ 1u, abort_flag, p.err, 0x400u + b);
                     tc_fence_after();
-                    const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
+                    const uint32_t tacc = tmem_base + (uint32_t)(b * Cfg::ACC_COLS);
                     const int it_end = min(kiters, (c + 1) * Cfg::CH);
+                    bool first = true;
                     for (; it < it_end; ++it, ++ib) {
-                        const int ky = it % 3;
-                        const int sa = ia % p.na_stages;
-                        if (ky == 0) mbar_wait(&fullA[sa], (ia / p.na_stages) & 1, abort_flag, p.err, 0x210u + sa);
-                        const int sb = ib % p.nb_stages;
+                        if (ky == 0) mbar_wait(&fullA[sa], pha, abort_flag, p.err, 0x210u + sa);
                         if (p.trace && blockIdx.x == 0 && ib < 256) p.trace[ib] = clock64();               // k-iter start
-                        mbar_wait(&fullB[sb], (ib / p.nb_stages) & 1, abort_flag, p.err, 0x220u + sb);
+                        mbar_wait(&fullB[sb], phb, abort_flag, p.err, 0x220u + sb);
                         tc_fence_after();
                         if (p.trace && blockIdx.x == 0 && ib < 256) p.trace[256 + ib] = clock64();         // operands ready
-                        const uint32_t ast = smem_u32(a_base + sa * Cfg::A_STAGE) + (uint32_t)(ky * Cfg::KY_BYTES);
-                        const uint32_t bst = smem_u32(b_base + sb * Cfg::B_STAGE);
-                        const bool first = (it == c * Cfg::CH);
+                        const uint64_t a_hi = umma_desc_sw128(a0 + (uint32_t)(sa * Cfg::A_STAGE + ky * Cfg::KY_BYTES));
+                        const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_PLANE >> 4);
+                        const uint64_t b_hi = umma_desc_sw128(b0 + (uint32_t)(sb * Cfg::B_STAGE));
+                        const uint64_t b_lo = b_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                        if (!(p.dbg & 1)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (p.dbg & 1) break;
-                            const uint64_t a_hi = umma_desc_sw128(ast + k * 32);
-                            const uint64_t a_lo = umma_desc_sw128(ast + Cfg::A_PLANE + k * 32);
-                            const uint64_t b_hi = umma_desc_sw128(bst + k * 32);
-                            const uint64_t b_lo = umma_desc_sw128(bst + Cfg::B_BYTES + k * 32);
-                            umma_f16(tacc, a_hi, b_lo, idesc, (first && k == 0) ? 0u : 1u);
-                            umma_f16(tacc, a_lo, b_hi, idesc, 1u);
-                            umma_f16(tacc, a_hi, b_hi, idesc, 1u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                                if (Cfg::FUSE) {
+                                    umma_f16(tacc, a_hi + ko, b_hi + ko, idesc2, (first && k == 0) ? 0u : 1u);
+                                    umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                                } else {
+                                    umma_f16(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
+                                    umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                                    umma_f16(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
+                                }
+                            }
                         }
+                        first = false;
                         if (p.cluster > 1) umma_commit_mc(&emptyB[sb], mc_mask);
                         else umma_commit(&emptyB[sb]);
-                        if (ky == 2) {
+                        if (++sb == p.nb_stages) { sb = 0; phb ^= 1u; }
+                        if (++ky == 3) {
+                            ky = 0;
                             umma_commit(&emptyA[sa]);
-                            ++ia;
+                            if (++sa == p.na_stages) { sa = 0; pha ^= 1u; }
                         }
                         if (p.trace && blockIdx.x == 0 && ib < 256) p.trace[512 + ib] = clock64();         // MMAs + commits issued
                     }
                     umma_commit(&tfull[b]);
+                    if (++b == Cfg::NBUF) { b = 0; pht ^= 1u; }
                 }
             }
         }
@@ -288,18 +302,30 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(&tfull[b], (cg_ / Cfg::NBUF) & 1, abort_flag, p.err, 0x300u + b);
                 tc_fence_after();
                 if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && cg_ < 128) p.trace[768 + 2 * cg_] = clock64();   // chunk complete seen
-                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * BN + colbase);
+                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * Cfg::ACC_COLS + colbase);
+                if (Cfg::FUSE) {
 #pragma unroll
-                for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tsrc + c0, r0);
-                    if (c0 + 32 < Cfg::NACC) tmem_ld32(tsrc + c0 + 32, r1);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < Cfg::NACC; c0 += 32) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tsrc + c0, r0);               // a_hi b_hi + a_lo b_hi
+                        tmem_ld32(tsrc + BN + c0, r1);          // a_hi b_lo
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
-                    if (c0 + 32 < Cfg::NACC) {
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                    }
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                    for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tsrc + c0, r0);
+                        if (c0 + 32 < Cfg::NACC) tmem_ld32(tsrc + c0 + 32, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+                        if (c0 + 32 < Cfg::NACC) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -357,14 +383,15 @@ static int make_map4(CUtensorMap* m, const void* base, int rank, const cuuint64_
 }
 
 extern int g_conv_oversub;
+extern int g_conv_fuse;
 int g_conv4_cluster = 2;     // tuning hook (wctb200_debug_set_conv4): 1 = no cluster, 2 = weight multicast across a CTA pair
 int g_conv4_dbg = 0;
 long long* g_conv4_trace = nullptr;
 int g_conv4_cin_max = 0;     // impl 2 dispatches to v4 for Cin <= this (0: never -- v4 is MMA-issue bound)
 
-template <int BN>
+template <int BN, bool FUSE_>
 static int launch4_bn(const CUtensorMap& mA, const CUtensorMap& mB, const Conv4Params& p, int smem_bytes, cudaStream_t st) {
-    using Cfg = Conv4Cfg<BN>;
+    using Cfg = Conv4Cfg<BN, FUSE_>;
     static int sms = 0;
     static int attr_bytes = 0;
     if (!sms) {
@@ -373,7 +400,7 @@ static int launch4_bn(const CUtensorMap& mA, const CUtensorMap& mB, const Conv4P
         WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     if (smem_bytes > attr_bytes) {
-        WCTB_CUDA(cudaFuncSetAttribute(conv_tc4_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        WCTB_CUDA(cudaFuncSetAttribute(conv_tc4_kernel<BN, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_bytes = smem_bytes;
     }
     const int m_pairs = (p.m_tiles + p.cluster - 1) / p.cluster;
@@ -393,7 +420,7 @@ static int launch4_bn(const CUtensorMap& mA, const CUtensorMap& mB, const Conv4P
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    WCTB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc4_kernel<BN>, mA, mB, p));
+    WCTB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc4_kernel<BN, FUSE_>, mA, mB, p));
     return 0;
 }
 
@@ -446,7 +473,9 @@ int launch_conv3x3_tc4(const __half* in, int N, int H, int W, int Cin, const __h
     p.na_stages = na;
     p.nb_stages = nb;
     const int smem_bytes = na * a_stage + nb * b_stage + aux;
-    int rc = BN == 128 ? launch4_bn<128>(mA, mB, p, smem_bytes, st) : launch4_bn<64>(mA, mB, p, smem_bytes, st);
+    const bool fuse = g_conv_fuse != 0 && (BN == 64 || g_conv_fuse == 1 || Cin >= 256);
+    int rc = BN == 128 ? (fuse ? launch4_bn<128, true>(mA, mB, p, smem_bytes, st) : launch4_bn<128, false>(mA, mB, p, smem_bytes, st))
+                       : (fuse ? launch4_bn<64, true>(mA, mB, p, smem_bytes, st) : launch4_bn<64, false>(mA, mB, p, smem_bytes, st));
     return rc ? rc : 1;
 }
 
