@@ -76,6 +76,11 @@ class ClockSampler(object):
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
+            # wait for the first sample: NVML start-up of the freshly spawned nvidia-smi takes 0.3-1 s and touches the
+            # driver; it must be over before the warm-up / timed steps begin (it then samples every 100 ms during them)
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 15.0 and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

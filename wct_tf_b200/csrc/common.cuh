@@ -179,6 +179,22 @@ __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const 
 }
 
 // ---------------------------------------------------------------------------
+// packed fp32 pairs: fma.rn.f32x2 does two FMAs per instruction on sm_100 (same FMA-pipe time, half the issue slots)
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// ---------------------------------------------------------------------------
 // PTX wrappers: mbarrier / TMA / tcgen05 (sm_100a)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

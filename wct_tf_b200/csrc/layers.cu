@@ -147,37 +147,42 @@ k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __r
         const int xs = (int)(t % segs) * 4; t /= segs;
         const int y = (int)(t % (unsigned)H);
         const int n = (int)(t / (unsigned)H);
-        float acc[4][8];
+        // accumulators as packed fp32 pairs (fma.rn.f32x2): the kernel is issue bound (ncu: IPC 2.7, FMA pipe 43 %,
+        // "not selected" the top stall), and a packed FMA does two channels per issue slot
+        f32x2 acc[4][4];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[p][j] = sb[g * 8 + j];
+            for (int j = 0; j < 4; ++j) acc[p][j] = pack2(sb[g * 8 + 2 * j], sb[g * 8 + 2 * j + 1]);
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int yy = reflect_idx(y + ky - 1, H);
             const float* row = img + ((long long)n * H + yy) * W * 3;
-            float in[6][3];
+            f32x2 in[6][3];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 int xx = reflect_idx(xs + j - 1, W);
                 xx = min(max(xx, 0), W - 1);                 // columns past the ragged right edge: any valid address
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) in[j][ci] = __ldg(row + xx * 3 + ci);
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = __ldg(row + xx * 3 + ci);
+                    in[j][ci] = pack2(v, v);
+                }
             }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     const int k = (ky * 3 + kx) * 3 + ci;
-                    const float4 w0 = *reinterpret_cast<const float4*>(sw + (k * 2) * 32 + g * 4);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sw + (k * 2 + 1) * 32 + g * 4);
+                    const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(sw + (k * 2) * 32 + g * 4);       // channels 0..3 as two pairs
+                    const ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(sw + (k * 2 + 1) * 32 + g * 4);   // channels 4..7
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
-                        const float v = in[p + kx][ci];
-                        acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
-                        acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
-                        acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
-                        acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+                        const f32x2 v = in[p + kx][ci];
+                        acc[p][0] = fma2(v, w0.x, acc[p][0]);
+                        acc[p][1] = fma2(v, w0.y, acc[p][1]);
+                        acc[p][2] = fma2(v, w1.x, acc[p][2]);
+                        acc[p][3] = fma2(v, w1.y, acc[p][3]);
                     }
                 }
         }
@@ -186,7 +191,11 @@ k_conv_head(const float* __restrict__ img, int N, int H, int W, const float* __r
             if (xs + p < W) {
                 float v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[p][j], 0.f);
+                for (int j = 0; j < 4; ++j) {
+                    unpack2(acc[p][j], v[2 * j], v[2 * j + 1]);
+                    v[2 * j] = fmaxf(v[2 * j], 0.f);
+                    v[2 * j + 1] = fmaxf(v[2 * j + 1], 0.f);
+                }
                 Half8 hi, lo;
                 split8(v, hi, lo);
                 store8_with_halo(out, go, n, y, xs + p, g * 8, hi, lo);
@@ -341,9 +350,9 @@ k_conv_tail_tiled(const __half* __restrict__ in, ActGeom gi, const float* __rest
         const float* src = w + ((size_t)(tap * gi.C + c4 * 4)) * 3 + o;          // w is [9*Cin][3], k = tap*Cin + c
         swt[i] = make_float4(src[0], src[3], src[6], src[9]);
     }
-    float acc[8][3];
+    f32x2 acc[8][3];                                  // packed pairs: (even, odd) channel partial sums, added at the end
 #pragma unroll
-    for (int p = 0; p < 8; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+    for (int p = 0; p < 8; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0ull;
 
     for (int c0 = 0; c0 < gi.C; c0 += TT_CH) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -363,22 +372,17 @@ k_conv_tail_tiled(const __half* __restrict__ in, ActGeom gi, const float* __rest
             const float4* wg = swt + (c0 / 4 + g) * 3;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                float4 a[10];
-                const float4* col = sact + (g * TT_PH + warp * 8) * TT_PW + lane + kx;
+                ulonglong2 a[10];                     // float4 viewed as two packed fp32 pairs
+                const ulonglong2* col = reinterpret_cast<const ulonglong2*>(sact) + (g * TT_PH + warp * 8) * TT_PW + lane + kx;
 #pragma unroll
                 for (int r = 0; r < 10; ++r) a[r] = col[r * TT_PW];
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int o = 0; o < 3; ++o) {
-                        const float4 wv = wg[(ky * 3 + kx) * C4 * 3 + o];
+                        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wg + (ky * 3 + kx) * C4 * 3 + o);
 #pragma unroll
-                        for (int p = 0; p < 8; ++p) {
-                            float s = acc[p][o];
-                            s = fmaf(a[p + ky].x, wv.x, s); s = fmaf(a[p + ky].y, wv.y, s);
-                            s = fmaf(a[p + ky].z, wv.z, s); s = fmaf(a[p + ky].w, wv.w, s);
-                            acc[p][o] = s;
-                        }
+                        for (int p = 0; p < 8; ++p) acc[p][o] = fma2(a[p + ky].y, wv.y, fma2(a[p + ky].x, wv.x, acc[p][o]));
                     }
                 }
             }
@@ -393,7 +397,9 @@ k_conv_tail_tiled(const __half* __restrict__ in, ActGeom gi, const float* __rest
                 float* d = img + (((long long)n * gi.H + y) * gi.W + x) * 3;
 #pragma unroll
                 for (int o = 0; o < 3; ++o) {
-                    float v = acc[p][o] + b[o];
+                    float e0, e1;
+                    unpack2(acc[p][o], e0, e1);
+                    float v = (e0 + e1) + b[o];
                     if (flags & WCTB200_CLIP01) v = fminf(fmaxf(v, 0.f), 1.f);
                     d[o] = v;
                 }

@@ -195,18 +195,6 @@ struct JacobiCfg {
 
 // ---- register-blocked pair rotation: operands live in registers as PACKED fp32 pairs
 // (fma.rn.f32x2: two FMAs per instruction on sm_100), column norms are cached ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float a, float b) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
 // single-MUFU approximations (the CUDA intrinsics wrap these in range/denormal fix-ups: measured 25 FMUL +
 // 12 FSETP + 7 MUFU per rotation in the SASS of the previous version)
 __device__ __forceinline__ float rsqrt_ap(float x) {
