@@ -8,7 +8,7 @@ from wct_tf_b200 import _capi
 lib = _capi.load()
 st = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(0)
-SCHED = [(int(a), int(b)) for a, b in (x.split(":") for x in os.environ.get("JAC_SCHED", "1:600").split(","))]
+SCHED = [(int(a), int(b)) for a, b in (x.split(":") for x in os.environ.get("JAC_SCHED", "-1:-1").split(","))]
 CASES = [(64, 4096, 16), (128, 4096, 16), (256, 2048, 16), (512, 1024, 15), (512, 1024, 4), (512, 300, 4)]
 if os.environ.get("JAC_CASES"):
     CASES = [tuple(int(v) for v in c.split(":")) for c in os.environ["JAC_CASES"].split(",")]

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
 namespace wctb {
@@ -19,19 +23,30 @@ int cuda_fail(cudaError_t e, const char* what) {
     return WCTB200_ECUDA;
 }
 
-int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
-    static bool pool_ready[64] = {false};
+// Per-stream scratch cache.  Work on one stream is ordered, so a stream can reuse ONE grow-only buffer per slot for every
+// call it serves.  (The first version used cudaMallocAsync/cudaFreeAsync: the stream-ordered pool only re-uses a block
+// across streams once a dependency exists, so with 8 streams it kept growing at unpredictable moments AFTER the warm-up
+// steps -- each growth maps hundreds of MB and showed up as a one-off 75..500 ms step in some bench runs.)
+int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st, int slot) {
+    struct Entry { void* p; size_t cap; };
+    static std::mutex mu;
+    static std::map<std::tuple<int, cudaStream_t, int>, Entry> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    std::lock_guard<std::mutex> lock(mu);
+    Entry& e = cache[std::make_tuple(dev, st, slot)];
+    if (e.cap < bytes) {
+        if (e.p) {
+            WCTB_CUDA(cudaStreamSynchronize(st));
+            WCTB_CUDA(cudaFree(e.p));
+            e.p = nullptr;
+            e.cap = 0;
         }
-        pool_ready[dev] = true;
+        const size_t cap = bytes + bytes / 8 + 256;
+        WCTB_CUDA(cudaMalloc(&e.p, cap));
+        e.cap = cap;
     }
-    WCTB_CUDA(cudaMallocAsync(ptr, bytes, st));
+    *ptr = e.p;
     return 0;
 }
 
@@ -238,7 +253,7 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     const size_t nmat = (size_t)count * C * C;
     float* scratch = nullptr;
     {
-        int rc0 = scratch_alloc(reinterpret_cast<void**>(&scratch), ((size_t)count * 16 + nmat + (size_t)count * C) * sizeof(float), ST(stream));
+        int rc0 = scratch_alloc(reinterpret_cast<void**>(&scratch), ((size_t)count * 16 + nmat + (size_t)count * C) * sizeof(float), ST(stream), 2);
         if (rc0) return rc0;
     }
     float* conv = scratch;
@@ -247,7 +262,6 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     cudaError_t ce = cudaMemcpyAsync(a0, a, nmat * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream));
     int rc = ce == cudaSuccess ? launch_jacobi(a, C, count, conv, sweeps, ST(stream)) : cuda_fail(ce, "cudaMemcpyAsync");
     if (!rc) rc = launch_eig_post(a, a0, lam, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
-    cudaFreeAsync(scratch, ST(stream));
     return rc;
 }
 

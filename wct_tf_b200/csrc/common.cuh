@@ -323,9 +323,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
 }
 #endif  // __CUDACC__
 
-// stream-ordered scratch (cudaMallocAsync) with the pool's release threshold raised once, so that
-// scratch freed before a synchronisation point is NOT handed back to the OS every step
-int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
+// per-(device, stream, slot) grow-only scratch buffer (capi.cu); valid until the next call with the same key
+int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st, int slot);
 
 // ---------------------------------------------------------------------------
 // kernel launchers implemented in the .cu files (host API used by capi.cu)

@@ -864,14 +864,13 @@ static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov,
     if (tc) {
         // tensor-core path (cov_tc.cu) on a centred SPF16 copy of the features (stream-ordered scratch)
         __half* centred = nullptr;
-        { int rc0 = scratch_alloc(reinterpret_cast<void**>(&centred), (size_t)g.plane * 2 * sizeof(__half), st); if (rc0) return rc0; }
+        { int rc0 = scratch_alloc(reinterpret_cast<void**>(&centred), (size_t)g.plane * 2 * sizeof(__half), st, 0); if (rc0) return rc0; }
         const long long total = (long long)g.N * g.H * g.W * (g.C / 8);
         long long blocks = (total + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         k_center<<<(unsigned)blocks, 256, 0, st>>>(act, g, mean, centred);
         cudaError_t le = cudaGetLastError();
         int rc2 = le == cudaSuccess ? launch_cov_tc(centred, g, cov, st) : cuda_fail(le, "k_center");
-        cudaFreeAsync(centred, st);
         if (rc2) return rc2;
     } else {
         const int nb = g.C / 64;
@@ -1068,12 +1067,10 @@ int launch_covariance(const __half* act, int N, int H, int W, int C, float eps_c
     WCTB_REQUIRE(C % 64 == 0 && C >= 64, "covariance: C=%d must be a multiple of 64", C);
     double *sum = nullptr, *cov = nullptr;
     const size_t nsum = (size_t)N * C, ncov = (size_t)N * C * C;
-    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st); if (rc0) return rc0; }
+    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st, 1); if (rc0) return rc0; }
     cov = sum + nsum;
     WCTB_CUDA(cudaMemsetAsync(sum, 0, (nsum + ncov) * sizeof(double), st));
-    int rc = stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, nullptr, eps_cov, st);
-    cudaFreeAsync(sum, st);
-    return rc;
+    return stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, nullptr, eps_cov, st);
 }
 
 int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
