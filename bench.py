@@ -173,13 +173,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=30, help="frames per GPU per step (30 = two sub-batches of 15: at most 15 eigensolver clusters of 8 CTAs are co-resident on a B200)")
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--adain", action="store_true", help="config 5: AdaIN instead of WCT")
     ap.add_argument("--oversub", type=int, default=0, help="tuning: conv CTAs per SM (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the style side on the main stream")
-    ap.add_argument("--groups", type=int, default=4, help="sub-batches per step run as independent stream pairs")
+    ap.add_argument("--groups", type=int, default=2, help="sub-batches per step run as independent stream pairs")
     ap.add_argument("--no-prio", action="store_true", help="tuning: all streams at the same priority")
     args = ap.parse_args()
     if args.impl == "reference":

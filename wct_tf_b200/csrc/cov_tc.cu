@@ -93,7 +93,11 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     const int t0 = split * p.tiles_per_split;
     const int t1 = min(t0 + p.tiles_per_split, tiles_img);
     const int ntiles = max(t1 - t0, 0);
-    const bool dup = (p.C == 64);          // single 64-channel slice: loaded twice so that M = N = 128 stays valid
+    // C = 64: a single 64-channel slice.  The 128-row operand is [hi plane | lo plane] of that slice and is used as BOTH
+    // A and B: ONE MMA per 16 pixels yields hi.hi, hi.lo, lo.hi (and lo.lo) as the four 64x64 quadrants of the 128x128
+    // accumulator; the epilogue adds the quadrants.  (The first version loaded the slice twice to fill M = N = 128 and
+    // issued the three split products separately: 3x the MMAs and 2x the TMA bytes for the same result.)
+    const bool dup = (p.C == 64);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -108,7 +112,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nchunks = (ntiles + Cfg::CH - 1) / Cfg::CH;
-    const uint32_t stage_bytes = diag ? Cfg::OPER : Cfg::STAGE;
+    const uint32_t stage_bytes = dup ? 2 * Cfg::SLICE : (diag ? Cfg::OPER : Cfg::STAGE);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -119,10 +123,15 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
                 const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
                 uint8_t* st = smem + s * Cfg::STAGE;
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
+                if (dup) {
+                    tma_load_5d_cov(st, &mapX, &full[s], 0, tx * 32, ty * 2, img, 0);                  // rows 0..63   : hi
+                    tma_load_5d_cov(st + Cfg::SLICE, &mapX, &full[s], 0, tx * 32, ty * 2, img, 1);     // rows 64..127 : lo
+                    continue;
+                }
                 for (int op = 0; op < (diag ? 1 : 2); ++op) {
                     const int blk = op == 0 ? bi : bj;
                     for (int sl = 0; sl < 2; ++sl) {
-                        const int ch = dup ? 0 : blk * 128 + sl * 64;
+                        const int ch = blk * 128 + sl * 64;
                         for (int pl = 0; pl < 2; ++pl)
                             tma_load_5d_cov(st + op * Cfg::OPER + (pl * 2 + sl) * Cfg::SLICE, &mapX, &full[s], ch, tx * 32,
                                             ty * 2, img, pl);
@@ -151,6 +160,11 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {           // 64 pixels = 4 x UMMA_K(16): 16 rows of 128 B = 2048 B per step
                         const uint32_t ko = k * 2048;
+                        if (dup) {
+                            const uint64_t d = umma_desc_mn_sw128(a0 + ko, p.lbo_bytes, p.sbo_bytes);   // [hi | lo] x [hi | lo]^T
+                            umma_f16(tacc, d, d, idesc, (first && k == 0) ? 0u : 1u);
+                            continue;
+                        }
                         const uint64_t a_hi = umma_desc_mn_sw128(a0 + ko, p.lbo_bytes, p.sbo_bytes);
                         const uint64_t a_lo = umma_desc_mn_sw128(a0 + 2 * Cfg::SLICE + ko, p.lbo_bytes, p.sbo_bytes);
                         const uint64_t b_hi = umma_desc_mn_sw128(b0 + ko, p.lbo_bytes, p.sbo_bytes);
@@ -192,13 +206,17 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
         }
         // this CTA's partial block -> fp64 accumulation buffer (row = channel bi*128 + m)
         const int m = g * 32 + lane;
-        const int row = bi * 128 + m;
-        const int ncols = dup ? 64 : 128;
-        if (ntiles > 0 && !*abort_flag && (!dup || m < 64)) {
-            double* dst = p.cov + ((long long)img * p.C + row) * p.C + (dup ? 0 : bj * 128);
+        if (ntiles > 0 && !*abort_flag) {
+            if (dup) {
+                // accumulator rows m and m+64 both belong to channel m & 63; columns j and 64+j to channel j
+                double* dst = p.cov + ((long long)img * p.C + (m & 63)) * p.C;
 #pragma unroll 8
-            for (int j = 0; j < 128; ++j)
-                if (j < ncols) atomicAdd(dst + j, (double)acc[j]);
+                for (int j = 0; j < 64; ++j) atomicAdd(dst + j, (double)acc[j] + (double)acc[64 + j]);
+            } else {
+                double* dst = p.cov + ((long long)img * p.C + bi * 128 + m) * p.C + bj * 128;
+#pragma unroll 8
+                for (int j = 0; j < 128; ++j) atomicAdd(dst + j, (double)acc[j]);
+            }
         }
     }
     tc_fence_before();
