@@ -217,11 +217,17 @@ __device__ __forceinline__ float rcp_ap(float x) {
 //     is orthonormal, an inexact t only leaves a residual for the next sweep;
 //   * (c,s): r = h^-1/2 refined by one Newton step, s = t r, and c is applied as 1 + cm1 with
 //     cm1 = -s^2/(1+r), so that small angles neither shrink nor grow the columns (no eigenvalue bias).
-__device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol2, float tolq2, float& flag, float& t,
-                                            float& s, float& cm1) {
+//   * a pair whose columns are BOTH at the rounding-noise floor (|col|^2 < null2 = 1e-11 max|col|^2 of the previous sweep)
+//     is left alone and not counted: such columns span the null space of a rank-deficient map, their mutual cosines
+//     are O(1) noise that never converges (26 sweeps instead of 13 on a rank-299 512x512 matrix), and their
+//     directions inside the null space do not matter.  Pairs of a noise column with a live column are still rotated:
+//     that is what keeps the noise columns' Rayleigh quotients second-order small.
+__device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol2, float tolq2, float null2, float& flag,
+                                            float& t, float& s, float& cm1) {
     const float ab = a * b, gg = g * g;
-    const bool rot = gg > tol2 * ab;
-    flag = fmaxf(flag, gg > tolq2 * ab ? 2.f : (rot ? 1.f : 0.f));
+    const bool live = fmaxf(a, b) > null2;
+    const bool rot = live && gg > tol2 * ab;
+    flag = fmaxf(flag, (live && gg > tolq2 * ab) ? 2.f : (rot ? 1.f : 0.f));
     const float d = b - a, g2 = g + g;
     const float w2 = fmaf(d, d, g2 * g2);
     const float w = w2 * rsqrt_ap(w2);
@@ -240,7 +246,8 @@ __device__ __forceinline__ void rot_scalars(float g, float a, float b, float tol
 // the kernel is latency bound (ncu: 38 % issue utilisation with 16 warps per SM).
 template <int HP>
 __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], float& a0, float& b0, f32x2 (&x1)[HP],
-                                          f32x2 (&y1)[HP], float& a1, float& b1, float tol2, float tolq2, float& flag) {
+                                          f32x2 (&y1)[HP], float& a1, float& b1, float tol2, float tolq2, float null2,
+                                          float& flag) {
     f32x2 d00 = 0ull, d01 = 0ull, d10 = 0ull, d11 = 0ull;
 #pragma unroll
     for (int i = 0; i < HP; ++i) {
@@ -258,8 +265,8 @@ __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], floa
         g1 += __shfl_xor_sync(0xffffffffu, g1, o);
     }
     float t0, s0, c0, t1, s1, c1;
-    rot_scalars(g0, a0, b0, tol2, tolq2, flag, t0, s0, c0);
-    rot_scalars(g1, a1, b1, tol2, tolq2, flag, t1, s1, c1);
+    rot_scalars(g0, a0, b0, tol2, tolq2, null2, flag, t0, s0, c0);
+    rot_scalars(g1, a1, b1, tol2, tolq2, null2, flag, t1, s1, c1);
     if (t0 != 0.f || t1 != 0.f) {          // warp-uniform: skip the FMAs only when BOTH pairs are already orthogonal
         const f32x2 s20 = pack2(s0, s0), ns20 = pack2(-s0, -s0), c20 = pack2(c0, c0);
         const f32x2 s21 = pack2(s1, s1), ns21 = pack2(-s1, -s1), c21 = pack2(c1, c1);
@@ -315,7 +322,7 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 template <int NN>
 __device__ __forceinline__ void ring_steps(float* cols, float* nrm, f32x2 (&x0)[NN / 64], f32x2 (&x1)[NN / 64], float& a0,
                                            float& a1, int bot0, int npairs, int wsub, int bar, int lane, float tol2,
-                                           float tolq2, float& flag) {
+                                           float tolq2, float null2, float& flag) {
     constexpr int HP = NN / 64;
     for (int s = 0; s < npairs; ++s) {
         const int j = bot0 + 2 * ((wsub + s) & (npairs - 1));
@@ -325,8 +332,8 @@ __device__ __forceinline__ void ring_steps(float* cols, float* nrm, f32x2 (&x0)[
         load_col<NN>(cy0, lane, y0);
         load_col<NN>(cy1, lane, y1);
         float b0 = nrm[j], b1 = nrm[j + 1];
-        rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, flag);
-        rot_regs2<HP>(x0, y1, a0, b1, x1, y0, a1, b0, tol2, tolq2, flag);
+        rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, null2, flag);
+        rot_regs2<HP>(x0, y1, a0, b1, x1, y0, a1, b0, tol2, tolq2, null2, flag);
         store_col<NN>(cy0, lane, y0);
         store_col<NN>(cy1, lane, y1);
         if (lane == 0) { nrm[j] = b0; nrm[j + 1] = b1; }
@@ -338,13 +345,13 @@ __device__ __forceinline__ void ring_steps(float* cols, float* nrm, f32x2 (&x0)[
 // tops (top, top+1) from shared memory, one ring pass, tops back to shared memory (the pairs INSIDE a block)
 template <int NN>
 __device__ __forceinline__ void cross_steps(float* cols, float* nrm, int top, int bot0, int npairs, int wsub, int bar,
-                                            int lane, float tol2, float tolq2, float& flag) {
+                                            int lane, float tol2, float tolq2, float null2, float& flag) {
     constexpr int HP = NN / 64;
     f32x2 x0[HP], x1[HP];
     load_col<NN>(cols + top * NN, lane, x0);
     load_col<NN>(cols + (top + 1) * NN, lane, x1);
     float a0 = nrm[top], a1 = nrm[top + 1];
-    ring_steps<NN>(cols, nrm, x0, x1, a0, a1, bot0, npairs, wsub, bar, lane, tol2, tolq2, flag);
+    ring_steps<NN>(cols, nrm, x0, x1, a0, a1, bot0, npairs, wsub, bar, lane, tol2, tolq2, null2, flag);
     store_col<NN>(cols + top * NN, lane, x0);
     store_col<NN>(cols + (top + 1) * NN, lane, x1);
     if (lane == 0) { nrm[top] = a0; nrm[top + 1] = a1; }
@@ -367,7 +374,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     constexpr int HP = NN / 64;
     extern __shared__ __align__(16) float cols[];          // [64][NN]
     __shared__ float nrm[64];
-    __shared__ unsigned int s_max;
+    __shared__ unsigned int s_max, s_amax;
 
     const int rank = blockIdx.x;
     const int prob = blockIdx.y;
@@ -386,10 +393,11 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     // the verification sweep (no rotations, ~60 % of a sweep's cost) is skipped.
     const float tolq2 = 1e-4f * 1e-4f;
 
+    float null2 = 0.f;                                 // noise floor of the previous sweep (0: every pair is live)
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
-        if (threadIdx.x == 0) s_max = 0u;
-        float flag = 0.f;
+        if (threadIdx.x == 0) { s_max = 0u; s_amax = 0u; }
+        float flag = 0.f, amax = 0.f;
         for (int r = 0; r < (P == 1 ? 1 : M); ++r) {
             int bt, bb;
             if (P == 1) { bt = 0; bb = 1; }
@@ -418,6 +426,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
 #pragma unroll
                 for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
                 if (lane == 0) nrm[c] = ss;
+                amax = fmaxf(amax, ss);
             }
             __syncthreads();
             // ---- pairs inside each 32-column block: once per sweep
@@ -426,7 +435,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                     const int wpg = 1 << lv;               // warps per sub-block pair = column pairs per half
                     const int base = (warp >> lv) * (4 << lv);
                     cross_steps<NN>(cols, nrm, base + 2 * (warp & (wpg - 1)), base + (2 << lv), wpg, warp & (wpg - 1),
-                                    1 + (warp >> lv), lane, tol2, tolq2, flag);
+                                    1 + (warp >> lv), lane, tol2, tolq2, null2, flag);
                     __syncthreads();
                 }
                 {   // 1|1 : columns (4w,4w+1) and (4w+2,4w+3)
@@ -437,7 +446,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                     load_col<NN>(c0 + 2 * NN, lane, x1);
                     load_col<NN>(c0 + 3 * NN, lane, y1);
                     float a0 = nrm[4 * warp], b0 = nrm[4 * warp + 1], a1 = nrm[4 * warp + 2], b1 = nrm[4 * warp + 3];
-                    rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, flag);
+                    rot_regs2<HP>(x0, y0, a0, b0, x1, y1, a1, b1, tol2, tolq2, null2, flag);
                     store_col<NN>(c0, lane, x0);
                     store_col<NN>(c0 + NN, lane, y0);
                     store_col<NN>(c0 + 2 * NN, lane, x1);
@@ -460,7 +469,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
                         while (clock64() - t0 < (long long)grp * stagger) {}
                     }
                     ring_steps<NN>(cols, nrm, x0, x1, a0, a1, 32 + 2 * ring * (grp ^ h), ring, wsub, 1 + grp, lane, tol2,
-                                   tolq2, flag);
+                                   tolq2, null2, flag);
                     __syncthreads();
                 }
                 store_col<NN>(cols + 2 * warp * NN, lane, x0);
@@ -480,19 +489,26 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             }
         }
         // ---- convergence: worst pair class seen in this sweep (0 / 1 / 2), agreed across the cluster
-        if (lane == 0) atomicMax(&s_max, __float_as_uint(flag));
+        if (lane == 0) { atomicMax(&s_max, __float_as_uint(flag)); atomicMax(&s_amax, __float_as_uint(amax)); }
         __syncthreads();
         float gmax = __uint_as_float(s_max);
+        float amx = __uint_as_float(s_amax);
         if (P > 1) {
             if (threadIdx.x == 0) {
                 reinterpret_cast<volatile float*>(cw)[rank] = gmax;
+                reinterpret_cast<volatile float*>(cw)[8 + rank] = amx;
                 __threadfence();
             }
             cluster.sync();
             gmax = 0.f;
-            for (int i = 0; i < P; ++i) gmax = fmaxf(gmax, reinterpret_cast<volatile float*>(cw)[i]);
+            amx = 0.f;
+            for (int i = 0; i < P; ++i) {
+                gmax = fmaxf(gmax, reinterpret_cast<volatile float*>(cw)[i]);
+                amx = fmaxf(amx, reinterpret_cast<volatile float*>(cw)[8 + i]);
+            }
             cluster.sync();   // everyone has read before the next sweep overwrites
         }
+        null2 = 1e-11f * amx;                          // |column| < 3e-6 of the largest column: below what fp32 resolves in A
         __syncthreads();
         if (gmax < 2.f) { ++sweep; break; }
     }
