@@ -227,3 +227,25 @@ def test_cli_end_to_end(tmp_path):
                   "--passes", "2", "--concat"])
     out = np.asarray(Image.open(odir / "a_st.png"))      # {content}_{style}{ext}, stylize.py:114
     assert out.shape == (40, 40 + 56, 3) and out.dtype == np.uint8
+
+
+def test_wct_from_reference_weight_files(tmp_path):
+    """WCT(checkpoints=<TF checkpoint dirs>, vgg_path=<.t7>) -- the reference's own constructor arguments (wct.py:17-18)
+    -- gives bit-identical output to the same weights passed as a dict."""
+    from tests.t7_writer import write_vgg_t7
+    from tests.tf_bundle_writer import write_bundle
+    targets = ["relu3_1", "relu1_1"]
+    w = make_synthetic_weights(21, relu_targets=targets)
+    write_vgg_t7(str(tmp_path / "vgg_normalised.t7"), w["vgg"])
+    dirs = []
+    for t in targets:
+        tensors = {}
+        for l in w["decoders"][t]:
+            scope = "encoder_decoder_%s/decoder_%s/decoder_model_%s/%s/%s" % (t, t, t, l["name"], l["name"])
+            tensors[scope + "/kernel"], tensors[scope + "/bias"] = l["kernel"], l["bias"]
+        write_bundle(str(tmp_path / t / "model.ckpt-1"), tensors)
+        dirs.append(str(tmp_path / t))
+    c, s = _imgs(1, 40, 3)[0], _imgs(1, 56, 4)[0]
+    a = WCT(checkpoints=dirs, relu_targets=targets, vgg_path=str(tmp_path / "vgg_normalised.t7")).predict(c, s, alpha=0.7)
+    b = WCT(checkpoints=None, relu_targets=targets, vgg_path=None, weights=w).predict(c, s, alpha=0.7)
+    assert a.dtype == np.uint8 and np.array_equal(a, b)

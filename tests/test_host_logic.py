@@ -197,3 +197,47 @@ def test_t7_reader_against_reference_torchfile(tmp_path):
     w2 = W.load_weights(path, [ck], ["relu3_1"])
     assert np.array_equal(w2["vgg"][3]["weight"], w["vgg"][3]["weight"])
     assert [l["name"] for l in w2["vgg"]][-1] == "conv3_1"
+
+
+def test_tf_checkpoint_reader_and_reference_loading_protocol(tmp_path):
+    """Decoders come from TF1 Saver checkpoint DIRECTORIES like the reference (wct.py:45-58), the encoder from a .t7:
+    the TF-free bundle reader returns exactly what tests/tf_bundle_writer.py stored, ignores optimizer slots and
+    raises the reference's exception for an empty directory."""
+    from tests.t7_writer import write_vgg_t7
+    from tests.tf_bundle_writer import write_bundle
+    from wct_tf_b200 import tf_checkpoint as T, weights as W
+    targets = ["relu2_1", "relu3_1"]
+    w = W.make_synthetic_weights(9, relu_targets=targets)
+    write_vgg_t7(str(tmp_path / "vgg_normalised.t7"), w["vgg"])
+    dirs = []
+    for t in targets:
+        tensors = {}
+        for l in w["decoders"][t]:
+            scope = "encoder_decoder_%s/decoder_%s/decoder_model_%s/%s/%s" % (t, t, t, l["name"], l["name"])
+            tensors[scope + "/kernel"] = l["kernel"]
+            tensors[scope + "/bias"] = l["bias"]
+            tensors[scope + "/kernel/Adam"] = np.ones_like(l["kernel"])          # optimizer slots must be ignored
+            tensors[scope + "/kernel/Adam_1"] = np.ones_like(l["kernel"])
+        tensors["encoder_decoder_%s/train_%s/global_step_train" % (t, t)] = np.array(15000, dtype=np.int64)
+        d = tmp_path / ("ckpt_" + t)
+        write_bundle(str(d / "model.ckpt-15000"), tensors)
+        dirs.append(str(d))
+    assert T.crc32c(b"123456789") == 0xE3069283                                  # CRC-32C check value
+    raw = T.read_bundle(T.latest_checkpoint(dirs[0]))
+    assert int(raw["encoder_decoder_relu2_1/train_relu2_1/global_step_train"]) == 15000
+    w2 = W.load_weights(str(tmp_path / "vgg_normalised.t7"), dirs, targets)
+    for t in targets:
+        assert [l["name"] for l in w2["decoders"][t]] == [l["name"] for l in w["decoders"][t]]
+        for a, b in zip(w2["decoders"][t], w["decoders"][t]):
+            assert np.array_equal(a["kernel"], b["kernel"]) and np.array_equal(a["bias"], b["bias"])
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(Exception, match="No checkpoint found for target relu3_1"):
+        W.load_weights(str(tmp_path / "vgg_normalised.t7"), [dirs[0], str(empty)], targets)
+    # a flipped byte in the shard is caught by the per-tensor checksum
+    prefix = T.latest_checkpoint(dirs[1])
+    blob = bytearray(open(prefix + ".data-00000-of-00001", "rb").read())
+    blob[100] ^= 0xFF
+    open(prefix + ".data-00000-of-00001", "wb").write(bytes(blob))
+    with pytest.raises(T.TFCheckpointError, match="checksum"):
+        T.read_bundle(prefix)

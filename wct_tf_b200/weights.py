@@ -103,9 +103,10 @@ def load_weights(vgg_path, checkpoints, relu_targets):
     pairs with ``relu_targets[i]``; a target without a checkpoint raises.
 
     Encoder: the reference's own Torch7 ``vgg_normalised.t7`` (read by ``t7.py``) or an ``.npz``
-    bundle.  Decoders: ``.npz`` bundles written by ``save_weights`` (each checkpoint holds at least
-    its own decoder).  TF1 Saver checkpoints (wct.py:51-56) are NOT readable offline (no
-    TensorFlow; the files do not exist here) -- convert them once with TF and ``save_weights``."""
+    bundle.  Decoders: a TF1 Saver checkpoint directory / prefix as the reference uses (wct.py:51-56;
+    read without TensorFlow by ``tf_checkpoint.py`` -- tested only against bundles written by
+    tests/tf_bundle_writer.py, never against a file written by TensorFlow itself), or an ``.npz``
+    bundle written by ``save_weights`` (each checkpoint holds at least its own decoder)."""
     if vgg_path is None or checkpoints is None:
         raise ValueError("vgg_path and checkpoints are required when no weights dict is given")
     if str(vgg_path).endswith(".t7"):
@@ -117,8 +118,12 @@ def load_weights(vgg_path, checkpoints, relu_targets):
         raise NotImplementedError("encoder weights must be a Torch7 .t7 file or an .npz bundle")
     decoders = {}
     for relu, ck in zip(relu_targets, checkpoints):     # wct.py:47 zip pairing
-        d = _load_npz(ck)["decoders"] if str(ck).endswith(".npz") else {}
-        if relu not in d:
-            raise Exception('No checkpoint found for target {} in dir {}'.format(relu, ck))  # wct.py:58
-        decoders[relu] = d[relu]
+        if str(ck).endswith(".npz"):
+            d = _load_npz(ck)["decoders"]
+            if relu not in d:
+                raise Exception('No checkpoint found for target {} in dir {}'.format(relu, ck))  # wct.py:58
+            decoders[relu] = d[relu]
+        else:
+            from .tf_checkpoint import load_decoder_checkpoint   # raises the same Exception when nothing is found
+            decoders[relu] = load_decoder_checkpoint(str(ck), relu)
     return dict(vgg=vgg, decoders=decoders)
