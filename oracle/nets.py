@@ -140,7 +140,7 @@ def postprocess(image):
 
 
 def pipeline(content_u8, style_u8, weights, relu_targets, alpha=1.0, adain=False,
-             semantics="tf", dtype=np.float32, return_info=False):
+             semantics="tf", dtype=np.float32, return_info=False, swap5=False, ss_alpha=0.6, ss_patch_size=3, ss_stride=1):
     """model.py:60-94 + wct.py:70-106 on the CPU.
 
     semantics: 'tf' -> ops.wct_tf (what the reference graph executes, model.py:154,158)
@@ -158,7 +158,11 @@ def pipeline(content_u8, style_u8, weights, relu_targets, alpha=1.0, adain=False
             x = np.clip(x, 0, 1)  # model.py:86
         cf = encode(x, weights, [relu], dtype)[relu]  # model.py:135-139
         sf = style_feats[relu]
-        if adain:  # model.py:153,157
+        if swap5 and relu == "relu5_1":  # model.py:148-152: tf.case gives style-swap precedence over AdaIN at relu5_1
+            f, inf = ref_ops.wct_style_swap(cf, sf, ss_alpha, ss_patch_size, ss_stride, return_info=True)
+            inf["relu"] = relu
+            info.append(inf)
+        elif adain:  # model.py:153,157
             f = ref_ops.adain(cf, sf, alpha)
             info.append(dict(relu=relu))
         else:

@@ -5,6 +5,7 @@ Follows /root/reference/ops.py:
   wct_tf   ops.py:24-90    (what the reference graph really executes; pinned by tests/golden/pipeline_*.npz:
                             the reference's own wct_tf source evaluated over the NumPy TF stand-in np_tf1.py)
   adain    ops.py:282-294  (pinned the same way, pipeline_adain4_a07.npz)
+  wct_style_swap / style_swap  ops.py:145-278  (pinned the same way, pipeline_swap5_*.npz)
 
 All functions take features shaped 1xHxWxC (or HxWxC) like the reference and
 are dtype-polymorphic: float64 inputs give an fp64 "truth" run of the same
@@ -111,6 +112,73 @@ def adain(content_features, style_features, alpha, epsilon=1e-5):
     inv = (cv + dt.type(epsilon)) ** dt.type(-0.5) * np.sqrt(sv)
     norm = (c - cm) * inv + sm
     return dt.type(alpha) * norm + dt.type(1 - alpha) * c
+
+
+def style_swap(content, style, patch_size=3, stride=1, return_info=False):
+    """ops.py:219-278 on 1xHxWxC arrays.  Every patch_size x patch_size patch of ``style`` (VALID, ``stride``) becomes
+    a conv filter; the filters are l2-normalised along the PATCH axis (``tf.nn.l2_normalize(style_patches, dim=3)`` on a
+    [p,p,C,n_patches] tensor, ops.py:233 -- i.e. per filter tap, across patches, not per patch); the content is
+    cross-correlated with them (VALID), each position takes the arg-max patch (first maximum, like tf.argmax), the
+    UN-normalised patch is pasted back by the transposed conv and overlaps are averaged (ops.py:255-276)."""
+    c = np.asarray(content)
+    st = np.asarray(style)
+    c = c[0] if c.ndim == 4 else c
+    st = st[0] if st.ndim == 4 else st
+    dt = c.dtype
+    hc, wc, nc = c.shape
+    hs, ws, _ = st.shape
+    p = int(patch_size)
+    rows, cols = (hs - p) // stride + 1, (ws - p) // stride + 1
+    # [n_patches, p, p, C]   (tf.extract_image_patches order: rows then cols)
+    patches = np.stack([st[r * stride:r * stride + p, q * stride:q * stride + p, :] for r in range(rows) for q in range(cols)])
+    norm = np.sqrt(np.maximum((patches ** 2).sum(axis=0, keepdims=True), dt.type(1e-12)))      # l2_normalize epsilon 1e-12
+    pn = patches / norm
+    ho, wo = (hc - p) // stride + 1, (wc - p) // stride + 1
+    flat = pn.reshape(len(patches), -1)
+    scores = np.empty((ho, wo, len(patches)), dtype=dt)
+    for y in range(ho):
+        for x in range(wo):
+            scores[y, x] = flat @ c[y * stride:y * stride + p, x * stride:x * stride + p, :].reshape(-1)
+    idx = scores.argmax(axis=2)
+    out = np.zeros((1, (ho - 1) * stride + p, (wo - 1) * stride + p, nc), dtype=dt)
+    cnt = np.zeros(out.shape[1:3], dtype=dt)
+    for y in range(ho):
+        for x in range(wo):
+            out[0, y * stride:y * stride + p, x * stride:x * stride + p, :] += patches[idx[y, x]]
+            cnt[y * stride:y * stride + p, x * stride:x * stride + p] += 1
+    out = out / cnt[None, :, :, None]
+    if return_info:
+        srt = np.sort(scores, axis=2)
+        return out, dict(idx=idx, margin=srt[:, :, -1] - srt[:, :, -2], scores=scores)
+    return out
+
+
+def wct_style_swap(content, style, alpha, patch_size=3, stride=1, eps=1e-8, thresh=THRESH, return_info=False):
+    """ops.py:145-217: whiten content AND style (S^-1/2 on the kept eigenvalues of cov + eps*I), style-swap the
+    whitened encodings, colour the result with the style (S^+1/2), add the style mean, blend with fc + mc."""
+    fcx, shape = _flat(content)
+    fsx, sshape = _flat(style)
+    dt = fcx.dtype
+    mc = fcx.mean(axis=1, keepdims=True)
+    fc = fcx - mc
+    fcfc = fc @ fc.T / dt.type(fcx.shape[1] - 1) + np.eye(fcx.shape[0], dtype=dt) * dt.type(eps)
+    ms = fsx.mean(axis=1, keepdims=True)
+    fs = fsx - ms
+    fsfs = fs @ fs.T / dt.type(fsx.shape[1] - 1) + np.eye(fsx.shape[0], dtype=dt) * dt.type(eps)
+    Ec, wc, _ = np.linalg.svd(fcfc)
+    Es, ws, _ = np.linalg.svd(fsfs)
+    k_c, k_s = int((wc > thresh).sum()), int((ws > thresh).sum())
+    fc_hat = (Ec[:, :k_c] * wc[:k_c] ** dt.type(-0.5)) @ Ec[:, :k_c].T @ fc
+    fs_hat = (Es[:, :k_s] * ws[:k_s] ** dt.type(-0.5)) @ Es[:, :k_s].T @ fs
+    swapped, inf = style_swap(_unflat(fc_hat, shape), _unflat(fs_hat, sshape), patch_size, stride, return_info=True)
+    assert swapped.shape[1:3] == shape[:2], "style swap changed the encoding size (wct.py:84-90 refits the content for stride > 1)"
+    ss, _ = _flat(swapped)
+    fcs_hat = (Es[:, :k_s] * np.sqrt(ws[:k_s])) @ Es[:, :k_s].T @ ss + ms
+    out = _unflat(dt.type(alpha) * fcs_hat + dt.type(1 - alpha) * (fc + mc), shape)
+    if return_info:
+        inf.update(k_c=k_c, k_s=k_s, wc=wc, ws=ws)
+        return out, inf
+    return out
 
 
 def spectral_gap_ok(w, lo=1e-6, hi=1e-4):

@@ -31,11 +31,12 @@ from wct_tf_b200 import weights as W  # noqa: E402
 
 ALL = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
 CASES = [
-    # name, relu_targets, content HxW, style HxW, alpha, adain, seed
-    ("wct5_a06", ALL, (48, 64), (64, 48), 0.6, False, 11),
-    ("wct_21_41_a10", ["relu2_1", "relu4_1"], (40, 56), (48, 48), 1.0, False, 12),     # any order / subset (README.md:46)
-    ("wct_31_11_odd_a08", ["relu3_1", "relu1_1"], (37, 45), (41, 50), 0.8, False, 13),  # odd sizes: pool 'same' + upsample grow the frame
-    ("adain4_a07", ALL[1:], (48, 48), (40, 56), 0.7, True, 14),
+    # name, relu_targets, content HxW, style HxW, alpha, adain, seed, swap5 (ss_alpha)
+    ("wct5_a06", ALL, (48, 64), (64, 48), 0.6, False, 11, None),
+    ("wct_21_41_a10", ["relu2_1", "relu4_1"], (40, 56), (48, 48), 1.0, False, 12, None),     # any order / subset (README.md:46)
+    ("wct_31_11_odd_a08", ["relu3_1", "relu1_1"], (37, 45), (41, 50), 0.8, False, 13, None),  # odd sizes: pool 'same' + upsample grow the frame
+    ("adain4_a07", ALL[1:], (48, 48), (40, 56), 0.7, True, 14, None),
+    ("swap5_51_31_a08", ["relu5_1", "relu3_1"], (96, 112), (112, 96), 0.8, False, 15, 0.6),   # --swap5: style swap at relu5_1 (ops.py:145-278), WCT at relu3_1
 ]
 
 
@@ -52,7 +53,8 @@ def weight_checksum(w):
 def main():
     tmp = tempfile.mkdtemp()
     with np_tf1.reference_modules() as ref:
-        for name, targets, hwc, hws, alpha, adain, seed in CASES:
+        for name, targets, hwc, hws, alpha, adain, seed, ss in CASES:
+            swap = dict(swap5=True, ss_alpha=ss) if ss is not None else {}
             w = W.make_synthetic_weights(seed, relu_targets=targets)
             t7 = os.path.join(tmp, name + ".t7")
             write_vgg_t7(t7, w["vgg"])
@@ -61,18 +63,21 @@ def main():
             content = rng.integers(0, 256, hwc + (3,), dtype=np.uint8)
             style = rng.integers(0, 256, hws + (3,), dtype=np.uint8)
             c01, s01 = content[None] / 255.0, style[None] / 255.0          # wct.py:60-64
-            out64, lv64 = np_tf1.run_reference(ref, c01, s01, t7, dec, targets, alpha, adain, np.float64)
-            out32, _ = np_tf1.run_reference(ref, c01, s01, t7, dec, targets, alpha, adain, np.float32)
+            out64, lv64 = np_tf1.run_reference(ref, c01, s01, t7, dec, targets, alpha, adain, np.float64, **swap)
+            out32, _ = np_tf1.run_reference(ref, c01, s01, t7, dec, targets, alpha, adain, np.float32, **swap)
             # well-posedness of the vector: no covariance eigenvalue near the 1e-5 cut at any level
             _, info = nets.pipeline(content, style, w, targets, alpha=alpha, adain=adain, semantics="tf", dtype=np.float64,
-                                    return_info=True)
+                                    return_info=True, **swap)
             ks = []
             if not adain:
                 for inf in info:
                     assert ref_ops.spectral_gap_ok(inf["wc"]) and ref_ops.spectral_gap_ok(inf["ws"]), (name, inf["relu"])
                     ks.append((inf["k_c"], inf["k_s"]))
+                    if "margin" in inf:                    # style swap: the arg-max must be decided by a clear margin everywhere
+                        assert inf["margin"].min() > 1e-3, (name, float(inf["margin"].min()))
             arrays = dict(content=content, style=style, alpha=np.float64(alpha), adain=np.bool_(adain), seed=np.int64(seed),
                           relu_targets=np.array(targets), out_ref_fp64=out64, out_ref_fp32=out32, wsum=np.float64(weight_checksum(w)),
+                          swap5=np.bool_(ss is not None), ss_alpha=np.float64(ss if ss is not None else 0.6),
                           k=np.array(ks, dtype=np.int64).reshape(-1, 2))
             for i, (enc, dec_in, decoded) in enumerate(lv64):
                 arrays["lvl%d_decoder_input" % i] = dec_in.astype(np.float32)

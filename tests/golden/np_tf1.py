@@ -103,6 +103,51 @@ def _case(pred_fn_pairs, default):
     return default()
 
 
+def _extract_image_patches(x, ksizes, strides, rates, padding):
+    assert padding == "VALID" and list(rates) == [1, 1, 1, 1] and x.shape[0] == 1
+    p, st = ksizes[1], strides[1]
+    h, w = x.shape[1], x.shape[2]
+    rows, cols = (h - p) // st + 1, (w - p) // st + 1
+    out = np.empty((1, rows, cols, p * p * x.shape[3]), dtype=x.dtype)
+    for r in range(rows):
+        for q in range(cols):
+            out[0, r, q] = x[0, r * st:r * st + p, q * st:q * st + p, :].reshape(-1)     # (row, col, channel) order
+    return out
+
+
+def _l2_normalize(x, dim, epsilon=1e-12):
+    return x / np.sqrt(np.maximum(np.sum(x * x, axis=dim, keepdims=True), STATE["dtype"](epsilon)))
+
+
+def _conv2d(x, filt, strides, padding):
+    assert padding == "VALID" and x.shape[0] == 1
+    p, q, cin, cout = filt.shape
+    st = strides[1]
+    ho, wo = (x.shape[1] - p) // st + 1, (x.shape[2] - q) // st + 1
+    f2 = filt.reshape(p * q * cin, cout)
+    out = np.empty((1, ho, wo, cout), dtype=x.dtype)
+    for y in range(ho):
+        for xx in range(wo):
+            out[0, y, xx] = x[0, y * st:y * st + p, xx * st:xx * st + q, :].reshape(-1) @ f2
+    return out
+
+
+def _conv2d_transpose(value, filt, output_shape, strides, padding):
+    assert padding == "VALID" and value.shape[0] == 1
+    p, q, cout, cin = filt.shape                       # [height, width, output_channels, in_channels]
+    st = strides[1]
+    out = np.zeros(tuple(int(v) for v in output_shape), dtype=value.dtype)
+    for y in range(value.shape[1]):
+        for x in range(value.shape[2]):
+            out[0, y * st:y * st + p, x * st:x * st + q, :] += filt @ value[0, y, x]
+    return out
+
+
+def _deconv_output_length(input_length, filter_size, padding, stride):
+    assert padding == "valid"
+    return input_length * stride + max(filter_size - stride, 0)
+
+
 def _make_tf():
     tf = types.ModuleType("tensorflow")
     tf.float32, tf.int32 = np.float32, np.int32
@@ -130,11 +175,20 @@ def _make_tf():
     tf.clip_by_value = lambda x, lo, hi: np.clip(x, lo, hi)
     tf.cond = lambda pred, a, b: a() if bool(pred) else b()
     tf.case = _case
-    tf.nn = types.SimpleNamespace(moments=_moments, batch_normalization=_batch_normalization)
+    tf.extract_image_patches = _extract_image_patches
+    tf.argmax = lambda x, axis=None: np.argmax(x, axis=axis)
+    tf.one_hot = lambda idx, depth, on, off, axis: np.where(np.arange(int(depth)) == np.expand_dims(idx, -1), _f(on), _f(off))
+    tf.stack = lambda vals: np.array([int(v) for v in vals])
+    tf.ones = lambda shape, dtype=None: np.ones(shape, dtype=STATE["dtype"])
+    tf.tile = lambda x, m: np.tile(x, [int(v) for v in m])
+    tf.divide = lambda a, b: a / b
+    tf.nn = types.SimpleNamespace(moments=_moments, batch_normalization=_batch_normalization, l2_normalize=_l2_normalize,
+                                  conv2d=_conv2d, conv2d_transpose=_conv2d_transpose)
     tf.losses = types.SimpleNamespace(mean_squared_error=None)
     py = types.ModuleType("tensorflow.python")
     layers = types.ModuleType("tensorflow.python.layers")
     utils = types.ModuleType("tensorflow.python.layers.utils")
+    utils.deconv_output_length = _deconv_output_length
     py.layers, layers.utils, tf.python = layers, utils, py
     return {"tensorflow": tf, "tensorflow.python": py, "tensorflow.python.layers": layers,
             "tensorflow.python.layers.utils": utils}
@@ -310,12 +364,12 @@ def reference_modules():
                 sys.modules[k] = v
 
 
-def run_reference(ref, content01, style01, vgg_t7, decoder_weights, relu_targets, alpha, adain, dtype):
+def run_reference(ref, content01, style01, vgg_t7, decoder_weights, relu_targets, alpha, adain, dtype, swap5=False, ss_alpha=0.6):
     """Build (= eagerly evaluate) the reference's WCTModel in test mode exactly as wct.py:31-32 does and return
     (decoded_output of model.py:94, [per-level (content_encoded, decoder_input, decoded)])."""
     import io
-    STATE.update(dtype=dtype, feeds={"content_imgs": content01, "style_img": style01, "alpha": alpha},
-                 unnamed=[np.bool_(False), np.bool_(bool(adain))], weights=decoder_weights)
+    STATE.update(dtype=dtype, feeds={"content_imgs": content01, "style_img": style01, "alpha": alpha, "ss_alpha": ss_alpha},
+                 unnamed=[np.bool_(bool(swap5)), np.bool_(bool(adain))], weights=decoder_weights)
     with contextlib.redirect_stdout(io.StringIO()):
         m = ref.model.WCTModel(mode="test", relu_targets=list(relu_targets), vgg_path=vgg_t7)
     levels = [(np.asarray(e.content_encoded), np.asarray(e.decoder_input), np.asarray(e.decoded)) for e in m.encoder_decoders]

@@ -102,7 +102,7 @@ def load_pipeline_fixture(path):
 
 
 def test_pipeline_golden_present():
-    assert len(PIPE_GOLDEN) >= 4
+    assert len(PIPE_GOLDEN) >= 5
 
 
 @pytest.mark.parametrize("path", PIPE_GOLDEN, ids=[os.path.basename(p)[9:-4] for p in PIPE_GOLDEN])
@@ -110,13 +110,14 @@ def test_oracle_pipeline_matches_reference_code_fixture(path):
     """oracle.nets.pipeline (encoder + wct_tf | adain + decoder + level wiring) == the reference's WCTModel code."""
     g, targets, w = load_pipeline_fixture(path)
     alpha, adain = float(g["alpha"]), bool(g["adain"])
+    swap = dict(swap5=bool(g["swap5"]), ss_alpha=float(g["ss_alpha"]))
     o64, info = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf",
-                              dtype=np.float64, return_info=True)
+                              dtype=np.float64, return_info=True, **swap)
     assert o64.shape == g["out_ref_fp64"].shape
     assert np.abs(o64 - g["out_ref_fp64"]).max() <= 1e-9          # same algorithm in exact arithmetic
     if not adain:
         assert [(i["k_c"], i["k_s"]) for i in info] == [tuple(r) for r in g["k"].tolist()]
-    o32 = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf", dtype=np.float32)
+    o32 = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf", dtype=np.float32, **swap)
     noise = np.abs(g["out_ref_fp32"] - g["out_ref_fp64"]).max()     # the reference code's own fp32 rounding (chained levels amplify it)
     assert np.abs(o32 - g["out_ref_fp32"]).max() <= max(1e-4, 4 * noise)
 
@@ -133,6 +134,7 @@ def test_reference_code_live_reproduces_fixture_if_present(tmp_path):
     dec = {l["name"]: (l["kernel"], l["bias"]) for t in targets for l in w["decoders"][t]}
     with np_tf1.reference_modules() as ref:
         out, levels = np_tf1.run_reference(ref, g["content"][None] / 255.0, g["style"][None] / 255.0, t7, dec, targets,
-                                           float(g["alpha"]), bool(g["adain"]), np.float64)
+                                           float(g["alpha"]), bool(g["adain"]), np.float64, swap5=bool(g["swap5"]),
+                                           ss_alpha=float(g["ss_alpha"]))
     assert np.abs(out - g["out_ref_fp64"]).max() <= 1e-12
     assert "tensorflow" not in __import__("sys").modules or not hasattr(__import__("sys").modules["tensorflow"], "placeholder_with_default")
