@@ -138,6 +138,18 @@ WCTB200_API int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc,
                         const void* style, int Ns, int Hs, int Ws, int C,
                         float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream);
 
+/*
+ * wct_style_swap (ops.py:145-217) + style_swap (ops.py:219-278) for ONE content/style pair, patch 3x3, stride 1
+ * (the reference's defaults, stylize.py --ss-patch-size 3 --ss-stride 1): whiten both encodings, replace every 3x3
+ * content patch by its best-correlated style patch (filters normalised per tap across patches, first arg-max,
+ * overlaps averaged), colour with the style, blend with `alpha` (= --ss-alpha).  k_out (may be NULL): [k_c, k_s].
+ * Used at relu5_1 when --swap5 is given (model.py:148-152).
+ */
+WCTB200_API size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws);
+WCTB200_API int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* style, int Hs, int Ws, int C,
+                             float alpha, float eps_cov, float thresh, void* out, int32_t* k_out, void* ws, size_t ws_bytes,
+                             void* stream);
+
 /* Stand-alone pieces of the transform, exposed for parity tests and profiling:
  * per-channel mean [N][C] and covariance [N][C][C] = fc fc^T/(HW-1) + eps_cov*I of a feature batch
  * (ops.py:43-45,105-108), fp32 outputs. */

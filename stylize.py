@@ -35,8 +35,8 @@ def build_parser():
     p.add_argument('--alpha', type=float, help="Alpha blend value", default=1)
     p.add_argument('--concat', action='store_true', help="Concatenate style image and stylized output", default=False)
     p.add_argument('--adain', action='store_true', help="Use AdaIN instead of WCT", default=False)
-    # style-swap flags are accepted for CLI compatibility; --swap5 itself is out of scope
-    p.add_argument('--swap5', action='store_true', help="Swap style on layer relu5_1 (not supported)", default=False)
+    # style swap at relu5_1 (ops.py:145-278); built for --ss-patch-size 3 --ss-stride 1
+    p.add_argument('--swap5', action='store_true', help="Swap style on layer relu5_1", default=False)
     p.add_argument('--ss-alpha', type=float, default=0.6)
     p.add_argument('--ss-patch-size', type=int, default=3)
     p.add_argument('--ss-stride', type=int, default=1)

@@ -111,7 +111,7 @@ def test_engine_vs_reference_code_golden(path):
     eng = Engine(w, targets, semantics="tf")
     cap = {}
     out = eng.stylize(torch.from_numpy(g["content"][None]).cuda(), torch.from_numpy(g["style"][None]).cuda(), alpha=alpha,
-                      adain=adain, want_info=True, capture=cap)
+                      adain=adain, want_info=True, capture=cap, swap5=bool(g["swap5"]), ss_alpha=float(g["ss_alpha"]))
     eng.check_device()
     got = out.cpu().numpy()
     assert got.shape == g["out_ref_fp64"].shape
@@ -154,8 +154,12 @@ def test_wct_predict_surface(weights):
     ref = nets.pipeline(c, s, weights, ["relu2_1", "relu1_1"], alpha=0.6, semantics="tf", dtype=np.float64)
     diff = np.abs(out.astype(int) - nets.postprocess(ref[0]).astype(int))
     assert diff.max() <= 1                                            # 1e-3 float error may flip a u8 LSB
+    # --swap5 only acts at relu5_1 (model.py:144-158): without that target it changes nothing ...
+    assert np.array_equal(wct.predict(c, s, alpha=0.6, swap5=True, ss_alpha=0.5), out)
+    # ... and only the reference's default patch 3 / stride 1 is built
+    wct2 = WCT(checkpoints=None, relu_targets=["relu2_1", "relu1_1"], vgg_path=None, device="/gpu:0", weights=weights, ss_stride=2)
     with pytest.raises(NotImplementedError):
-        wct.predict(c, s, swap5=True)
+        wct2.predict(c, s, swap5=True)
     out2 = wct.predict(c, s, alpha=0.6, adain=True)
     ref2 = nets.pipeline(c, s, weights, ["relu2_1", "relu1_1"], alpha=0.6, adain=True, dtype=np.float64)
     assert np.abs(out2.astype(int) - nets.postprocess(ref2[0]).astype(int)).max() <= 1

@@ -48,6 +48,8 @@ SIGNATURES = {
     "wctb200_debug_set_jacobi": (_i, [_i, _i]),
     "wctb200_debug_set_conv4": (_i, [_i, _i]),
     "wctb200_debug_set_conv_fuse": (_i, [_i]),
+    "wctb200_style_swap_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "wctb200_style_swap_level": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "wctb200_debug_conv4_trace": (_i, [_vp]),
 }
 

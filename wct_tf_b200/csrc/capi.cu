@@ -70,6 +70,9 @@ int launch_f32_to_u8(const float*, size_t, uint8_t*, cudaStream_t);
 int launch_act_from_f32(const float*, ActGeom, __half*, cudaStream_t);
 int launch_act_to_f32(const __half*, ActGeom, float*, cudaStream_t);
 int launch_prep_weights(const float*, int, int, int, __half*, cudaStream_t);
+size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws);
+int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, float alpha, float eps_cov,
+                            float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_conv3x3_ref(const __half*, ActGeom, const float*, const float*, int, int, __half*, cudaStream_t);
 int launch_conv_head(const float*, int, int, int, const float*, const float*, __half*, cudaStream_t);
 int launch_conv_tail(const __half*, ActGeom, const float*, const float*, int, float*, cudaStream_t);
@@ -283,6 +286,17 @@ int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes) {
     if (lbo_bytes >= 0) g_cov_lbo = lbo_bytes;
     if (sbo_bytes >= 0) g_cov_sbo = sbo_bytes;
     return g_cov_impl;
+}
+size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws) {
+    if (!geom_ok(1, Hc, Wc, C) || !geom_ok(1, Hs, Ws, C) || Hc < 3 || Wc < 3 || Hs < 3 || Ws < 3) return 0;
+    return style_swap_workspace_bytes(C, Hc, Wc, Hs, Ws);
+}
+int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* style, int Hs, int Ws, int C, float alpha,
+                             float eps_cov, float thresh, void* out, int32_t* k_out, void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(content && style && out && ws, "style_swap_level: null pointer");
+    WCTB_REQUIRE(geom_ok(1, Hc, Wc, C) && geom_ok(1, Hs, Ws, C), "style_swap_level: bad geometry");
+    return launch_style_swap_level(HCP(content), Hc, Wc, HCP(style), Hs, Ws, C, alpha, eps_cov, thresh, HP(out), k_out, ws, ws_bytes,
+                                   ST(stream));
 }
 int wctb200_debug_set_conv_fuse(int mode) {
     g_conv_fuse = mode < 0 ? -1 : (mode ? 1 : 0);

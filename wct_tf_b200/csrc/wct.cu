@@ -1138,4 +1138,251 @@ int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __ha
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Style swap at one level (ops.py:145-278: wct_style_swap + style_swap), ONE content/style pair, 3x3 patches, stride 1.
+//   whiten content and style (same eigensolver as the WCT level; whitening on BOTH sides, ops.py:187-196)
+//   -> every 3x3 patch of the whitened style becomes a conv filter, normalised per filter TAP across patches
+//      (tf.nn.l2_normalize(style_patches, dim=3), ops.py:233) -> cross-correlation with the whitened content on the
+//      tensor cores (the patches are just a weight tensor for the 3x3 conv kernel; VALID = the interior of the SAME conv)
+//   -> first arg-max per position (ops.py:242) -> paste the un-normalised patch back and average the overlaps
+//      (conv2d_transpose / counting, ops.py:255-276 = a gather of <= 9 style pixels per output pixel)
+//   -> colour with the style (S^+1/2), add the style mean, blend with the content (ops.py:203-210).
+// ---------------------------------------------------------------------------
+static inline int swap_grid(long long total, int block) {
+    long long b = (total + block - 1) / block;
+    return (int)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b));
+}
+
+struct SwapWs {
+    size_t base, zeros, dvec2, sigma2, mats, msplit, bias3, norms, idx, wc_feat, ws_feat, ss_feat, tmp, scores, wsplit, total;
+    int cout_pad, n_patches;
+};
+static SwapWs swap_layout(int C, int Hc, int Wc, int Hs, int Ws) {
+    SwapWs L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    L.n_patches = (Hs - 2) * (Ws - 2);
+    L.cout_pad = (L.n_patches + 63) / 64 * 64;
+    L.base = take(wct_layout(C, 1, 1).total);
+    L.zeros = take((size_t)C * 4);
+    L.dvec2 = take((size_t)C * 4);
+    L.sigma2 = take((size_t)C * 4);
+    L.mats = take((size_t)3 * C * C * 4);                         // W_c, W_s (whitening), C_s (colouring)
+    L.msplit = take((size_t)3 * 2 * C * C * 2);
+    L.bias3 = take((size_t)3 * C * 4);
+    L.norms = take((size_t)9 * C * 4);
+    L.idx = take((size_t)(Hc - 2) * (Wc - 2) * 4);
+    const size_t fc = (size_t)ActGeom(1, Hc, Wc, C).plane * 2 * sizeof(__half), fs = (size_t)ActGeom(1, Hs, Ws, C).plane * 2 * sizeof(__half);
+    L.wc_feat = take(fc);
+    L.ws_feat = take(fs);
+    L.ss_feat = take(fc);
+    L.tmp = take(fc);
+    L.scores = take((size_t)ActGeom(1, Hc, Wc, L.cout_pad).plane * 2 * sizeof(__half));
+    L.wsplit = take((size_t)2 * 9 * C * L.cout_pad * sizeof(__half));
+    L.total = o;
+    return L;
+}
+size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws) { return swap_layout(C, Hc, Wc, Hs, Ws).total; }
+
+// 1 / ||patch tap||: for every (tap, channel) the l2 norm ACROSS all patches (ops.py:233); block = (tap, 256 channels)
+__global__ void k_swap_tap_norms(const __half* __restrict__ feat, ActGeom g, float* __restrict__ inv_norm) {
+    const int tap = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.C) return;
+    const int ky = tap / 3, kx = tap % 3;
+    float s = 0.f;
+    for (int sy = 0; sy < g.H - 2; ++sy)
+        for (int sx = 0; sx < g.W - 2; ++sx) {
+            const long long pos = ((long long)(sy + ky + 1)) * g.Wp + (sx + kx + 1);      // interior pixel -> padded position
+            const float v = merge_f32(feat[pos * g.C + c], feat[g.plane + pos * g.C + c]);
+            s = fmaf(v, v, s);
+        }
+    inv_norm[tap * g.C + c] = rsqrtf(fmaxf(s, 1e-12f));
+}
+// conv weights of the correlation: [plane][patch n][tap*C + c] = whitened_style[sy+ky][sx+kx][c] * inv_norm[tap][c]; rows >= n_patches zero
+__global__ void k_swap_patch_weights(const __half* __restrict__ feat, ActGeom g, const float* __restrict__ inv_norm,
+                                     int n_patches, int cout_pad, __half* __restrict__ wsplit) {
+    const long long K = 9ll * g.C, total = K * cout_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / K);
+        const int k = (int)(i - (long long)n * K);
+        float v = 0.f;
+        if (n < n_patches) {
+            const int tap = k / g.C, c = k - tap * g.C;
+            const int sy = n / (g.W - 2), sx = n - sy * (g.W - 2);
+            const long long pos = ((long long)(sy + tap / 3 + 1)) * g.Wp + (sx + tap % 3 + 1);
+            v = merge_f32(feat[pos * g.C + c], feat[g.plane + pos * g.C + c]) * inv_norm[k];
+        }
+        __half hi, lo;
+        split_f32(v, hi, lo);
+        wsplit[i] = hi;
+        wsplit[total + i] = lo;
+    }
+}
+// first arg-max over the patch axis for every VALID position (y,x): the SAME-conv output at interior pixel (y+1, x+1)
+__global__ void k_swap_argmax(const __half* __restrict__ scores, ActGeom g, int n_patches, int* __restrict__ idx) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int wo = g.W - 2, ho = g.H - 2;
+    if (warp >= ho * wo) return;
+    const int y = warp / wo, x = warp - y * wo;
+    const long long pos = ((long long)(y + 2)) * g.Wp + (x + 2);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int n = lane; n < n_patches; n += 32) {
+        const float v = merge_f32(scores[pos * g.C + n], scores[g.plane + pos * g.C + n]);
+        if (v > best) { best = v; bi = n; }                       // strictly greater: keeps the first maximum of this lane
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) idx[warp] = bi;
+}
+// conv2d_transpose of the one-hot map with the raw patches, divided by the overlap count: output pixel (Y,X) averages,
+// over the <= 9 patch positions (Y-dy, X-dx) that cover it, the style pixel (sy+dy, sx+dx) of the matched patch
+__global__ void k_swap_gather(const __half* __restrict__ sfeat, ActGeom gs, const int* __restrict__ idx, ActGeom gc,
+                              __half* __restrict__ out) {
+    const int cg = gc.C / 8;
+    const long long total = (long long)gc.H * gc.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        const int pix = (int)(i / cg);
+        const int Y = pix / gc.W, X = pix - Y * gc.W;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        int cnt = 0;
+        for (int dy = 0; dy < 3; ++dy) {
+            const int py = Y - dy;
+            if (py < 0 || py >= gc.H - 2) continue;
+            for (int dx = 0; dx < 3; ++dx) {
+                const int px = X - dx;
+                if (px < 0 || px >= gc.W - 2) continue;
+                const int n = idx[py * (gc.W - 2) + px];
+                const int sy = n / (gs.W - 2), sx = n - sy * (gs.W - 2);
+                float v[8];
+                load8(sfeat, gs, ((long long)(sy + dy + 1)) * gs.Wp + (sx + dx + 1), c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                ++cnt;
+            }
+        }
+        const float inv = 1.f / (float)cnt;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        Half8 hi, lo;
+        split8(acc, hi, lo);
+        store8_with_halo(out, gc, 0, Y, X, c0, hi, lo);
+    }
+}
+// out = a*x + b*y on SPF16 interiors (+ halos)
+__global__ void k_blend2(const __half* __restrict__ x, const __half* __restrict__ y, ActGeom g, float a, float b,
+                         __half* __restrict__ out) {
+    const int cg = g.C / 8;
+    const long long total = (long long)g.N * g.H * g.W * cg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cg) * 8;
+        long long pix = i / cg;
+        const int X = (int)(pix % g.W); pix /= g.W;
+        const int Y = (int)(pix % g.H);
+        const int n = (int)(pix / g.H);
+        const long long pos = ((long long)n * g.Hp + Y + 1) * g.Wp + X + 1;
+        float u[8], v[8];
+        load8(x, g, pos, c0, u);
+        load8(y, g, pos, c0, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = fmaf(a, u[j], b * v[j]);
+        Half8 hi, lo;
+        split8(u, hi, lo);
+        store8_with_halo(out, g, n, Y, X, c0, hi, lo);
+    }
+}
+
+int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, float alpha,
+                            float eps_cov, float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "style_swap: C=%d not in {64,128,256,512}", C);
+    WCTB_REQUIRE(Hc >= 3 && Wc >= 3 && Hs >= 3 && Ws >= 3, "style_swap: maps must be at least 3x3 (content %dx%d, style %dx%d)", Hc, Wc, Hs, Ws);
+    const SwapWs S = swap_layout(C, Hc, Wc, Hs, Ws);
+    if (ws_bytes < S.total) {
+        set_error("style_swap: workspace %zu < %zu bytes", ws_bytes, S.total);
+        return WCTB200_EWS;
+    }
+    uint8_t* sw = static_cast<uint8_t*>(ws);
+    const WctWs L = wct_layout(C, 1, 1);
+    uint8_t* w = sw + S.base;
+    double* sum = reinterpret_cast<double*>(w + L.sum);
+    double* cov = reinterpret_cast<double*>(w + L.cov);
+    float* mean = reinterpret_cast<float*>(w + L.mean);          // [mc, ms]
+    float* G = reinterpret_cast<float*>(w + L.G);
+    float* A0 = reinterpret_cast<float*>(w + L.A0);
+    float* lam = reinterpret_cast<float*>(w + L.lam);
+    float* sigma = reinterpret_cast<float*>(w + L.sigma);
+    float* dvec = reinterpret_cast<float*>(w + L.dvec);          // whitening scalings of content and style
+    float* conv = reinterpret_cast<float*>(w + L.conv);
+    int* kc = reinterpret_cast<int*>(w + L.kcount);
+    float* zeros = reinterpret_cast<float*>(sw + S.zeros);
+    float* dvec2 = reinterpret_cast<float*>(sw + S.dvec2);       // colouring scaling of the style
+    float* sigma2 = reinterpret_cast<float*>(sw + S.sigma2);
+    float* mats = reinterpret_cast<float*>(sw + S.mats);
+    __half* msplit = reinterpret_cast<__half*>(sw + S.msplit);
+    float* bias3 = reinterpret_cast<float*>(sw + S.bias3);
+    float* norms = reinterpret_cast<float*>(sw + S.norms);
+    int* idx = reinterpret_cast<int*>(sw + S.idx);
+    __half* wc_feat = reinterpret_cast<__half*>(sw + S.wc_feat);
+    __half* ws_feat = reinterpret_cast<__half*>(sw + S.ws_feat);
+    __half* ss_feat = reinterpret_cast<__half*>(sw + S.ss_feat);
+    __half* tmp = reinterpret_cast<__half*>(sw + S.tmp);
+    __half* scores = reinterpret_cast<__half*>(sw + S.scores);
+    __half* wsplit = reinterpret_cast<__half*>(sw + S.wsplit);
+    const long long CC = (long long)C * C;
+
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
+    WCTB_CUDA(cudaMemsetAsync(kc, 0, 4 * 4, st));
+    WCTB_CUDA(cudaMemsetAsync(zeros, 0, (size_t)C * 4, st));
+    ActGeom gc(1, Hc, Wc, C), gs(1, Hs, Ws, C);
+    int rc = stats_and_cov(content, gc, sum, cov, mean, G, A0, eps_cov, st);
+    if (rc) return rc;
+    rc = stats_and_cov(style, gs, sum + C, cov + CC, mean + C, G + CC, A0 + CC, eps_cov, st);
+    if (rc) return rc;
+    rc = launch_jacobi(G, C, 2, conv, kc + 2, st);
+    if (rc) return rc;
+    rc = launch_eig_post(G, A0, lam, C, 2, thresh, 0.f, 2, sigma, dvec, kc, st);          // S^-1/2 for BOTH (ops.py:187,193)
+    if (rc) return rc;
+    k_eig_post<<<dim3((unsigned)cdiv(C, 8), 1), 256, 0, st>>>(G + CC, lam + C, C, thresh, 0.f, 0, sigma2, dvec2, nullptr);   // S^+1/2 (ops.py:203)
+    WCTB_CHECK_LAUNCH("k_eig_post(colour)");
+    dim3 g2((unsigned)(C / 64), (unsigned)(C / 64), 2), g1((unsigned)(C / 64), (unsigned)(C / 64), 1);
+    k_outer_gemm<<<g2, 256, 0, st>>>(G, CC, G, CC, dvec, C, mats, CC, C);                   // W_c, W_s
+    WCTB_CHECK_LAUNCH("k_outer_gemm(whiten)");
+    k_outer_gemm<<<g1, 256, 0, st>>>(G + CC, CC, G + CC, CC, dvec2, C, mats + 2 * CC, CC, C);   // C_s
+    WCTB_CHECK_LAUNCH("k_outer_gemm(colour)");
+    // operand 0/1: x -> W (x - m)   (alpha = 1, "style mean" = 0);  operand 2: x -> C_s x + m_s  ("content mean" = 0)
+    k_finalize_transform<<<dim3((unsigned)cdiv(C, 8), 2), 256, 0, st>>>(mats, C, 2, 1, 1.f, 0, mean, zeros, msplit, bias3);
+    WCTB_CHECK_LAUNCH("k_finalize_transform(whiten)");
+    k_finalize_transform<<<dim3((unsigned)cdiv(C, 8), 1), 256, 0, st>>>(mats + 2 * CC, C, 1, 1, 1.f, 0, zeros, mean + C, msplit + 4 * CC,
+                                                                         bias3 + 2 * C);
+    WCTB_CHECK_LAUNCH("k_finalize_transform(colour)");
+    rc = launch_conv3x3_tc(content, 1, Hc, Wc, C, msplit, 1, 1, bias3, C, 0, wc_feat, st);
+    if (rc) return rc;
+    rc = launch_conv3x3_tc(style, 1, Hs, Ws, C, msplit + 2 * CC, 1, 1, bias3 + C, C, 0, ws_feat, st);
+    if (rc) return rc;
+    k_swap_tap_norms<<<dim3((unsigned)cdiv(C, 256), 9), 256, 0, st>>>(ws_feat, gs, norms);
+    WCTB_CHECK_LAUNCH("k_swap_tap_norms");
+    k_swap_patch_weights<<<swap_grid(9ll * C * S.cout_pad, 256), 256, 0, st>>>(ws_feat, gs, norms, S.n_patches, S.cout_pad, wsplit);
+    WCTB_CHECK_LAUNCH("k_swap_patch_weights");
+    rc = launch_conv3x3_tc(wc_feat, 1, Hc, Wc, C, wsplit, 9, 1, nullptr, S.cout_pad, 0, scores, st);
+    if (rc) return rc;
+    const int npos = (Hc - 2) * (Wc - 2);
+    k_swap_argmax<<<(unsigned)cdiv((long long)npos * 32, 256), 256, 0, st>>>(scores, ActGeom(1, Hc, Wc, S.cout_pad), S.n_patches, idx);
+    WCTB_CHECK_LAUNCH("k_swap_argmax");
+    k_swap_gather<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(ws_feat, gs, idx, gc, ss_feat);
+    WCTB_CHECK_LAUNCH("k_swap_gather");
+    rc = launch_conv3x3_tc(ss_feat, 1, Hc, Wc, C, msplit + 4 * CC, 1, 1, bias3 + 2 * C, C, 0, tmp, st);
+    if (rc) return rc;
+    k_blend2<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(tmp, content, gc, alpha, 1.f - alpha, out);   // ops.py:210
+    WCTB_CHECK_LAUNCH("k_blend2");
+    if (k_out) WCTB_CUDA(cudaMemcpyAsync(k_out, kc, 2 * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 }  // namespace wctb

@@ -224,6 +224,26 @@ class Engine(object):
                    bytes_=4.0 * C * (2 * content.N * hwc + style.N * hws))
         return out, kbuf
 
+    def style_swap(self, content, style, ss_alpha, want_info=False):
+        """wct_style_swap (ops.py:145-217) on one content/style pair: patch 3x3, stride 1."""
+        assert content.N == 1 and style.N == 1, "style swap works on one content/style pair (ops.py:146)"
+        st = self._stream()
+        C = content.C
+        out = self._act(1, content.H, content.W, C)
+        nbytes = self.lib.wctb200_style_swap_workspace_bytes(C, content.H, content.W, style.H, style.W)
+        if nbytes == 0:
+            raise ValueError("style swap needs encodings of at least 3x3 (content %dx%d, style %dx%d)"
+                             % (content.H, content.W, style.H, style.W))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        kbuf = torch.empty(4, dtype=torch.int32, device=self.device) if want_info else None
+        sem = SEMANTICS["tf"]                  # the reference only has the TF graph version of this op
+        self._call("style_swap[C%d]" % C, 22, self.lib.wctb200_style_swap_level, content.ptr, content.H, content.W, style.ptr,
+                   style.H, style.W, C, float(ss_alpha), sem["eps_cov"], sem["thresh"], out.ptr,
+                   kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st)
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append(ws)                  # the workspace must outlive the asynchronous launches of this step
+        return out, kbuf
+
     def style_prepare(self, style):
         """Style side of one level (ops.py:48-55,76): means, covariance, eigendecomposition, C_s.
         Returns the device state buffer consumed by ``wct_apply``."""
@@ -253,7 +273,7 @@ class Engine(object):
         return out, kbuf
 
     # ------------------------------------------------------------------ pipeline
-    def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None):
+    def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None, swap5=False, ss_alpha=0.6):
         """content_u8: cuda uint8 [N,H,W,3]; style_u8: cuda uint8 [Ns,Hs,Ws,3], Ns in {1, N}.
         Returns the float32 ``decoded_output`` [N,H',W',3] (unclipped, model.py:94).
         ``capture`` (dict) receives every level's input image / features for parity tests.
@@ -263,6 +283,12 @@ class Engine(object):
         eigendecompositions are latency bound on a few SMs, so one group's Jacobi clusters overlap the
         other groups' convolutions (same arithmetic per frame; only the schedule changes)."""
         N = content_u8.shape[0]
+        swap5 = bool(swap5) and "relu5_1" in [l.relu_target for l in self.model.levels]    # model.py:148: only relu5_1 swaps
+        if swap5:
+            if N != 1 or style_u8.shape[0] != 1:
+                raise ValueError("swap5 works on one content/style pair per call (ops.py:146)")
+            self._keep = []
+            return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture, True, ss_alpha)
         G = min(self.groups, N) if (capture is None and not want_info) else 1
         if G > 1:
             main = torch.cuda.current_stream(self.device)
@@ -292,7 +318,7 @@ class Engine(object):
             return out
         return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture)
 
-    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture):
+    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture, swap5=False, ss_alpha=0.6):
         lib, st = self.lib, self._stream()
         N = content_u8.shape[0]
         assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
@@ -300,7 +326,7 @@ class Engine(object):
         content = torch.empty(content_u8.shape, dtype=torch.float32, device=self.device)
         self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st)
         main = torch.cuda.current_stream(self.device)
-        split = not adain                      # WCT: style side on its own stream; AdaIN: cheap, keep it inline
+        split = not adain and not swap5        # WCT: style side on its own stream; AdaIN / style swap: keep it inline
         side = main
         if split and self.overlap_style:
             if self._group not in self._style_streams:
@@ -328,7 +354,9 @@ class Engine(object):
         n_style = style_u8.shape[0]
         for lvl in self.model.levels:
             cf, _ = self.encode(x, lvl.relu_target)
-            if split:
+            if swap5 and lvl.relu_target == "relu5_1":     # model.py:148-152: style swap wins over AdaIN / WCT at relu5_1
+                f, kbuf = self.style_swap(cf, style_feats[lvl.relu_target], ss_alpha, want_info)
+            elif split:
                 if side is not main:
                     main.wait_event(style_events[lvl.relu_target])
                 f, kbuf = self.wct_apply(cf, style_states[lvl.relu_target], n_style, alpha, want_info)

@@ -6,7 +6,7 @@ sm_100a engine (engine.py -> libwctb200.so).  Differences, all explicit:
     weights.py) OR ``weights=`` may pass an in-memory weights dict (the offline
     build has no .t7 / TF checkpoints, so benchmarks use synthetic weights);
   * ``device`` accepts the reference's TF strings ('/gpu:0') and torch strings;
-  * ``swap5=True`` (style-swap, ops.py:145-278) is out of scope -> NotImplementedError;
+  * ``swap5=True`` (style-swap at relu5_1, ops.py:145-278) is built for patch 3 / stride 1 (the defaults);
   * ``predict_batch`` is new: a batch of frames per call (frames are independent).
 """
 from __future__ import annotations
@@ -61,7 +61,7 @@ class WCT(object):
         """wct.py:66-68"""
         return np.uint8(np.clip(image, 0, 1) * 255)
 
-    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False, out=None):
+    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False, out=None, swap5=False, ss_alpha=1):
         """contents: uint8 [N,H,W,3]; styles: uint8 [1|N,Hs,Ws,3] (numpy or torch; host buffers --
         ideally pinned -- or device tensors).  Returns uint8 [N,H',W',3] on the host: a numpy array,
         or ``out`` (a pinned uint8 torch tensor of the right shape) filled in place.  The call is
@@ -81,7 +81,15 @@ class WCT(object):
         with torch.cuda.device(dev):
             c = to_dev(contents)
             s = to_dev(styles)
-            out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
+            if swap5:
+                if self.ss_patch_size != 3 or self.ss_stride != 1:
+                    raise NotImplementedError("style swap is built for --ss-patch-size 3 --ss-stride 1 (the reference's defaults)")
+                # one pair per call like the reference graph (ops.py:146); frames of a batch are swapped one by one
+                outs = [eng.stylize(c[i:i + 1], s[i:i + 1] if s.shape[0] > 1 else s, alpha=alpha, adain=adain, swap5=True,
+                                    ss_alpha=ss_alpha) for i in range(c.shape[0])]
+                out_f = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+            else:
+                out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
             out_dev = eng.to_u8(out_f)
             if out is not None:
                 out.copy_(out_dev, non_blocking=True)
@@ -95,10 +103,8 @@ class WCT(object):
 
     def predict(self, content, style, alpha=1, swap5=False, ss_alpha=1, adain=False):
         '''Stylize a single content/style pair (wct.py:70-106).'''
-        if swap5:
-            raise NotImplementedError("style-swap at relu5_1 (ops.py:145-278) is out of scope for this engine")
         s = time.time()
-        out = self.predict_batch(np.asarray(content), np.asarray(style), alpha=alpha, adain=adain)
+        out = self.predict_batch(np.asarray(content), np.asarray(style), alpha=alpha, adain=adain, swap5=swap5, ss_alpha=ss_alpha)
         if self.verbose:
             print("Stylized in:", time.time() - s)   # wct.py:104
         return out[0]
