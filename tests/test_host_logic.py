@@ -241,3 +241,14 @@ def test_tf_checkpoint_reader_and_reference_loading_protocol(tmp_path):
     open(prefix + ".data-00000-of-00001", "wb").write(bytes(blob))
     with pytest.raises(T.TFCheckpointError, match="checksum"):
         T.read_bundle(prefix)
+
+
+def test_tf_checkpoint_snappy_block_decoder():
+    """Index blocks may be snappy-compressed (LevelDB block type 1): literals, 1/2-byte-offset copies, overlapping copies."""
+    from wct_tf_b200.tf_checkpoint import _snappy_decompress
+    # "abcdabcdabcdabcdXYZ": literal "abcd", copy(len 12, offset 4) with a 2-byte offset, literal "XYZ"
+    comp = bytes([19, (4 - 1) << 2]) + b"abcd" + bytes([((12 - 1) << 2) | 2, 4, 0]) + bytes([(3 - 1) << 2]) + b"XYZ"
+    assert _snappy_decompress(comp) == b"abcdabcdabcdabcdXYZ"
+    # copy with a 1-byte offset (tag type 1: len 4..11, offset < 2048): "xyxyxyxyxy"
+    comp = bytes([10, (2 - 1) << 2]) + b"xy" + bytes([((8 - 4) << 2) | 1, 2])
+    assert _snappy_decompress(comp) == b"xy" * 5

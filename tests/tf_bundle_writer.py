@@ -52,7 +52,7 @@ def write_bundle(prefix, tensors, block_entries=5):
     os.makedirs(os.path.dirname(prefix), exist_ok=True)
     data, pairs = bytearray(), [(b"", _field(1, 0, _vi(1)) + _field(2, 0, _vi(0)))]          # BundleHeaderProto: 1 shard, little endian
     for name in sorted(tensors):
-        a = np.ascontiguousarray(tensors[name])
+        a = np.asarray(tensors[name], order="C")          # (ascontiguousarray would turn a scalar into shape (1,))
         raw = a.tobytes()
         pairs.append((name.encode(), _entry(a, len(data), len(raw), masked_crc32c(raw))))
         data += raw
