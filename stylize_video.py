@@ -1,0 +1,176 @@
+#!/usr/bin/env python
+"""Video / frame-sequence driver with the reference's flags (stylize_video.py:17-42 of eridgd/WCT-TF).
+
+The reference splits the video into PNG frames with ffmpeg, calls ``WCT.predict`` once per frame and re-encodes
+(stylize_video.py:75-149).  Here frames go through ``WCT.predict_batch`` in batches that share ONE style image (the
+style side of every level is computed once per batch), while a thread pool decodes the next batch and writes the
+previous one, so the GPU never waits for PNG I/O.  ``--in-path`` may also be a directory of frames (then no ffmpeg is
+needed and the stylised frames are left in ``--out-path``); ffmpeg is used only when it is installed.
+Additions: ``--batch``, ``--synthetic-weights``, ``--adain``.
+"""
+from __future__ import division, print_function
+
+import argparse
+import os
+import random
+import shutil
+import subprocess
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument('--checkpoints', nargs='+', type=str, help='List of checkpoint directories', default=None)
+    p.add_argument('--relu-targets', nargs='+', type=str, help='List of reluX_1 layers, corresponding to --checkpoints', required=True)
+    p.add_argument('--vgg-path', type=str, help='Path to vgg_normalised.t7', default='models/vgg_normalised.t7')
+    p.add_argument('--in-path', type=str, help='Video file, or a directory of frames', required=True)
+    p.add_argument('--out-path', type=str, help='Output folder (videos / stylised frames)', required=True)
+    p.add_argument('--style-path', type=str, help='Style image or folder of style images', required=True)
+    p.add_argument('--tmp-dir', type=str, dest='tmp_dir', help='tmp dir for processing', default=None)
+    p.add_argument('--keep-tmp', action='store_true', help="Don't remove the frame tmp dir afterwards", default=False)
+    p.add_argument('--keep-colors', action='store_true', help="Preserve the colors of the style image", default=False)
+    p.add_argument('--style-size', type=int, help="Resize style image to this size before cropping", default=0)
+    p.add_argument('--crop-size', type=int, help="Crop square size", default=0)
+    p.add_argument('--content-size', type=int, help="Resize short side of content image to this", default=0)
+    p.add_argument('--passes', type=int, help="# of stylization passes per content image", default=1)
+    p.add_argument('--device', type=str, help='Device to perform compute on, e.g. /gpu:0', default='/gpu:0')
+    p.add_argument('--alpha', type=float, help="Alpha blend value", default=1)
+    p.add_argument('--concat', action='store_true', help="Concatenate style image and stylized output", default=False)
+    p.add_argument('--swap5', action='store_true', help="Swap style on layer relu5_1", default=False)
+    p.add_argument('--ss-alpha', type=float, help="Style swap alpha blend", default=0.6)
+    p.add_argument('--ss-patch-size', type=int, help="Style swap patch size", default=3)
+    p.add_argument('--ss-stride', type=int, help="Style swap stride", default=1)
+    # additions
+    p.add_argument('--batch', type=int, default=15, help="frames per predict_batch call")
+    p.add_argument('--adain', action='store_true', default=False)
+    p.add_argument('--fps', type=int, default=30, help="frame rate of the encoded video (stylize_video.py:137)")
+    p.add_argument('--synthetic-weights', type=int, default=None, help="use seeded random weights (no model files needed)")
+    return p
+
+
+def frame_key(name):
+    """frame_12.png sorts after frame_2.png (the reference iterates os.listdir order; ffmpeg numbers the frames)."""
+    digits = ''.join(ch if ch.isdigit() else ' ' for ch in os.path.basename(name)).split()
+    return (int(digits[-1]) if digits else -1, name)
+
+
+def batches(seq, n):
+    for i in range(0, len(seq), n):
+        yield seq[i:i + n]
+
+
+def stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool):
+    """All frames of one clip with one style.  Frames of equal size are batched; decode of batch i+1 and the PNG writes
+    of batch i-1 overlap the GPU work of batch i."""
+    def load(f):
+        img = io.get_img(f)
+        return io.resize_to(img, args.content_size) if args.content_size > 0 else img
+
+    def finish(out_f, stylized, style_rgb):
+        if args.concat:                                        # stylize_video.py:125-128
+            side = stylized.shape[0]
+            stylized = np.hstack([io._imresize(style_rgb, (side, side)), stylized])
+        io.save_img(out_f, stylized)
+
+    todo = list(batches(list(zip(in_files, out_files)), max(1, args.batch)))
+    pending_loads = [pool.submit(load, f) for f, _ in todo[0]] if todo else []
+    writes, count = [], 0
+    for bi, group in enumerate(todo):
+        frames = [f.result() for f in pending_loads]
+        pending_loads = [pool.submit(load, f) for f, _ in todo[bi + 1]] if bi + 1 < len(todo) else []
+        same = all(fr.shape == frames[0].shape for fr in frames) and not args.keep_colors and not args.swap5
+        if same and len(frames) > 1:
+            x = np.stack(frames)
+            out = wct_model.predict_batch(x, style_img[None], alpha=args.alpha, adain=args.adain)
+            for _ in range(args.passes - 1):                   # stylize_video.py:119-121
+                out = wct_model.predict_batch(out, style_img[None], alpha=args.alpha, adain=args.adain)
+            results = [(out[i], style_img) for i in range(len(frames))]
+        else:                                                  # per-frame styles (CORAL), style swap or ragged sizes
+            results = []
+            for fr in frames:
+                style_rgb = io.preserve_colors_np(style_img, fr) if args.keep_colors else style_img
+                o = wct_model.predict(fr, style_rgb, args.alpha, args.swap5, args.ss_alpha, args.adain)
+                for _ in range(args.passes - 1):
+                    o = wct_model.predict(o, style_rgb, args.alpha, False, args.ss_alpha, args.adain)
+                results.append((o, style_rgb))
+        for (_, out_f), (o, srgb) in zip(group, results):
+            writes.append(pool.submit(finish, out_f, np.array(o, copy=True), srgb))
+            count += 1
+    for w in writes:
+        w.result()
+    return count
+
+
+def have_ffmpeg():
+    return shutil.which('ffmpeg') is not None
+
+
+def main(argv=None, wct_factory=None):
+    args = build_parser().parse_args(argv)
+    from wct_tf_b200 import imageio as io
+    start = time.time()
+    if wct_factory is None:
+        from wct_tf_b200.wct import WCT
+        weights = None
+        if args.synthetic_weights is not None:
+            from wct_tf_b200.weights import make_synthetic_weights
+            weights = make_synthetic_weights(args.synthetic_weights, relu_targets=args.relu_targets)
+        elif not args.checkpoints:
+            raise SystemExit("--checkpoints is required (or --synthetic-weights SEED)")
+        wct_model = WCT(checkpoints=args.checkpoints, relu_targets=args.relu_targets, vgg_path=args.vgg_path,
+                        device=args.device, ss_patch_size=args.ss_patch_size, ss_stride=args.ss_stride, weights=weights)
+    else:
+        wct_model = wct_factory(args)
+
+    style_files = io.get_files(args.style_path) if os.path.isdir(args.style_path) else [args.style_path]
+    os.makedirs(args.out_path, exist_ok=True)
+    from_dir = os.path.isdir(args.in_path)
+    tmp_dir = args.tmp_dir or os.path.join(args.out_path, '_____fns_frames_%s' % random.randint(0, 99999))
+    if from_dir:
+        in_files = sorted(io.get_files(args.in_path), key=frame_key)
+    else:
+        if not have_ffmpeg():
+            raise SystemExit("ffmpeg is not installed: pass a directory of frames as --in-path")
+        in_dir = os.path.join(tmp_dir, 'input')
+        os.makedirs(in_dir, exist_ok=True)
+        subprocess.check_call(['ffmpeg', '-i', args.in_path, os.path.join(in_dir, 'frame_%d.png')])   # stylize_video.py:75-81
+        in_files = sorted([os.path.join(in_dir, x) for x in os.listdir(in_dir)], key=frame_key)
+    clip = os.path.basename(os.path.normpath(os.path.splitext(args.in_path)[0] if not from_dir else args.in_path))
+    ext = '.mp4' if from_dir else os.path.splitext(args.in_path)[1]
+
+    total = 0
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        for style_fullpath in style_files:                     # stylize_video.py:97
+            style_img = io.get_img(style_fullpath)
+            if args.style_size > 0:
+                style_img = io.resize_to(style_img, args.style_size)
+            if args.crop_size > 0:
+                style_img = io.center_crop(style_img, args.crop_size)
+            style_prefix = os.path.basename(os.path.splitext(style_fullpath)[0])
+            out_v = os.path.join(args.out_path, '{}_{}{}'.format(clip, style_prefix, ext))
+            frames_dir = os.path.join(args.out_path if from_dir else tmp_dir, '{}_{}_frames'.format(clip, style_prefix))
+            if os.path.isfile(out_v):                          # stylize_video.py:108-110
+                print("SKIP", out_v)
+                continue
+            os.makedirs(frames_dir, exist_ok=True)
+            out_files = [os.path.join(frames_dir, os.path.splitext(os.path.basename(f))[0] + '.png') for f in in_files]
+            n = stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool)
+            total += n
+            print("Stylized {} frames with {} -> {}".format(n, style_prefix, frames_dir))
+            if have_ffmpeg():                                  # stylize_video.py:137-149
+                pattern = os.path.join(frames_dir, 'frame_%d.png')
+                subprocess.check_call(['ffmpeg', '-y', '-i', pattern, '-f', 'mp4', '-q:v', '0', '-vcodec', 'mpeg4',
+                                       '-r', str(args.fps), out_v])
+                print('Video at: %s' % out_v)
+    if not from_dir and not args.keep_tmp and len(style_files) == 1:
+        shutil.rmtree(tmp_dir, ignore_errors=True)
+    dt = time.time() - start
+    print('Processed {} frames in: {:.2f}s ({:.1f} frames/s incl. PNG I/O)'.format(total, dt, total / max(dt, 1e-9)))
+    return total
+
+
+if __name__ == '__main__':
+    main()

@@ -38,3 +38,41 @@ def test_coral_matches_target_statistics():
     assert np.allclose(out.reshape(-1, 3).mean(0), tgt.reshape(-1, 3).mean(0), atol=1e-6)
     u8 = io.preserve_colors_np(np.uint8(src * 255), np.uint8(tgt * 255))
     assert u8.dtype == np.uint8 and u8.shape == src.shape
+
+
+def test_video_driver_batches_frames_in_order(tmp_path):
+    """stylize_video.py: frames are numerically ordered, batched with ONE shared style, passes/concat are applied like
+    stylize_video.py:114-130, ragged frames fall back to per-frame predict; no GPU needed (fake WCT)."""
+    import numpy as np
+    from PIL import Image
+    import stylize_video as V
+
+    frames = tmp_path / "clip"
+    frames.mkdir()
+    for i in [1, 2, 10, 11, 3]:                                 # lexicographic order would put 10, 11 before 2
+        Image.fromarray(np.full((8, 12, 3), i, dtype=np.uint8)).save(str(frames / ("frame_%d.png" % i)))
+    Image.fromarray(np.full((16, 12, 3), 4, dtype=np.uint8)).save(str(frames / "frame_4.png"))   # a ragged frame
+    style = tmp_path / "style.png"
+    Image.fromarray(np.full((6, 6, 3), 200, dtype=np.uint8)).save(str(style))
+    calls = []
+
+    class FakeWCT(object):
+        def predict_batch(self, contents, styles, alpha=1, adain=False, **kw):
+            calls.append(("batch", [int(c[0, 0, 0]) for c in contents], styles.shape[0]))
+            return np.asarray(contents) + 1
+
+        def predict(self, content, style, alpha=1, swap5=False, ss_alpha=1, adain=False):
+            calls.append(("single", int(content[0, 0, 0])))
+            return np.asarray(content) + 1
+
+    out = tmp_path / "out"
+    n = V.main(["--relu-targets", "relu1_1", "--in-path", str(frames), "--style-path", str(style), "--out-path", str(out),
+                "--batch", "2", "--passes", "2", "--concat"], wct_factory=lambda a: FakeWCT())
+    assert n == 6
+    assert calls[:2] == [("batch", [1, 2], 1), ("batch", [2, 3], 1)]          # first batch, its second pass
+    order = [c[1] for c in calls if c[0] == "batch"][::2]
+    assert order == [[1, 2], [10, 11]]                                        # frames 3|4 differ in size -> per-frame
+    assert [c[1] for c in calls if c[0] == "single"] == [3, 4, 4, 5]          # 3 (two passes), then the ragged 4 (two passes)
+    res = np.array(Image.open(str(out / "clip_style_frames" / "frame_10.png")))
+    assert res.shape == (8, 8 + 12, 3) and res[0, -1, 0] == 12 and res[0, 0, 0] == 200   # --concat: [style | stylised]
+    assert V.frame_key("frame_12.png") > V.frame_key("frame_2.png")

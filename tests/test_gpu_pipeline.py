@@ -253,3 +253,27 @@ def test_wct_from_reference_weight_files(tmp_path):
     a = WCT(checkpoints=dirs, relu_targets=targets, vgg_path=str(tmp_path / "vgg_normalised.t7")).predict(c, s, alpha=0.7)
     b = WCT(checkpoints=None, relu_targets=targets, vgg_path=None, weights=w).predict(c, s, alpha=0.7)
     assert a.dtype == np.uint8 and np.array_equal(a, b)
+
+
+def test_video_driver_matches_per_frame_predict(tmp_path, weights):
+    """stylize_video.py on a directory of frames == WCT.predict frame by frame (the reference's loop, stylize_video.py:112-135),
+    up to the 1-LSB uint8 effect of batch-vs-single fp64-atomic ordering."""
+    from PIL import Image
+    import stylize_video as V
+    frames = tmp_path / "clip"
+    frames.mkdir()
+    imgs = _imgs(5, 64, 77)
+    for i in range(5):
+        Image.fromarray(imgs[i]).save(str(frames / ("frame_%d.png" % (i + 1))))
+    style = _imgs(1, 48, 78)[0]
+    Image.fromarray(style).save(str(tmp_path / "style.png"))
+    targets = ["relu3_1", "relu2_1", "relu1_1"]
+    n = V.main(["--relu-targets"] + targets + ["--in-path", str(frames), "--style-path", str(tmp_path / "style.png"),
+                "--out-path", str(tmp_path / "out"), "--batch", "3", "--alpha", "0.7"],
+               wct_factory=lambda a: WCT(checkpoints=None, relu_targets=targets, vgg_path=None, weights=weights))
+    assert n == 5
+    ref = WCT(checkpoints=None, relu_targets=targets, vgg_path=None, weights=weights)
+    for i in range(5):
+        got = np.array(Image.open(str(tmp_path / "out" / "clip_style_frames" / ("frame_%d.png" % (i + 1)))))
+        want = ref.predict(imgs[i], style, alpha=0.7)
+        assert got.shape == want.shape and np.abs(got.astype(int) - want.astype(int)).max() <= 1
