@@ -84,9 +84,8 @@ def stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool):
         same = all(fr.shape == frames[0].shape for fr in frames) and not args.keep_colors and not args.swap5
         if same and len(frames) > 1:
             x = np.stack(frames)
-            out = wct_model.predict_batch(x, style_img[None], alpha=args.alpha, adain=args.adain)
-            for _ in range(args.passes - 1):                   # stylize_video.py:119-121
-                out = wct_model.predict_batch(out, style_img[None], alpha=args.alpha, adain=args.adain)
+            # --passes (stylize_video.py:119-121) run back to back on the device
+            out = wct_model.predict_batch(x, style_img[None], alpha=args.alpha, adain=args.adain, passes=args.passes)
             results = [(out[i], style_img) for i in range(len(frames))]
         else:                                                  # per-frame styles (CORAL), style swap or ragged sizes
             results = []

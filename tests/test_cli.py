@@ -57,9 +57,9 @@ def test_video_driver_batches_frames_in_order(tmp_path):
     calls = []
 
     class FakeWCT(object):
-        def predict_batch(self, contents, styles, alpha=1, adain=False, **kw):
-            calls.append(("batch", [int(c[0, 0, 0]) for c in contents], styles.shape[0]))
-            return np.asarray(contents) + 1
+        def predict_batch(self, contents, styles, alpha=1, adain=False, passes=1, **kw):
+            calls.append(("batch", [int(c[0, 0, 0]) for c in contents], styles.shape[0], passes))
+            return np.asarray(contents) + passes
 
         def predict(self, content, style, alpha=1, swap5=False, ss_alpha=1, adain=False):
             calls.append(("single", int(content[0, 0, 0])))
@@ -69,9 +69,8 @@ def test_video_driver_batches_frames_in_order(tmp_path):
     n = V.main(["--relu-targets", "relu1_1", "--in-path", str(frames), "--style-path", str(style), "--out-path", str(out),
                 "--batch", "2", "--passes", "2", "--concat"], wct_factory=lambda a: FakeWCT())
     assert n == 6
-    assert calls[:2] == [("batch", [1, 2], 1), ("batch", [2, 3], 1)]          # first batch, its second pass
-    order = [c[1] for c in calls if c[0] == "batch"][::2]
-    assert order == [[1, 2], [10, 11]]                                        # frames 3|4 differ in size -> per-frame
+    assert calls[0] == ("batch", [1, 2], 1, 2)                                # first batch: one shared style, both passes in one call
+    assert [c[1] for c in calls if c[0] == "batch"] == [[1, 2], [10, 11]]     # frames 3|4 differ in size -> per-frame
     assert [c[1] for c in calls if c[0] == "single"] == [3, 4, 4, 5]          # 3 (two passes), then the ragged 4 (two passes)
     res = np.array(Image.open(str(out / "clip_style_frames" / "frame_10.png")))
     assert res.shape == (8, 8 + 12, 3) and res[0, -1, 0] == 12 and res[0, 0, 0] == 200   # --concat: [style | stylised]

@@ -277,3 +277,16 @@ def test_video_driver_matches_per_frame_predict(tmp_path, weights):
         got = np.array(Image.open(str(tmp_path / "out" / "clip_style_frames" / ("frame_%d.png" % (i + 1)))))
         want = ref.predict(imgs[i], style, alpha=0.7)
         assert got.shape == want.shape and np.abs(got.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_passes_on_device_equal_host_round_trips(weights):
+    """predict_batch(passes=2) (frames stay on the GPU between passes) == predict(predict(x)) (stylize.py:102-104)."""
+    targets = ["relu2_1", "relu1_1"]
+    wct = WCT(checkpoints=None, relu_targets=targets, vgg_path=None, weights=weights)
+    c, s = _imgs(2, 48, 31), _imgs(1, 40, 32)
+    once = wct.predict_batch(c, s, alpha=0.6)
+    twice = wct.predict_batch(once, s, alpha=0.6)
+    fused = wct.predict_batch(c, s, alpha=0.6, passes=2)
+    assert np.array_equal(fused, twice)
+    dev = wct.predict_batch(c, s, alpha=0.6, passes=2, return_device=True)
+    assert dev.is_cuda and dev.dtype == torch.uint8 and np.array_equal(dev.cpu().numpy(), twice)

@@ -61,11 +61,17 @@ class WCT(object):
         """wct.py:66-68"""
         return np.uint8(np.clip(image, 0, 1) * 255)
 
-    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False, out=None, swap5=False, ss_alpha=1):
+    def predict_batch(self, contents, styles, alpha=1, adain=False, return_float=False, out=None, swap5=False, ss_alpha=1,
+                      passes=1, return_device=False):
         """contents: uint8 [N,H,W,3]; styles: uint8 [1|N,Hs,Ws,3] (numpy or torch; host buffers --
         ideally pinned -- or device tensors).  Returns uint8 [N,H',W',3] on the host: a numpy array,
         or ``out`` (a pinned uint8 torch tensor of the right shape) filled in place.  The call is
-        synchronous like the reference's ``sess.run`` (wct.py:97)."""
+        synchronous like the reference's ``sess.run`` (wct.py:97).
+
+        ``passes`` > 1 repeats the stylisation on the previous OUTPUT like stylize.py:102-104 (``--passes``), but keeps the
+        intermediate frames on the device: each pass still ends in the uint8 quantisation of wct.py:66-68 and restarts from
+        /255 (wct.py:60-64), so the result is bit-identical to calling predict once per pass; style swap only acts in the
+        first pass, as in stylize_video.py:117-121.  ``return_device=True`` returns the uint8 cuda tensor instead of a host copy."""
         eng = self.engine
         dev = eng.device
 
@@ -91,6 +97,12 @@ class WCT(object):
             else:
                 out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
             out_dev = eng.to_u8(out_f)
+            for _ in range(int(passes) - 1):
+                out_f = eng.stylize(out_dev, s, alpha=alpha, adain=adain)
+                out_dev = eng.to_u8(out_f)
+            if return_device:
+                torch.cuda.current_stream(dev).synchronize()
+                return (out_dev, out_f) if return_float else out_dev
             if out is not None:
                 out.copy_(out_dev, non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()
