@@ -21,34 +21,31 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 
+# video-specific flags; the stylisation flags are shared with stylize.py (same names and defaults as the reference,
+# stylize_video.py:17-42)
+_VIDEO_FLAGS = [
+    (("--in-path",), dict(type=str, required=True, help="video file, or a directory of frames")),
+    (("--out-path",), dict(type=str, required=True, help="folder for the encoded videos / stylised frames")),
+    (("--style-path",), dict(type=str, required=True, help="style image, or a folder of them")),
+    (("--tmp-dir",), dict(type=str, dest="tmp_dir", default=None, help="where ffmpeg unpacks the frames")),
+    (("--keep-tmp",), dict(action="store_true", default=False, help="keep the unpacked frames")),
+    (("--batch",), dict(type=int, default=15, help="frames per predict_batch call (not in the reference)")),
+    (("--fps",), dict(type=int, default=30, help="frame rate of the encoded video (not in the reference: fixed 30 there)")),
+]
+_SHARED = ("--checkpoints", "--relu-targets", "--vgg-path", "--keep-colors", "--style-size", "--crop-size", "--content-size",
+           "--passes", "--device", "--alpha", "--concat", "--swap5", "--ss-alpha", "--ss-patch-size", "--ss-stride", "--adain",
+           "--synthetic-weights")
+
+
 def build_parser():
-    p = argparse.ArgumentParser()
-    p.add_argument('--checkpoints', nargs='+', type=str, help='List of checkpoint directories', default=None)
-    p.add_argument('--relu-targets', nargs='+', type=str, help='List of reluX_1 layers, corresponding to --checkpoints', required=True)
-    p.add_argument('--vgg-path', type=str, help='Path to vgg_normalised.t7', default='models/vgg_normalised.t7')
-    p.add_argument('--in-path', type=str, help='Video file, or a directory of frames', required=True)
-    p.add_argument('--out-path', type=str, help='Output folder (videos / stylised frames)', required=True)
-    p.add_argument('--style-path', type=str, help='Style image or folder of style images', required=True)
-    p.add_argument('--tmp-dir', type=str, dest='tmp_dir', help='tmp dir for processing', default=None)
-    p.add_argument('--keep-tmp', action='store_true', help="Don't remove the frame tmp dir afterwards", default=False)
-    p.add_argument('--keep-colors', action='store_true', help="Preserve the colors of the style image", default=False)
-    p.add_argument('--style-size', type=int, help="Resize style image to this size before cropping", default=0)
-    p.add_argument('--crop-size', type=int, help="Crop square size", default=0)
-    p.add_argument('--content-size', type=int, help="Resize short side of content image to this", default=0)
-    p.add_argument('--passes', type=int, help="# of stylization passes per content image", default=1)
-    p.add_argument('--device', type=str, help='Device to perform compute on, e.g. /gpu:0', default='/gpu:0')
-    p.add_argument('--alpha', type=float, help="Alpha blend value", default=1)
-    p.add_argument('--concat', action='store_true', help="Concatenate style image and stylized output", default=False)
-    p.add_argument('--swap5', action='store_true', help="Swap style on layer relu5_1", default=False)
-    p.add_argument('--ss-alpha', type=float, help="Style swap alpha blend", default=0.6)
-    p.add_argument('--ss-patch-size', type=int, help="Style swap patch size", default=3)
-    p.add_argument('--ss-stride', type=int, help="Style swap stride", default=1)
-    # additions
-    p.add_argument('--batch', type=int, default=15, help="frames per predict_batch call")
-    p.add_argument('--adain', action='store_true', default=False)
-    p.add_argument('--fps', type=int, default=30, help="frame rate of the encoded video (stylize_video.py:137)")
-    p.add_argument('--synthetic-weights', type=int, default=None, help="use seeded random weights (no model files needed)")
-    return p
+    import stylize
+    parser = argparse.ArgumentParser(description="stylise a video or a frame sequence")
+    for names, kw in stylize._FLAGS:
+        if names[-1] in _SHARED:
+            parser.add_argument(*names, **kw)
+    for names, kw in _VIDEO_FLAGS:
+        parser.add_argument(*names, **kw)
+    return parser
 
 
 def frame_key(name):
