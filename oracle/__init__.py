@@ -13,7 +13,7 @@ Pinning status (see DESIGN.md "Oracle"):
     in the build container (``tests/golden/make_golden.py`` imports
     ``/root/reference/ops.py`` with TensorFlow/Keras stubbed and commits the
     outputs as ``tests/golden/wct_np_*.npz``).
-  * ``wct_tf``, ``adain``, encoder, decoder, level wiring -- PINNED AT SOURCE LEVEL:
+  * ``wct_tf``, ``adain``, ``wct_style_swap``/``style_swap``, encoder, decoder, level wiring -- PINNED AT SOURCE LEVEL:
     ``tests/golden/make_pipeline_golden.py`` imports the reference's own model.py /
     ops.py / vgg_normalised.py / torchfile.py unmodified and evaluates them over
     ``tests/golden/np_tf1.py`` (an eager NumPy stand-in for the TensorFlow/Keras calls
