@@ -182,6 +182,8 @@ WCTB200_API int wctb200_debug_set_conv4(int cluster, int cin_max);
 WCTB200_API int wctb200_debug_conv4_trace(void* dev_buf_1024_i64);
 /* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = per-size default. */
 WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
+/* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4). */
+WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
 /* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
 WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 

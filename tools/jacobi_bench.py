@@ -14,6 +14,8 @@ if os.environ.get("JAC_CASES"):
     CASES = [tuple(int(v) for v in c.split(":")) for c in os.environ["JAC_CASES"].split(",")]
 for (C, hw, count), (lg, stag) in [(c, s) for c in CASES for s in SCHED]:
     lib.wctb200_debug_set_jacobi(lg, stag)
+    if os.environ.get("JAC_TOLQ"):
+        lib.wctb200_debug_set_jacobi_tolq(float(os.environ["JAC_TOLQ"]))
     mats = []
     rng = np.random.default_rng(C + hw)
     for i in range(count):

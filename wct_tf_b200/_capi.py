@@ -46,6 +46,7 @@ SIGNATURES = {
     "wctb200_debug_set_conv_oversub": (_i, [_i]),
     "wctb200_debug_set_cov": (_i, [_i, _i, _i]),
     "wctb200_debug_set_jacobi": (_i, [_i, _i]),
+    "wctb200_debug_set_jacobi_tolq": (_i, [_f]),
     "wctb200_debug_set_conv4": (_i, [_i, _i]),
     "wctb200_debug_set_conv_fuse": (_i, [_i]),
     "wctb200_style_swap_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

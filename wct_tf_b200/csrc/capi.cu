@@ -102,6 +102,7 @@ extern int g_conv4_cluster;
 extern int g_conv4_cin_max;
 extern int g_conv4_dbg;
 extern long long* g_conv4_trace;
+int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
 extern int g_jacobi_stagger;
 extern int g_cov_sbo;
@@ -312,6 +313,7 @@ int wctb200_debug_conv4_trace(void* dev_buf_1024_i64) {
     g_conv4_trace = static_cast<long long*>(dev_buf_1024_i64);
     return 0;
 }
+int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
 int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
     if (lg_groups <= 4) g_jacobi_lg = lg_groups < 0 ? -1 : lg_groups;              // negative: back to the per-size default
     g_jacobi_stagger = stagger_cycles < 0 ? -1 : stagger_cycles;

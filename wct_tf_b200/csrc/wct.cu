@@ -363,6 +363,8 @@ __device__ __forceinline__ void cross_steps(float* cols, float* nrm, int top, in
 //                 barrier), groups start `stagger` cycles apart so that they stay out of phase;
 //   round 0     : additionally the pairs INSIDE both blocks, by recursive halving with the same register-blocked
 //                 step (16|16 -> 8|8 -> 4|4 -> 2|2 -> 1|1 : 8+4+2+1+1 steps instead of 62 one-pair-per-warp steps).
+__device__ float g_jacobi_tolq = 1e-4f;   // predicted-convergence level (see k_jacobi); device global so a probe can vary it
+
 template <int NN>
 __global__ void __launch_bounds__(512, 1)
 k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol,
@@ -391,7 +393,7 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
     // Quadratic convergence: a sweep whose largest cosine was rho leaves ~rho^2 behind.  When a sweep saw
     // nothing above tol_q = 1e-4 (rho^2 = 1e-8 << tol ~ 2.7e-6) its own rotations already finished the job and
     // the verification sweep (no rotations, ~60 % of a sweep's cost) is skipped.
-    const float tolq2 = 1e-4f * 1e-4f;
+    const float tolq2 = g_jacobi_tolq * g_jacobi_tolq;
 
     float null2 = 0.f;                                 // noise floor of the previous sweep (0: every pair is live)
     int sweep = 0;
@@ -819,6 +821,9 @@ static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq,
 // one group), smaller matrices -> 2 groups 600 cycles apart.
 int g_jacobi_lg = -1;
 int g_jacobi_stagger = -1;
+int set_jacobi_tolq(float v) {
+    return cudaMemcpyToSymbol(g_jacobi_tolq, &v, sizeof(float)) == cudaSuccess ? 0 : -1;
+}
 
 int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
     const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
