@@ -286,8 +286,11 @@ def main():
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
                 "frac": achieved_tf / pk["tf"],
-                # dram__bytes_read+write per launch from profiles/r01_ncu_full_conv_tc2.txt (512->512 @64x64, batch 2)
-                "traffic": 27383296 + 16640,
+                # dram__bytes_read+write of ONE launch from profiles/r01_ncu_full_conv_tc2.txt (the 512->512 @64x64 layer at
+                # batch 2: 18.9 MB of weights + 8.9 MB of activations read once, the output stays in L2) -- `achieved` above
+                # is the average over all 65 conv launches of a step, so `traffic_of` names the launch the bytes belong to
+                "traffic": 27385344 + 44288,
+                "traffic_of": "conv_tc2_kernel<128,fused> 512->512 @64x64, batch 2 (ncu --set full); algorithmic operand bytes of that launch: 27.3 MB",
                 "kernel": "conv_tc_kernel (tcgen05 kind::f16, split-fp16 x3: 3 MMAs per algorithmic MAC -> ceiling 1/3 of the bf16 peak)",
                 "peak_source": pk["source"] + " of measured",
                 "share_of_step": conv_ms / step_prof_ms if step_prof_ms else None,
