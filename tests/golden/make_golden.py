@@ -57,5 +57,21 @@ def main():
               "range", float(out64.min()), float(out64.max()))
 
 
+def coral_golden():
+    """--keep-colors: the reference's own utils.preserve_colors_np -> coral.coral_numpy (pure NumPy, imported unmodified)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_coral", "/root/reference/coral.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(21)
+    style = np.uint8(rng.random((20, 26, 3)) * np.array([250, 90, 160]))
+    content = np.uint8(rng.random((18, 22, 3)) * np.array([60, 220, 120]) + 20)
+    coraled = ref.coral_numpy(style / 255., content / 255.)
+    out = np.uint8(np.clip(coraled, 0, 1) * 255.)                       # utils.py:88-90
+    np.savez_compressed(os.path.join(HERE, "coral_keep_colors.npz"), style=style, content=content, coraled=coraled, out=out)
+    print("coral golden", out.shape, out.mean())
+
+
 if __name__ == "__main__":
     main()
+    coral_golden()

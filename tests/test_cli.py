@@ -75,3 +75,13 @@ def test_video_driver_batches_frames_in_order(tmp_path):
     res = np.array(Image.open(str(out / "clip_style_frames" / "frame_10.png")))
     assert res.shape == (8, 8 + 12, 3) and res[0, -1, 0] == 12 and res[0, 0, 0] == 200   # --concat: [style | stylised]
     assert V.frame_key("frame_12.png") > V.frame_key("frame_2.png")
+
+
+def test_keep_colors_matches_reference_golden():
+    """--keep-colors = utils.preserve_colors_np -> coral.coral_numpy of the reference (tests/golden/make_golden.py), including
+    its non-symmetric ``matSqrt`` (coral.py:8-11)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coral_keep_colors.npz"))
+    c = io.coral(g["style"] / 255., g["content"] / 255.)
+    assert np.abs(c - g["coraled"]).max() < 1e-9
+    assert np.array_equal(io.preserve_colors_np(g["style"], g["content"]), g["out"])

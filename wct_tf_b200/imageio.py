@@ -49,8 +49,11 @@ def center_crop(img, size=256):
 
 
 def _mat_sqrt(x):
-    u, d, vt = np.linalg.svd(x)
-    return (u * np.sqrt(d)) @ vt
+    """coral.py:8-11 verbatim in effect: ``U, D, V = np.linalg.svd(x); U diag(sqrt D) V.T``.  numpy returns V^H as the third
+    value, so for the symmetric input this is U sqrt(D) U -- NOT the symmetric square root U sqrt(D) U^T.  The reference's
+    --keep-colors output depends on it, so it is reproduced (pinned by tests/golden/coral_keep_colors.npz)."""
+    u, d, vh = np.linalg.svd(x)
+    return (u * np.sqrt(d)) @ vh.T
 
 
 def coral(source, target):
