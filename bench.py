@@ -313,7 +313,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only (the other ranks would just wait)
             cores = min(os.cpu_count() or 1, 32)
             sec = cpu_frame_seconds(weights, 1, cores)
             cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
