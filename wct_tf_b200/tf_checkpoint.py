@@ -100,13 +100,23 @@ def _snappy_decompress(b):
     return bytes(out)
 
 
+def _checksum_problem(verify, message):
+    """verify=True: raise; verify="warn" (default): warn -- this reader could not be tried on a checkpoint written by TensorFlow
+    itself, so a disagreement about what a checksum covers must not make a readable file unreadable; verify=False: ignore."""
+    if verify is True:
+        raise TFCheckpointError(message)
+    if verify:
+        import warnings
+        warnings.warn("tf_checkpoint: " + message)
+
+
 def _read_block(f, offset, size, verify):
     raw = f[offset:offset + size + 5]
     if len(raw) < size + 5:
         raise TFCheckpointError("truncated table block")
     contents, ctype = raw[:size], raw[size]
     if verify and struct.unpack("<I", raw[size + 1:size + 5])[0] != masked_crc32c(raw[:size + 1]):
-        raise TFCheckpointError("table block checksum mismatch")
+        _checksum_problem(verify, "table block checksum mismatch")
     if ctype == 1:
         contents = _snappy_decompress(contents)
     elif ctype != 0:
@@ -134,7 +144,7 @@ def _handle(b, p=0):
     return off, size, p
 
 
-def read_table(path, verify=True):
+def read_table(path, verify="warn"):
     """All (key, value) pairs of a LevelDB-format table file, in key order."""
     f = open(path, "rb").read()
     if len(f) < 48 or struct.unpack("<Q", f[-8:])[0] != TABLE_MAGIC:
@@ -198,7 +208,7 @@ def _parse_entry(b):
     return e
 
 
-def read_bundle(prefix, verify=True):
+def read_bundle(prefix, verify="warn"):
     """{variable name: numpy array} of one checkpoint ``prefix`` (the path without .index / .data-*)."""
     entries = read_table(prefix + ".index", verify)
     if not entries or entries[0][0] != b"":
@@ -227,7 +237,7 @@ def read_bundle(prefix, verify=True):
         if len(raw) != e["size"] or e["size"] != want:
             raise TFCheckpointError("tensor %r: %d bytes in the shard, shape %s needs %d" % (key.decode(), len(raw), e["shape"], want))
         if verify and e["crc32c"] is not None and e["crc32c"] != masked_crc32c(raw):
-            raise TFCheckpointError("tensor %r: checksum mismatch" % key.decode())
+            _checksum_problem(verify, "tensor %r: checksum mismatch" % key.decode())
         out[key.decode()] = np.frombuffer(raw, dtype=dt).reshape(e["shape"]).copy()
     return out
 
