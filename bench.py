@@ -13,8 +13,10 @@ no work is shared or cached between frames).
   value   frames/s, inputs (uint8 frames) already resident in HBM, CUDA-event timed
   e2e     frames/s through the public API (WCT.predict_batch) with PINNED HOST uint8
           buffers: H2D of contents+styles and D2H of the uint8 results inside the timed region
-  roofline  the dominant kernel = conv_tc_kernel (tcgen05 implicit-GEMM conv): algorithmic
-          conv FLOPs / CUDA-event time of those launches, vs the measured bf16 peak
+  roofline  the dominant kernel = conv_tc2_kernel (tcgen05 implicit-GEMM conv): EXECUTED algorithmic conv
+          FLOPs (2*taps*Cin*Cout per output pixel; 4 taps for the convs that absorbed an UpSampling2D) /
+          CUDA-event time of those launches, vs the measured bf16 peak; per-level tensor-pipe fractions and
+          covariance-only HBM GB/s beside it (north_star)
   cpu_baseline  the oracle (CPU restatement of the reference, torch-CPU convs + NumPy/LAPACK
           transform) timed on the host cores on ONE frame of the same workload
 
@@ -41,6 +43,9 @@ TARGETS = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
 SIZE = 512
 ALPHA = 0.8
 SEMANTICS = "tf"   # what stylize.py actually executes (model.py:154,158)
+
+WORKLOAD = ("configs[1]: 5-level relu5_1->relu1_1, 512x512 content, 512x512 style per frame, alpha=0.8, "
+            "wct_tf semantics")
 
 # algorithmic FLOPs per frame, style re-encoded per frame
 GFLOP_PER_FRAME = 1050.10
@@ -123,6 +128,22 @@ def cpu_frame_seconds(weights, n_frames=1, threads=None):
     return (time.time() - t0) / n_frames
 
 
+def make_config(world, B, adain, groups, scaling, global_batch):
+    """The `config` object of the JSON line -- identical for the GPU arm and the --impl reference arm."""
+    cfg = {"workload": WORKLOAD if not adain else WORKLOAD.replace("wct_tf semantics", "AdaIN (configs[4])"),
+           "frames_per_gpu_per_step": B, "global_batch": global_batch, "parallelism": "frame-sharded dp%d" % world,
+           "style": "one distinct style per frame, re-encoded every step (no caching)",
+           "l2": "two input sets alternate; per-step activation working set (>5 GB) >> 126 MB L2",
+           "precision": "fp32-class: split-fp16 pairs (22-23 bits, power-of-two scaled weights) x3 products on tcgen05, "
+                        "fp32 accumulate (TMEM chunks of 4 k-iterations summed in registers)",
+           "streams": "%d sub-batch group(s) per step, each a (content, style) stream pair" % groups}
+    if scaling == "strong":
+        cfg["workload"] = ("configs[2]: batch of %d 512x512 frames, ONE shared 512x512 style, 5 levels, alpha=0.8, wct_tf "
+                           "semantics, contiguous shards of B/G frames per GPU (parallel.stylize_sharded)" % global_batch)
+        cfg["style"] = "one shared style, re-encoded on every GPU every step"
+    return cfg
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port) on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -131,12 +152,14 @@ def run_reference(args):
     import torch
     from wct_tf_b200.weights import make_synthetic_weights
     from oracle import nets
-    cores = min(os.cpu_count() or 1, 32)     # torch-CPU convs of this size get slower beyond ~32 threads
-    torch.set_num_threads(cores)
+    host_cores = os.cpu_count() or 1
+    threads = min(host_cores, 32)            # torch-CPU convs of this size get slower beyond ~32 threads
+    torch.set_num_threads(threads)
     weights = make_synthetic_weights(42)
     c, s = frames(1, 1000), frames(1, 7)
     budget = 240.0
     t_used, times = 0.0, []
+    dt = 0.0
     for i in range(args.warmup + args.steps):
         t0 = time.time()
         nets.pipeline(c[0], s[0], weights, TARGETS, alpha=ALPHA, semantics=SEMANTICS, dtype=np.float32)
@@ -147,25 +170,30 @@ def run_reference(args):
         # bounded: stop early (>=1 timed step) rather than run past a few minutes
         if times and t_used + dt > budget:
             break
-        if not times and i + 1 >= args.warmup:
-            pass
     if not times:
         times = [dt]
     ms = 1000.0 * float(np.mean(times))
     value = 1000.0 / ms
+    world = max(1, args.gpus)
+    gb = args.global_batch if args.scaling == "strong" else world * args.batch
     line = {
         "impl": "reference", "metric": "512x512 5-level WCT stylised frames/sec", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "5-level relu5_1->relu1_1, 512x512 content, 512x512 style, alpha=0.8, wct_tf semantics, "
-                               "1 frame per step", "steps_requested": args.steps},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d timed full frame(s); TensorFlow/Keras not installable offline -> oracle port "
-                                   "(torch-CPU convs + NumPy/LAPACK wct_tf)" % len(times)},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": make_config(world, args.batch if args.scaling == "weak" else gb // world, args.adain, max(1, args.groups),
+                              args.scaling, gb),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": host_cores, "threads": threads, "kind": "port",
+                         "sample": "%d timed step(s) of ONE full frame each (a bounded sample of the workload: per-frame "
+                                   "work is identical, the CPU arm does not batch); TensorFlow/Keras not installable "
+                                   "offline -> oracle port (torch-CPU convs + NumPy/LAPACK wct_tf)" % len(times)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def level_of_key(key):
+    return key.split(":", 1)[0] if ":" in key else None
 
 
 def main():
@@ -177,16 +205,24 @@ def main():
     ap.add_argument("--impl", type=str, default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--adain", action="store_true", help="config 5: AdaIN instead of WCT")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --batch frames per GPU, one style per frame (configs[1]); strong: configs[2], --global-batch "
+                         "frames with ONE shared style sharded over the GPUs through parallel.stylize_sharded")
+    ap.add_argument("--global-batch", type=int, default=64)
     ap.add_argument("--oversub", type=int, default=0, help="tuning: conv CTAs per SM (0 = library default)")
     ap.add_argument("--no-overlap", action="store_true", help="tuning: run the style side on the main stream")
     ap.add_argument("--groups", type=int, default=2, help="sub-batches per step run as independent stream pairs")
     ap.add_argument("--no-prio", action="store_true", help="tuning: all streams at the same priority")
+    ap.add_argument("--no-fuse-upsample", action="store_true", help="tuning: separate upsample2 kernels + 9-tap convs")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel profiling steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
+    from wct_tf_b200 import _capi, parallel
+    from wct_tf_b200.engine import Engine
     from wct_tf_b200.weights import make_synthetic_weights
     from wct_tf_b200.wct import WCT
 
@@ -199,9 +235,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch
+    strong = args.scaling == "strong"
+    GB = args.global_batch if strong else world * args.batch
+    lo, hi = parallel.shard_range(GB, world, rank) if strong else (rank * args.batch, (rank + 1) * args.batch)
+    B = hi - lo                                          # frames this rank processes per step
     weights = make_synthetic_weights(42)
     wct = WCT(relu_targets=TARGETS, device="cuda:%d" % local, weights=weights, semantics=SEMANTICS)
+    if args.no_fuse_upsample:
+        wct.engine = Engine(weights, TARGETS, device="cuda:%d" % local, semantics=SEMANTICS, fuse_upsample=False)
     eng = wct.engine
     if args.oversub:
         eng.lib.wctb200_debug_set_conv_oversub(args.oversub)
@@ -210,11 +251,16 @@ def main():
     eng.groups = max(1, args.groups)
     eng.group_priorities = not args.no_prio
 
-    # distinct frames per rank (frame-sharded batch); two input sets rotated between steps
+    # two input sets rotated between steps.  weak: distinct frames AND styles per rank; strong: the global batch is the same
+    # on every rank (frame i -> rank floor(i*G/B), parallel.shard_range), one shared style.
     sets = []
     for j in range(2):
-        c = frames(B, 1000 + 17 * rank + 1000 * j)
-        s = frames(B, 7 + 31 * rank + 1000 * j)
+        if strong:
+            c = frames(GB, 1000 + 1000 * j)[lo:hi]
+            s = frames(1, 7 + 1000 * j)
+        else:
+            c = frames(B, 1000 + 17 * rank + 1000 * j)
+            s = frames(B, 7 + 31 * rank + 1000 * j)
         sets.append((c, s))
     dev_sets = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in sets]
     pin_sets = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in sets]
@@ -259,90 +305,164 @@ def main():
         sampler.start()
     ms_total, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     eng.check_device()
 
-    # ---- roofline of the dominant kernel: per-call CUDA events on the launching stream, 2 profiled steps
-    # (style/content stream overlap is switched off for these two steps so that an event-bracketed
-    #  duration is the kernel's own time, not its time while sharing SMs with the Jacobi kernels)
-    eng.profile = {}
-    eng.groups = 1
-    eng.overlap_style = False
-    for i in range(2):
-        step_resident(i)
-    torch.cuda.synchronize(dev)
-    eng.overlap_style = not args.no_overlap
-    eng.groups = max(1, args.groups)
-    prof = {}
-    for key, rec in eng.profile.items():
-        ms = sum(a.elapsed_time(b) for a, b in rec["events"])
-        prof[key] = dict(ms=ms / 2, flops=rec["flops"] / 2, bytes=rec["bytes"] / 2, calls=len(rec["events"]) // 2)
-    eng.profile = None
     pk = peaks()
-    conv = {k: v for k, v in prof.items() if k.startswith("conv3x3_tc")}
-    conv_ms = sum(v["ms"] for v in conv.values())
-    conv_fl = sum(v["flops"] for v in conv.values())
-    step_prof_ms = sum(v["ms"] for v in prof.values())
-    achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf"],
-                # dram__bytes_read+write of ONE launch from profiles/r01_ncu_full_conv_tc2.txt (the 512->512 @64x64 layer at
-                # batch 2: 18.9 MB of weights + 8.9 MB of activations read once, the output stays in L2) -- `achieved` above
-                # is the average over all 65 conv launches of a step, so `traffic_of` names the launch the bytes belong to
-                "traffic": 27385344 + 44288,
-                "traffic_of": "conv_tc2_kernel<128,fused> 512->512 @64x64, batch 2 (ncu --set full); algorithmic operand bytes of that launch: 27.3 MB",
-                "kernel": "conv_tc_kernel (tcgen05 kind::f16, split-fp16 x3: 3 MMAs per algorithmic MAC -> ceiling 1/3 of the bf16 peak)",
-                "peak_source": pk["source"] + " of measured",
-                "share_of_step": conv_ms / step_prof_ms if step_prof_ms else None,
-                "launches_per_step": sum(v["calls"] for v in conv.values())}
-    breakdown = {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]}
-    hbm = {}
-    for k, v in prof.items():
-        if (k.startswith("wct_") or k in ("upsample2", "maxpool2", "conv_tail", "conv_head")) and v["ms"] > 0:
-            hbm[k] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+    roofline, breakdown, hbm, by_level, cov_hbm = None, None, None, None, None
+    if not args.no_roofline:
+        # ---- roofline of the dominant kernel: per-call CUDA events on the launching stream.  Stream overlap is switched
+        # off for these steps so that an event-bracketed duration is the kernel's own time, not its time while sharing
+        # SMs with the Jacobi clusters of another stream.  The new configuration gets its own warm-up (new workspace
+        # keys, scratch growth) before anything is recorded.
+        PROF_WARM, PROF_STEPS = 2, 5
+        eng.groups = 1
+        eng.overlap_style = False
+        for i in range(PROF_WARM):
+            step_resident(i)
+        torch.cuda.synchronize(dev)
+        eng.profile = {}
+        for i in range(PROF_STEPS):
+            step_resident(i)
+        torch.cuda.synchronize(dev)
+        prof = {}
+        for key, rec in eng.profile.items():
+            ms = sum(a.elapsed_time(b) for a, b in rec["events"])
+            prof[key] = dict(ms=ms / PROF_STEPS, flops=rec["flops"] / PROF_STEPS, bytes=rec["bytes"] / PROF_STEPS,
+                             calls=len(rec["events"]) // PROF_STEPS)
+        eng.profile = None
+        eng.overlap_style = not args.no_overlap
+        eng.groups = max(1, args.groups)
+
+        def base(k):
+            return k.split(":", 1)[1] if ":" in k else k
+        conv = {k: v for k, v in prof.items() if base(k).startswith("conv3x3_")}
+        conv_ms = sum(v["ms"] for v in conv.values())
+        conv_fl = sum(v["flops"] for v in conv.values())
+        step_prof_ms = sum(v["ms"] for v in prof.values())
+        achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        traffic, traffic_of = None, ("not captured for this build: needs one `ncu --set full` launch of conv_tc2_kernel at the "
+                                     "bench batch (profiles/r02_conv_traffic.json)")
+        tp = os.path.join(ROOT, "profiles", "r02_conv_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_of = tj.get("dram_bytes_per_launch"), tj.get("of")
+        roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
+                    "frac": achieved_tf / pk["tf"], "traffic": traffic, "traffic_of": traffic_of,
+                    "kernel": "conv_tc2_kernel (tcgen05 kind::f16, split-fp16 x3: 3 MMAs per algorithmic MAC -> ceiling 1/3 of the "
+                              "bf16 peak); flops counted = EXECUTED 2*taps*Cin*Cout per output pixel (taps = 4 in the UP2 convs)",
+                    "tensor_pipe_frac": 3.0 * achieved_tf / pk["tf"],
+                    "peak_source": pk["source"] + " of measured",
+                    "share_of_step": conv_ms / step_prof_ms if step_prof_ms else None,
+                    "launches_per_step": sum(v["calls"] for v in conv.values()),
+                    "timed": "%d profiled steps after %d warm-up steps in the profiling configuration" % (PROF_STEPS, PROF_WARM)}
+        # per-level conv tensor-pipe fraction (north_star): all conv launches of a level's encoder + decoder
+        by_level = {}
+        for k, v in conv.items():
+            lv = level_of_key(k) or "?"
+            d = by_level.setdefault(lv, dict(ms=0.0, flops=0.0))
+            d["ms"] += v["ms"]
+            d["flops"] += v["flops"]
+        for lv, d in by_level.items():
+            tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+            by_level[lv] = {"conv_ms": round(d["ms"], 3), "tflops": round(tf, 1), "tensor_pipe_frac": round(3.0 * tf / pk["tf"], 3)}
+        merged = {}
+        for k, v in prof.items():
+            m = merged.setdefault(base(k), dict(ms=0.0, bytes=0.0))
+            m["ms"] += v["ms"]
+            m["bytes"] += v["bytes"]
+        breakdown = {k: round(v["ms"], 3) for k, v in sorted(merged.items(), key=lambda kv: -kv[1]["ms"])[:16]}
+        hbm = {}
+        for k, v in merged.items():
+            if (k.startswith("wct_") or k in ("upsample2", "maxpool2", "conv_tail", "conv_head")) and v["ms"] > 0:
+                hbm[k] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+
+        # ---- covariance-only HBM rate (north_star): means + C x HW . HW x C covariance of one level's feature batch
+        # through wctb200_covariance (no eigensolver in the bracket); bytes = the compulsory 4*C*HW per frame
+        cov_hbm = {}
+        nb = min(B, 16)
+        for C, hw in ((64, 512), (128, 256), (256, 128), (512, 64)):
+            feat = torch.rand((nb, hw, hw, C), dtype=torch.float32, device=dev)
+            act = eng.act_from_f32(feat)
+            mean = torch.empty((nb, C), dtype=torch.float32, device=dev)
+            cov = torch.empty((nb, C, C), dtype=torch.float32, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+
+            def run():
+                _capi.check(eng.lib.wctb200_covariance(act.ptr, nb, hw, hw, C, 1e-8, mean.data_ptr(), cov.data_ptr(), st))
+            for _ in range(3):
+                run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                run()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / 5
+            gbs = 4.0 * C * hw * hw * nb / (ms * 1e-3) / 1e9
+            cov_hbm["C%d@%d" % (C, hw)] = {"ms": round(ms, 3), "gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 3),
+                                           "flops_tf": round(2.0 * C * C * hw * hw * nb / (ms * 1e-3) / 1e12, 1)}
+            del feat, act
+        eng.check_device()
 
     gather_ms = None
+    sharded_ms = None
     if world > 1:
         out = step_resident(0)
-        bufs = [torch.empty_like(out) for _ in range(world)]
-        torch.cuda.synchronize(dev)
-        t0 = time.time()
-        dist.all_gather(bufs, out)          # NCCL over NVLink, off the hot path
-        torch.cuda.synchronize(dev)
-        gather_ms = 1000 * (time.time() - t0)
+        bufs = [torch.empty_like(out) for _ in range(world)] if not strong else None
+        if strong:
+            def sharded_step(i):
+                c_all, s_one = sharded_inputs[i % 2]
+                return parallel.stylize_sharded(lambda cc, ss: eng.to_u8(eng.stylize(cc, ss, alpha=ALPHA, adain=args.adain)),
+                                                c_all, s_one)
+            sharded_inputs = [(torch.from_numpy(frames(GB, 1000 + 1000 * j)).to(dev), torch.from_numpy(frames(1, 7 + 1000 * j)).to(dev))
+                              for j in range(2)]
+            sharded_ms, _ = timed(sharded_step, max(3, args.steps // 2), 3)     # sharded compute + NCCL gather, event timed, max over ranks
+            sharded_ms /= max(3, args.steps // 2)
+        else:
+            for _ in range(3):
+                dist.all_gather(bufs, out)          # warm NCCL (lazy channel setup)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                dist.all_gather(bufs, out)          # NCCL over NVLink, off the hot path
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gather_ms = float(t.item())
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only (the other ranks would just wait)
-            cores = min(os.cpu_count() or 1, 32)
-            sec = cpu_frame_seconds(weights, 1, cores)
-            cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+            host_cores = os.cpu_count() or 1
+            threads = min(host_cores, 32)
+            sec = cpu_frame_seconds(weights, 1, threads)
+            cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": host_cores, "threads": threads, "kind": "port",
                    "sample": "1 full 512x512 5-level frame on the host (oracle port: torch-CPU convs + NumPy/LAPACK wct_tf; "
                              "TensorFlow not installable offline)"}
-        total_frames = world * B * args.steps
+        total_frames = GB * args.steps
         value = total_frames / (ms_total * 1e-3)
         e2e = total_frames / (ms_e2e * 1e-3)
         line = {
             "metric": "512x512 5-level WCT stylised frames/sec", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 5-level relu5_1->relu1_1, 512x512 content, 512x512 style per frame, "
-                                   "alpha=0.8, %s" % ("AdaIN" if args.adain else "wct_tf semantics"),
-                       "frames_per_gpu_per_step": B, "global_batch": world * B, "parallelism": "frame-sharded dp%d" % world,
-                       "style": "one distinct style per frame, re-encoded every step (no caching)",
-                       "l2": "two input sets alternate; per-step activation working set (>5 GB) >> 126 MB L2",
-                       "precision": "fp32 semantics: split-fp16 x3 on tcgen05, fp32 accumulate",
-                       "streams": "%d sub-batch group(s) per step, each a (content, style) stream pair" % eng.groups},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": make_config(world, B, args.adain, eng.groups, args.scaling, GB),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(2 * B * SIZE * SIZE * 3), "d2h_bytes_per_step": int(B * SIZE * SIZE * 3)},
+                    "h2d_bytes_per_step": int((B + (1 if strong else B)) * SIZE * SIZE * 3), "d2h_bytes_per_step": int(B * SIZE * SIZE * 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "algorithmic_tflops_whole_step": value * GFLOP_PER_FRAME / 1e3 if not args.adain else None,
+            "algorithmic_tflops_whole_step": value * GFLOP_PER_FRAME / 1e3 if not (args.adain or strong) else None,
+            "conv_by_level": by_level,
+            "covariance_hbm": cov_hbm,
             "kernel_ms_per_step": breakdown,
             "hbm_gbs_by_stage": hbm,
             "gather_ms": gather_ms,
+            "sharded_step_with_gather_ms": sharded_ms,
         }
         print(json.dumps(line))
     if world > 1:

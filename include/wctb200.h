@@ -19,7 +19,8 @@
  * Activation format "SPF16" (split-pair fp16, reflect-padded NHWC):
  *   one allocation of `wctb200_act_bytes(N,H,W,C)` bytes holding two fp16 planes
  *   [plane 0 = hi | plane 1 = lo], each [N][H+2][W+2][C]; the fp32 value of an
- *   element is hi+lo (22 significant bits).  The 1-pixel halo already holds the
+ *   element is hi+lo: 22-23 significant bits for |x| >= 0.125, an absolute error <= 3e-8 below that (lo is an fp16
+ *   subnormal there), |x| saturates at 65000 (fp16 range).  The 1-pixel halo already holds the
  *   REFLECT padding of ops.py:12-15 (mirror without edge repeat), written by the
  *   producer, so a 3x3 'valid' conv over the padded plane equals Conv2DReflect
  *   (ops.py:17-19).  C must be a multiple of 8; H,W >= 2.
@@ -51,6 +52,8 @@ extern "C" {
 /* conv / transform flags */
 #define WCTB200_RELU     1   /* ReLU epilogue                     (vgg_normalised.py:40, model.py:291) */
 #define WCTB200_CLIP01   2   /* clip to [0,1] (tail conv only)    (model.py:17,86) */
+#define WCTB200_HALO_EDGE 4  /* conv3x3: write an EDGE-replicated halo instead of the reflect halo -- for an output
+                                that is consumed by wctb200_conv3x3_up2 only (UpSampling2D follows, model.py:293) */
 
 WCTB200_API int         wctb200_abi_version(void);
 WCTB200_API const char* wctb200_last_error(void);
@@ -74,10 +77,16 @@ WCTB200_API int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t*
 /* ---- encoder / decoder layers ---------------------------------------------- */
 /* Weight preparation (one-time, device side):
  * w_hwio fp32 [3][3][Cin][Cout] (Keras kernel layout, vgg_normalised.py:33 /
- * model.py:291) -> split-fp16 GEMM operand [2 planes][Cout][9*Cin], k = tap*Cin + cin.
+ * model.py:291) -> split-fp16 GEMM operand [2 planes][Cout][9*Cin], k = tap*Cin + cin, stored scaled by a per-layer
+ * power of two (max|w| -> [512,1024); the factor sits in a trailer of the buffer and is undone in the conv epilogue)
+ * so that the lo plane of small weights does not fall into the fp16 subnormals.
  * `taps` is 9 (3x3) or 1 (a [Cin][Cout] matrix). */
 WCTB200_API size_t wctb200_conv_weight_bytes(int taps, int Cin, int Cout);
 WCTB200_API int wctb200_prep_conv_weights(const float* w_hwio, int taps, int Cin, int Cout, void* w_split, void* stream);
+/* Weights of `UpSampling2D() -> Conv2DReflect` (model.py:291-293) as ONE conv over the low-resolution input: four
+ * 2x2-tap kernels (one per output parity) whose taps are sums of the 3x3 taps that land on the same low-resolution
+ * pixel; [4 parities][2 planes][Cout][4*Cin].  Buffer size: wctb200_conv_weight_bytes(16, Cin, Cout). */
+WCTB200_API int wctb200_prep_conv_weights_up2(const float* w_hwio, int Cin, int Cout, void* w_up2, void* stream);
 
 /* Conv2DReflect 3x3 (+bias, optional ReLU) on tensor cores (tcgen05, split-fp16 x3):
  * replaces `Lambda(pad_reflect) -> Conv2D(valid)` of vgg_normalised.py:28-40 and
@@ -85,6 +94,12 @@ WCTB200_API int wctb200_prep_conv_weights(const float* w_hwio, int taps, int Cin
 WCTB200_API int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin,
                     const void* w_split, const float* bias, int Cout, int flags,
                     void* act_out, void* stream);
+/* UpSampling2D (nearest x2, model.py:293) followed by Conv2DReflect 3x3 (+bias, optional ReLU), fused: act_in is the
+ * LOW-resolution SPF16 [N,H,W,Cin] whose halo is EDGE-replicated (its producer ran with WCTB200_HALO_EDGE), act_out is
+ * SPF16 [N,2H,2W,Cout] with the usual reflect halo.  4/9 of the MACs of the unfused pair and no upsampled tensor. */
+WCTB200_API int wctb200_conv3x3_up2(const void* act_in, int N, int H, int W, int Cin,
+                        const void* w_up2, const float* bias, int Cout, int flags,
+                        void* act_out, void* stream);
 /* Same contract on CUDA cores in plain fp32 (validation kernel, fp32 weights [3][3][Cin][Cout]). */
 WCTB200_API int wctb200_conv3x3_ref(const void* act_in, int N, int H, int W, int Cin,
                         const float* w_hwio, const float* bias, int Cout, int flags,
@@ -160,32 +175,6 @@ WCTB200_API int wctb200_covariance(const void* act, int N, int H, int W, int C, 
  * a: [count][C][C] symmetric (overwritten: column i becomes sigma_i * u_i),
  * sigma: [count][C] = |lambda_i|, sweeps: [count] (may be NULL). */
 WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream);
-
-/* Tuning hook, NOT part of the stable ABI: force the conv output-channel tile
- * (64/128/256; 0 = built-in heuristic).  Used by bench/profiling scripts. */
-WCTB200_API int wctb200_debug_set_conv_bn(int bn);
-/* 1 = one tile per CTA with all-TMEM accumulation, 2 = persistent CTAs with chunked register
- * accumulation with the Cin <= 64 layers on v4 (default), 3 = 2 + on-chip tap reuse through row-shifted
- * descriptors and cluster-multicast weights (experiment), 4 = v4 everywhere (8x16 tiles, three kx-shifted
- * patches, aligned ky reuse), 5 = v2 everywhere.  Returns the implementation now selected. */
-WCTB200_API int wctb200_debug_set_conv_impl(int impl);
-/* impl 2: CTAs per SM in the persistent grid (default 4; 1 = exactly one CTA per SM). */
-WCTB200_API int wctb200_debug_set_conv_oversub(int k);
-/* covariance: impl 1 = fp32 FFMA, 2 = tcgen05 on a centred split-fp16 copy (default);
- * lbo/sbo: MN-major descriptor strides in bytes (probe; negative keeps the current value). */
-WCTB200_API int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes);
-/* conv v2: fuse the a_hi*b_hi and a_hi*b_lo products into one N = 2*tile MMA: -1 auto (default), 0 never, 1 always. */
-WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
-/* conv v4 (aligned tap reuse): cluster 1|2 (weight multicast), largest Cin the default dispatch sends to v4; <0 keeps. */
-WCTB200_API int wctb200_debug_set_conv4(int cluster, int cin_max);
-/* conv v4 timeline probe: device buffer of 1024 int64 receiving clock64 samples of CTA 0 (NULL = off). */
-WCTB200_API int wctb200_debug_conv4_trace(void* dev_buf_1024_i64);
-/* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = per-size default. */
-WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
-/* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4). */
-WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
-/* impl 3 knobs: cluster size (1|2) and whether UMMA descriptors carry the base offset. */
-WCTB200_API int wctb200_debug_set_conv3(int cluster, int bo_mode);
 
 #ifdef __cplusplus
 }

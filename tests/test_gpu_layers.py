@@ -1,7 +1,5 @@
 """GPU parity: encoder/decoder layers through the C-ABI vs the CPU oracle.
 Tolerances are on fp32-class arithmetic: 2e-5 * (1 + |ref|)."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -104,9 +102,9 @@ CONV_CASES = [
     (1, 8, 130, 64, 64, True),         # 2-D tiles (4 x 30), ragged right edge
     (2, 9, 128, 128, 128, True),       # 2-D tiles, ragged bottom edge, batch
     (1, 37, 260, 64, 64, False),
-    (1, 13, 40, 64, 64, True),         # v4 tiles (8 x 16), ragged in both directions (edge tiles shift inwards)
-    (3, 16, 48, 64, 128, True),        # v4, odd number of M tiles per cluster pair, two cout tiles at BN=64
-    (1, 24, 16, 192, 64, True),        # v4, three 64-channel slices
+    (1, 13, 40, 64, 64, True),
+    (3, 16, 48, 64, 128, True),        # two cout tiles at BN=64
+    (1, 24, 16, 192, 64, True),        # three 64-channel slices
 ]
 
 
@@ -133,14 +131,22 @@ def test_conv3x3_ref_kernel(case):
     assert_close(got, ref, name="conv_ref_%d_%d" % (cin, cout))
 
 
-# 6 = v2 on CTA pairs (tcgen05 cta_group::2); WCTB_TEST_CONV_IMPLS narrows the list while developing a kernel
-CONV_IMPLS = [int(v) for v in os.environ.get("WCTB_TEST_CONV_IMPLS", "6,4,41,42,3,2,50,51,1").split(",")]
+def weight_repr(k):
+    """The value the library stores for fp32 weights k: split-fp16 pair of k * 2^S, S such that max|k| * 2^S is in
+    [512, 1024) (csrc/layers.cu: k_prep_weights), divided by 2^S again."""
+    k = np.asarray(k, dtype=np.float32)
+    amax = float(np.abs(k).max())
+    if amax <= 0:
+        return k.astype(np.float64)
+    _, e = np.frexp(np.float32(amax))
+    sc = 2.0 ** int(np.clip(10 - int(e), -14, 40))
+    return U.split_repr(k * np.float32(sc)) / sc
 
 
-@pytest.mark.parametrize("impl", CONV_IMPLS)     # 41 = impl 4 without the CTA-pair weight multicast; 50/51 = v2 with the fused [b_hi|b_lo] MMA off/on
+@pytest.mark.parametrize("fuse", [-1, 0, 1])     # fused [b_hi|b_lo] MMA: auto / off / forced on
 @pytest.mark.parametrize("bn", [0, 64, 256])
 @pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_conv3x3_tensor_core(case, bn, impl):
+def test_conv3x3_tensor_core(case, bn, fuse):
     n, h, w, cin, cout, relu = case
     if bn and cout % bn:
         pytest.skip("tile does not divide Cout")
@@ -150,32 +156,79 @@ def test_conv3x3_tensor_core(case, bn, impl):
     d_k, d_b = U.dev(k), U.dev(b)
     _capi.check(U.lib().wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsplit.data_ptr(), U.stream()))
     out = U.act_alloc(n, h, w, cout)
-    if impl in (3, 4, 41, 42, 6) and bn == 256:
-        pytest.skip("impl 3/4 tiles are 64 or 128 wide")
     U.lib().wctb200_debug_set_conv_bn(bn)
-    U.lib().wctb200_debug_set_conv4(1 if impl == 41 else 2, -1)
-    U.lib().wctb200_debug_set_conv_fuse({50: 0, 51: 1, 42: 1}.get(impl, -1))      # 42 = impl 4 with the fused MMA forced on
-    impl = {41: 4, 42: 4, 50: 5, 51: 5}.get(impl, impl)
-    U.lib().wctb200_debug_set_conv_impl(impl)
+    U.lib().wctb200_debug_set_conv_fuse(fuse)
     try:
         _capi.check(U.lib().wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsplit.data_ptr(), d_b.data_ptr(), cout,
                                             _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
         U.check_device()
     finally:
         U.lib().wctb200_debug_set_conv_bn(0)
-        U.lib().wctb200_debug_set_conv_impl(2)
-        U.lib().wctb200_debug_set_conv4(2, -1)
         U.lib().wctb200_debug_set_conv_fuse(-1)
     got = U.act_to_numpy(out, n, h, w, cout)
-    ref = conv_ref64(U.split_repr(x), U.split_repr(k), b, relu)
-    # impl 1 accumulates the whole K loop in TMEM: the tensor core adds into its fp32 accumulator
-    # with truncation, so the error grows ~linearly with the number of K=16 steps (measured
-    # -1.2e-5 relative bias at K=4608).  impl 2 (default) sums short chunks in registers (RN).
-    tol = 2e-5 * max(1.0, 9 * cin / 1152.0) if impl == 1 else 1e-5
+    ref = conv_ref64(U.split_repr(x), weight_repr(k), b, relu)
     err = np.abs(got - ref) / (1.0 + np.abs(ref))
-    print("impl %d K=%d: max rel err %.2e, mean signed err %.2e" % (impl, 9 * cin, err.max(), (got - ref).mean()))
-    assert_close(got, ref, tol=tol, name="conv_tc%d_%d_%d_bn%d" % (impl, cin, cout, bn), x=x, k=k, b=b)
+    print("K=%d: max rel err %.2e, mean signed err %.2e" % (9 * cin, err.max(), (got - ref).mean()))
+    assert_close(got, ref, tol=1e-5, name="conv_tc_%d_%d_bn%d" % (cin, cout, bn), x=x, k=k, b=b)
+    # the stored weights carry >= 21 bits: the conv sits within 4e-6 of the conv with the EXACT fp32 weights
+    assert_close(got, conv_ref64(U.split_repr(x), k, b, relu), tol=4e-6, name="conv_tc_exactw_%d_%d" % (cin, cout))
     padded = U.act_raw_padded(out, n, h, w, cout)
+    assert np.isfinite(padded).all(), "halo cells left unwritten"
+    assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
+
+
+UP2_CASES = [
+    # N, H, W (low resolution), Cin, Cout, relu
+    (1, 4, 4, 64, 64, True),
+    (2, 5, 7, 128, 64, True),
+    (1, 8, 6, 128, 128, False),
+    (1, 2, 2, 64, 64, True),           # smallest map: every pixel touches the border
+    (2, 9, 17, 256, 128, True),
+    (1, 16, 16, 512, 512, True),
+    (1, 33, 20, 64, 64, True),
+]
+
+
+@pytest.mark.parametrize("bn", [0, 64])
+@pytest.mark.parametrize("case", UP2_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_up2_equals_upsample_then_conv(case, bn):
+    """wctb200_conv3x3_up2 (UpSampling2D folded into the conv: 4 parity kernels with pre-summed taps over the
+    low-resolution input with an EDGE halo) == UpSampling2D -> Conv2DReflect of model.py:291-293 in float64."""
+    n, h, w, cin, cout, relu = case
+    if bn and cout % bn:
+        pytest.skip("tile does not divide Cout")
+    rng = np.random.default_rng(11)
+    # the low-resolution input is itself produced by a conv launched with HALO_EDGE (as the engine does)
+    x0, k0, b0 = _conv_inputs((n, h, w, cin, cin, True), 12)
+    k = (rng.normal(0, 1, (3, 3, cin, cout)) * np.sqrt(2.0 / (9 * cin))).astype(np.float32)
+    b = rng.normal(0, 0.3, cout).astype(np.float32)
+    lib = U.lib()
+    x0in = U.act_from_numpy(x0)
+    w0 = torch.empty(lib.wctb200_conv_weight_bytes(9, cin, cin), dtype=torch.uint8, device="cuda")
+    d_k0, d_b0, d_k, d_b = U.dev(k0), U.dev(b0), U.dev(k), U.dev(b)
+    _capi.check(lib.wctb200_prep_conv_weights(d_k0.data_ptr(), 9, cin, cin, w0.data_ptr(), U.stream()))
+    low = U.act_alloc(n, h, w, cin)
+    _capi.check(lib.wctb200_conv3x3(x0in.data_ptr(), n, h, w, cin, w0.data_ptr(), d_b0.data_ptr(), cin,
+                                    _capi.RELU | _capi.HALO_EDGE, low.data_ptr(), U.stream()))
+    lowp = U.act_raw_padded(low, n, h, w, cin)
+    assert np.isfinite(lowp).all()
+    assert np.array_equal(lowp, np.pad(lowp[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="edge")), "HALO_EDGE"
+    wup = torch.empty(lib.wctb200_conv_weight_bytes(16, cin, cout), dtype=torch.uint8, device="cuda")
+    _capi.check(lib.wctb200_prep_conv_weights_up2(d_k.data_ptr(), cin, cout, wup.data_ptr(), U.stream()))
+    out = U.act_alloc(n, 2 * h, 2 * w, cout)
+    lib.wctb200_debug_set_conv_bn(bn)
+    try:
+        _capi.check(lib.wctb200_conv3x3_up2(low.data_ptr(), n, h, w, cin, wup.data_ptr(), d_b.data_ptr(), cout,
+                                            _capi.RELU if relu else 0, out.data_ptr(), U.stream()))
+        U.check_device()
+    finally:
+        lib.wctb200_debug_set_conv_bn(0)
+    got = U.act_to_numpy(out, n, 2 * h, 2 * w, cout)
+    xl = lowp[:, 1:-1, 1:-1]                                            # what the device holds (float64 of hi+lo)
+    up = np.repeat(np.repeat(xl, 2, axis=1), 2, axis=2)                 # UpSampling2D, model.py:293
+    ref = conv_ref64(up, k, b, relu)
+    assert_close(got, ref, tol=1e-5, name="conv_up2_%d_%d" % (cin, cout))
+    padded = U.act_raw_padded(out, n, 2 * h, 2 * w, cout)
     assert np.isfinite(padded).all(), "halo cells left unwritten"
     assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
 

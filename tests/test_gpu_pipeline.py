@@ -24,7 +24,9 @@ ALL = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
 # The chained levels of a RANDOM-weight pipeline amplify rounding noise ~1e3x (DESIGN.md "Parity"):
 # the reference's own fp32 run sits ~4e-3 from its fp64 run.  The free-running bound is therefore
 # stated as a multiple of that measured noise floor; the <=1e-3 claim is the teacher-forced one.
-FREE_RUN_NOISE_FACTOR = 8     # measured on B200: 4.1x (1.6e-2 vs the oracle's own 3.9e-3)
+# Round 1 measured 4.1x; the cause was the weights' lo plane falling into the fp16 subnormals (tests/noise_split_cpu.py,
+# profiles/r02_noise_split.txt); with the per-layer power-of-two weight scale the engine sits at the fp32 noise level.
+FREE_RUN_NOISE_FACTOR = 2
 
 
 @pytest.fixture(scope="module")
@@ -37,19 +39,15 @@ def _imgs(n, s, seed):
     return rng.integers(0, 256, (n, s, s, 3), dtype=np.uint8)
 
 
-@pytest.mark.parametrize("sem,adain,targets,size", [
-    ("np", False, ALL, 128),
-    ("tf", False, ALL, 128),
-    ("tf", True, ALL, 96),
-    ("np", False, ["relu3_1", "relu1_1", "relu2_1"], 72),     # any order / subset (README.md:46)
-    ("tf", False, ["relu1_1"], 64),
-])
-def test_teacher_forced_levels(weights, sem, adain, targets, size):
+def _teacher_forced(weights, sem, adain, targets, csize, ssize, alpha=0.8, seeds=(100, 7)):
+    """Every level of the engine's own run is recomputed by the fp64 oracle FROM THE ENGINE'S INPUT TO THAT LEVEL.
+    Returns the worst max-abs error over encoder output / transformed feature / level output (all levels)."""
     eng = Engine(weights, targets, semantics=sem)
-    content = _imgs(1, size, 100)
-    style = _imgs(1, size + 16, 7)
+    rng_c, rng_s = np.random.default_rng(seeds[0]), np.random.default_rng(seeds[1])
+    content = rng_c.integers(0, 256, (1, csize[0], csize[1], 3), dtype=np.uint8)
+    style = rng_s.integers(0, 256, (1, ssize[0], ssize[1], 3), dtype=np.uint8)
     cap = {}
-    out = eng.stylize(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), alpha=0.8, adain=adain,
+    out = eng.stylize(torch.from_numpy(content).cuda(), torch.from_numpy(style).cuda(), alpha=alpha, adain=adain,
                       want_info=True, capture=cap)
     eng.check_device()
     sfe = nets.encode(nets.preprocess(style).astype(np.float64), weights, targets, np.float64)
@@ -64,23 +62,76 @@ def test_teacher_forced_levels(weights, sem, adain, targets, size):
         got_cf = eng.act_to_f32(cap["content_feat"][i]).cpu().numpy()
         e_enc = np.abs(got_cf - cf).max()
         if adain:
-            f = ref_ops.adain(cf, sfe[relu], 0.8)
+            f = ref_ops.adain(cf, sfe[relu], alpha)
         else:
             fn = ref_ops.wct_tf if sem == "tf" else ref_ops.wct_np
-            f, info = fn(cf, sfe[relu], 0.8, return_info=True)
+            f, info = fn(cf, sfe[relu], alpha, return_info=True)
             k = eng.last_info[i].cpu().numpy()
             assert ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"]), "ill-posed vector"
-            assert (k[0], k[1]) == (info["k_c"], info["k_s"])
+            assert (k[0], k[1]) == (info["k_c"], info["k_s"])         # relu-target / rank bookkeeping: bit-exact
         got_f = eng.act_to_f32(cap["transformed"][i]).cpu().numpy()
         e_wct = np.abs(got_f - f).max()
         y = nets.decode(np.asarray(f, dtype=np.float64), weights, relu, np.float64)
         if i < len(targets) - 1:
             y = np.clip(y, 0, 1)
         e_out = np.abs(cap["level_output"][i].cpu().numpy() - y).max()
-        print("%s: encoder %.2e  transform %.2e  level output %.2e" % (relu, e_enc, e_wct, e_out))
+        print("%s %dx%d: encoder %.2e  transform %.2e  level output %.2e" % (relu, csize[0], csize[1], e_enc, e_wct, e_out))
         worst = max(worst, e_enc, e_wct, e_out)
-    assert worst <= 1e-3
     assert out.shape[0] == 1 and out.shape[3] == 3
+    return worst
+
+
+@pytest.mark.parametrize("sem,adain,targets,size", [
+    ("np", False, ALL, 128),
+    ("tf", False, ALL, 128),
+    ("tf", True, ALL, 96),
+    ("np", False, ["relu3_1", "relu1_1", "relu2_1"], 72),     # any order / subset (README.md:46)
+    ("tf", False, ["relu1_1"], 64),
+])
+def test_teacher_forced_levels(weights, sem, adain, targets, size):
+    assert _teacher_forced(weights, sem, adain, targets, (size, size), (size + 16, size + 16)) <= 1e-3
+
+
+# ---- the configurations BASELINE.json names, at their full sizes -------------------------------------------
+@pytest.mark.parametrize("sem", ["tf", "np"])
+def test_config2_512x512_five_levels_teacher_forced(weights, sem):
+    """configs[1]: 5-level relu5_1->relu1_1, 512x512 content, 512x512 style, alpha 0.8 (HW up to 262 144 in the
+    split-K covariance): every level <= 1e-3 from the fp64 oracle, k_c/k_s equal, spectral gap asserted."""
+    assert _teacher_forced(weights, sem, False, ALL, (512, 512), (512, 512), seeds=(1000, 7)) <= 1e-3
+
+
+def test_config4_1024_content_512_style_teacher_forced(weights):
+    """configs[3]: 1024x1024 content / 512x512 style (HW = 1 048 576 at relu1_1, 262 144 at relu2_1)."""
+    assert _teacher_forced(weights, "tf", False, ALL, (1024, 1024), (512, 512), seeds=(1000, 7)) <= 1e-3
+
+
+def test_config5_adain_512_teacher_forced(weights):
+    """configs[4]: --adain, 512x512, 5 levels."""
+    assert _teacher_forced(weights, "tf", True, ALL, (512, 512), (512, 512), seeds=(1000, 7)) <= 1e-3
+
+
+def test_config3_two_gpu_shards_equal_one_gpu_bit_for_bit(weights, tmp_path):
+    """configs[2] / SURVEY 4: a batch sharded over 2 GPUs (torchrun, parallel.stylize_sharded, NCCL gather) gives the SAME
+    uint8 frames as one GPU running the whole batch: per-frame arithmetic does not depend on the batch a frame is in
+    (deterministic split-K partials, no atomics) nor on the GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import subprocess
+    import sys
+    out = tmp_path / "sharded.npy"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "sharded_worker.py"), str(out), "6", "256"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
+    sharded = np.load(str(out))
+    from tests.sharded_worker import make_batch
+    c, s = make_batch(6, 256)
+    wct = WCT(checkpoints=None, relu_targets=ALL, vgg_path=None, weights=weights)
+    single = wct.predict_batch(c, s, alpha=0.8)
+    assert sharded.shape == single.shape and np.array_equal(sharded, single)
+    one_by_one = np.concatenate([wct.predict_batch(c[i:i + 1], s, alpha=0.8) for i in range(c.shape[0])])
+    assert np.array_equal(one_by_one, single)
 
 
 def test_free_running_five_levels_vs_oracle(weights):

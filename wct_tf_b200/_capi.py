@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libwctb200.so")
 
 RELU = 1
 CLIP01 = 2
+HALO_EDGE = 4
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -26,7 +27,9 @@ SIGNATURES = {
     "wctb200_image_f32_to_u8": (_i, [_vp, _sz, _vp, _vp]),
     "wctb200_conv_weight_bytes": (_sz, [_i, _i, _i]),
     "wctb200_prep_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "wctb200_prep_conv_weights_up2": (_i, [_vp, _i, _i, _vp, _vp]),
     "wctb200_conv3x3": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "wctb200_conv3x3_up2": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "wctb200_conv3x3_ref": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "wctb200_conv_head": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "wctb200_conv_tail": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
@@ -40,18 +43,17 @@ SIGNATURES = {
     "wctb200_adain_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "wctb200_covariance": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
-    "wctb200_debug_set_conv_bn": (_i, [_i]),
-    "wctb200_debug_set_conv_impl": (_i, [_i]),
-    "wctb200_debug_set_conv3": (_i, [_i, _i]),
-    "wctb200_debug_set_conv_oversub": (_i, [_i]),
-    "wctb200_debug_set_cov": (_i, [_i, _i, _i]),
-    "wctb200_debug_set_jacobi": (_i, [_i, _i]),
-    "wctb200_debug_set_jacobi_tolq": (_i, [_f]),
-    "wctb200_debug_set_conv4": (_i, [_i, _i]),
-    "wctb200_debug_set_conv_fuse": (_i, [_i]),
     "wctb200_style_swap_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "wctb200_style_swap_level": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
-    "wctb200_debug_conv4_trace": (_i, [_vp]),
+}
+
+# tuning / probe hooks (wct_tf_b200/csrc/wctb200_debug.h): NOT part of the ABI, bound for tools/ and tests/ only
+DEBUG_SIGNATURES = {
+    "wctb200_debug_set_conv_bn": (_i, [_i]),
+    "wctb200_debug_set_conv_oversub": (_i, [_i]),
+    "wctb200_debug_set_conv_fuse": (_i, [_i]),
+    "wctb200_debug_set_jacobi": (_i, [_i, _i]),
+    "wctb200_debug_set_jacobi_tolq": (_i, [_f]),
 }
 
 _lib = None
@@ -70,10 +72,11 @@ def load():
         raise WctB200Error("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
-        fn.restype = res
-        fn.argtypes = args
+    for table in (SIGNATURES, DEBUG_SIGNATURES):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
     if lib.wctb200_abi_version() != 1:
         raise WctB200Error("libwctb200 ABI version mismatch")
     _lib = lib

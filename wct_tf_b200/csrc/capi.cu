@@ -7,6 +7,7 @@
 #include <tuple>
 
 #include "common.cuh"
+#include "wctb200_debug.h"
 
 namespace wctb {
 
@@ -64,12 +65,26 @@ unsigned int* device_error_word() {
     return ptr[dev];
 }
 
+int device_sm_count() {
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 // launchers (layers.cu / wct.cu)
 int launch_u8_to_f32(const uint8_t*, size_t, float*, cudaStream_t);
 int launch_f32_to_u8(const float*, size_t, uint8_t*, cudaStream_t);
 int launch_act_from_f32(const float*, ActGeom, __half*, cudaStream_t);
 int launch_act_to_f32(const __half*, ActGeom, float*, cudaStream_t);
 int launch_prep_weights(const float*, int, int, int, __half*, cudaStream_t);
+int launch_prep_weights_up2(const float*, int, int, __half*, cudaStream_t);
 size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws);
 int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, float alpha, float eps_cov,
                             float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -91,21 +106,11 @@ int launch_covariance(const __half*, int, int, int, int, float, float*, float*, 
 int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
 int launch_eig_post(const float*, const float*, float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
 extern int g_conv_bn_override;
-extern int g_conv_impl;
-extern int g_conv3_cluster;
-extern int g_conv3_bo_mode;
 extern int g_conv_oversub;
-extern int g_cov_impl;
-extern int g_cov_lbo;
 extern int g_conv_fuse;
-extern int g_conv4_cluster;
-extern int g_conv4_cin_max;
-extern int g_conv4_dbg;
-extern long long* g_conv4_trace;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
 extern int g_jacobi_stagger;
-extern int g_cov_sbo;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
 static bool geom_ok(int N, int H, int W, int C) {
@@ -172,17 +177,32 @@ int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t* out, void* 
 
 size_t wctb200_conv_weight_bytes(int taps, int Cin, int Cout) {
     if (taps < 1 || Cin < 1 || Cout < 1) return 0;
-    return (size_t)2 * taps * Cin * Cout * sizeof(__half);
+    return (size_t)2 * taps * Cin * Cout * sizeof(__half) + 256;     // + trailer: the power-of-two scale (layers.cu)
 }
 int wctb200_prep_conv_weights(const float* w_hwio, int taps, int Cin, int Cout, void* w_split, void* stream) {
     WCTB_REQUIRE(w_hwio && w_split && (taps == 9 || taps == 1) && Cin >= 1 && Cout >= 1, "prep_conv_weights: bad arguments");
     return launch_prep_weights(w_hwio, taps, Cin, Cout, HP(w_split), ST(stream));
 }
 
+int wctb200_prep_conv_weights_up2(const float* w_hwio, int Cin, int Cout, void* w_up2, void* stream) {
+    WCTB_REQUIRE(w_hwio && w_up2 && Cin >= 1 && Cout >= 1, "prep_conv_weights_up2: bad arguments");
+    return launch_prep_weights_up2(w_hwio, Cin, Cout, HP(w_up2), ST(stream));
+}
+
 int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin, const void* w_split, const float* bias, int Cout,
                     int flags, void* act_out, void* stream) {
     WCTB_REQUIRE(act_in && w_split && act_out, "conv3x3: null pointer");
-    return launch_conv3x3_tc(HCP(act_in), N, H, W, Cin, HCP(w_split), 9, 1, bias, Cout, flags, HP(act_out), ST(stream));
+    WCTB_REQUIRE((flags & ~(WCTB200_RELU | WCTB200_HALO_EDGE)) == 0, "conv3x3: unknown flag bits 0x%x", flags);
+    return launch_conv_tc(CONV_3X3, HCP(act_in), N, H, W, Cin, HCP(w_split), 1, weight_scale_ptr(HCP(w_split), 9, Cin, Cout),
+                          bias, Cout, flags, HP(act_out), ST(stream));
+}
+int wctb200_conv3x3_up2(const void* act_in, int N, int H, int W, int Cin, const void* w_up2, const float* bias, int Cout,
+                        int flags, void* act_out, void* stream) {
+    WCTB_REQUIRE(act_in && w_up2 && act_out, "conv3x3_up2: null pointer");
+    WCTB_REQUIRE((flags & ~WCTB200_RELU) == 0, "conv3x3_up2: unknown flag bits 0x%x", flags);
+    WCTB_REQUIRE(geom_ok(N, 2 * H, 2 * W, Cout), "conv3x3_up2: output geometry too large");
+    return launch_conv_tc(CONV_UP2, HCP(act_in), N, H, W, Cin, HCP(w_up2), 1, weight_scale_ptr(HCP(w_up2), 16, Cin, Cout),
+                          bias, Cout, flags, HP(act_out), ST(stream));
 }
 int wctb200_conv3x3_ref(const void* act_in, int N, int H, int W, int Cin, const float* w_hwio, const float* bias, int Cout,
                         int flags, void* act_out, void* stream) {
@@ -269,25 +289,6 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     return rc;
 }
 
-// tuning hook (not part of the stable ABI): force the conv N tile (0 = heuristic)
-int wctb200_debug_set_conv_bn(int bn) {
-    g_conv_bn_override = bn;
-    return 0;
-}
-int wctb200_debug_set_conv_impl(int impl) {
-    if (impl >= 1 && impl <= 6) g_conv_impl = impl;
-    return g_conv_impl;
-}
-int wctb200_debug_set_conv_oversub(int k) {
-    g_conv_oversub = k < 1 ? 1 : (k > 16 ? 16 : k);
-    return g_conv_oversub;
-}
-int wctb200_debug_set_cov(int impl, int lbo_bytes, int sbo_bytes) {
-    if (impl == 1 || impl == 2) g_cov_impl = impl;
-    if (lbo_bytes >= 0) g_cov_lbo = lbo_bytes;
-    if (sbo_bytes >= 0) g_cov_sbo = sbo_bytes;
-    return g_cov_impl;
-}
 size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws) {
     if (!geom_ok(1, Hc, Wc, C) || !geom_ok(1, Hs, Ws, C) || Hc < 3 || Wc < 3 || Hs < 3 || Ws < 3) return 0;
     return style_swap_workspace_bytes(C, Hc, Wc, Hs, Ws);
@@ -299,30 +300,24 @@ int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* st
     return launch_style_swap_level(HCP(content), Hc, Wc, HCP(style), Hs, Ws, C, alpha, eps_cov, thresh, HP(out), k_out, ws, ws_bytes,
                                    ST(stream));
 }
+// tuning hooks (wctb200_debug.h; not part of the stable ABI)
+int wctb200_debug_set_conv_bn(int bn) {
+    g_conv_bn_override = bn;
+    return 0;
+}
+int wctb200_debug_set_conv_oversub(int k) {
+    g_conv_oversub = k < 1 ? 1 : (k > 16 ? 16 : k);
+    return g_conv_oversub;
+}
 int wctb200_debug_set_conv_fuse(int mode) {
     g_conv_fuse = mode < 0 ? -1 : (mode ? 1 : 0);
     return g_conv_fuse;
-}
-int wctb200_debug_set_conv4(int cluster, int cin_max) {
-    if (cluster == 1 || cluster == 2) g_conv4_cluster = cluster;
-    if (cin_max >= 0 && cin_max < 100000) g_conv4_cin_max = cin_max;
-    if (cin_max >= 100000) g_conv4_dbg = cin_max - 100000;      // timing probes (conv_tc4.cu: Conv4Params::dbg)
-    return g_conv4_cluster;
-}
-int wctb200_debug_conv4_trace(void* dev_buf_1024_i64) {
-    g_conv4_trace = static_cast<long long*>(dev_buf_1024_i64);
-    return 0;
 }
 int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
 int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
     if (lg_groups <= 4) g_jacobi_lg = lg_groups < 0 ? -1 : lg_groups;              // negative: back to the per-size default
     g_jacobi_stagger = stagger_cycles < 0 ? -1 : stagger_cycles;
     return g_jacobi_lg;
-}
-int wctb200_debug_set_conv3(int cluster, int bo_mode) {
-    g_conv3_cluster = cluster == 1 ? 1 : 2;
-    g_conv3_bo_mode = bo_mode ? 1 : 0;
-    return 0;
 }
 
 }  // extern "C"

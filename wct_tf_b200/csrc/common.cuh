@@ -7,6 +7,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/wctb200.h"
 
 namespace wctb {
@@ -41,17 +43,35 @@ unsigned int* device_error_word();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-DEVICE one-time kernel attribute: cudaFuncSetAttribute applies to the current device only, so the
+// "already done" state is one bit per device ordinal (a process may drive several GPUs: WCT(device='/gpu:1')
+// after '/gpu:0').  The kernel argument may contain commas: wrap it in parentheses.
+#define WCTB_ENSURE_SMEM(kernel, bytes)                                                                  \
+    do {                                                                                                 \
+        static std::atomic<unsigned long long> _done{0ull};                                              \
+        int _dev = 0;                                                                                    \
+        WCTB_CUDA(cudaGetDevice(&_dev));                                                                 \
+        const unsigned long long _bit = 1ull << (_dev & 63);                                             \
+        if (!(_done.load(std::memory_order_acquire) & _bit)) {                                           \
+            WCTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done.fetch_or(_bit, std::memory_order_release);                                             \
+        }                                                                                                \
+    } while (0)
+// SM count of the CURRENT device (cached per device ordinal)
+int device_sm_count();
+
 // ---------------------------------------------------------------------------
 // SPF16 geometry
 // ---------------------------------------------------------------------------
 struct ActGeom {
     int N, H, W, C;
     int Hp, Wp;          // H+2, W+2
+    int edge;            // halo written by a producer: 0 = REFLECT (ops.py:12-15), 1 = EDGE-replicated (input of an UP2 conv)
     long long P;         // N*Hp*Wp padded positions
     long long plane;     // P*C elements per plane
     __host__ __device__ ActGeom() {}
     __host__ __device__ ActGeom(int n, int h, int w, int c)
-        : N(n), H(h), W(w), C(c), Hp(h + 2), Wp(w + 2) {
+        : N(n), H(h), W(w), C(c), Hp(h + 2), Wp(w + 2), edge(0) {
         P = (long long)N * Hp * Wp;
         plane = P * C;
     }
@@ -106,8 +126,10 @@ __device__ __forceinline__ int halo_rows(int y, int H, int* rows) {
 // (fully unrolled with predicates: no local-memory index arrays)
 __device__ __forceinline__ void store8_with_halo(__half* __restrict__ act, const ActGeom& g, int n, int y, int x,
                                                  int c0, const Half8& hi, const Half8& lo) {
-    const int r1 = (y == 1) ? 0 : -1, r2 = (y == g.H - 2) ? g.H + 1 : -1;
-    const int q1 = (x == 1) ? 0 : -1, q2 = (x == g.W - 2) ? g.W + 1 : -1;
+    // reflect: padded row 0 mirrors interior row 1, row H+1 mirrors row H-2; edge: they replicate rows 0 and H-1
+    const int m = g.edge ? 0 : 1;
+    const int r1 = (y == m) ? 0 : -1, r2 = (y == g.H - 1 - m) ? g.H + 1 : -1;
+    const int q1 = (x == m) ? 0 : -1, q2 = (x == g.W - 1 - m) ? g.W + 1 : -1;
     const long long img = (long long)n * g.Hp;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -139,10 +161,11 @@ __device__ __forceinline__ void load8(const __half* __restrict__ act, const ActG
 // 64-channel convs were bound by L2 write requests).  Instead every warp transposes
 // 64 channels at a time through an 8 KB shared-memory staging buffer (XOR-swizzled, conflict
 // free) so that 8 consecutive lanes write one position's 128 contiguous bytes per plane.
-//   stg: this warp's private 8 KB buffer; sbias: bias of acc[0..NACC); cbase: channel of acc[0]
+//   stg: this warp's private 8 KB buffer; value = acc*oscale + sbias (oscale undoes the power-of-two weight scale);
+//   sbias: bias of acc[0..NACC); cbase: channel of acc[0]
 // ---------------------------------------------------------------------------
 template <int NACC>
-__device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const float* __restrict__ sbias, bool relu,
+__device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const float oscale, const float* __restrict__ sbias, bool relu,
                                                 uint8_t* __restrict__ stg, int lane, bool valid, int n, int y, int x,
                                                 __half* __restrict__ out, const ActGeom& go, int cbase) {
     const int packed = valid ? ((y << 16) | x) : -1;
@@ -153,7 +176,7 @@ __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const 
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float t = acc[h * 64 + q * 8 + j] + sbias[h * 64 + q * 8 + j];
+                const float t = fmaf(acc[h * 64 + q * 8 + j], oscale, sbias[h * 64 + q * 8 + j]);
                 v[j] = relu ? fmaxf(t, 0.f) : t;
             }
             Half8 hi, lo;
@@ -329,7 +352,12 @@ int scratch_alloc(void** ptr, size_t bytes, cudaStream_t st, int slot);
 // ---------------------------------------------------------------------------
 // kernel launchers implemented in the .cu files (host API used by capi.cu)
 // ---------------------------------------------------------------------------
-int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __half* w_split, int taps, int nsets,
-                      const float* bias, int Cout, int flags, __half* out, cudaStream_t st);
+enum ConvMode { CONV_3X3 = 0, CONV_APPLY = 1, CONV_UP2 = 2 };
+int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, const __half* w_split, int nsets,
+                   const float* wscale, const float* bias, int Cout, int flags, __half* out, cudaStream_t st);
+// trailer of a prepared weight buffer: [0] = 1/scale (float), see wctb200_prep_conv_weights
+static inline const float* weight_scale_ptr(const __half* w_split, int taps_total, int Cin, int Cout) {
+    return reinterpret_cast<const float*>(w_split + (size_t)2 * taps_total * Cin * Cout);
+}
 
 }  // namespace wctb

@@ -1,10 +1,12 @@
-// Conv2DReflect 3x3 (and 1x1 "apply") as an implicit GEMM on the 5th-gen tensor cores.
+// Conv2DReflect 3x3, the 1x1 "apply" of the feature transform, and UpSampling2D+Conv2DReflect as ONE conv,
+// all as an implicit GEMM on the 5th-gen tensor cores.
 //
 //   reference: Lambda(pad_reflect) -> Conv2D(valid) (+ReLU)   ops.py:12-19,
-//              vgg_normalised.py:28-40, model.py:291; and the whitening/colouring
-//              apply  M * fc  of ops.py:73,77 when taps == 1.
+//              vgg_normalised.py:28-40, model.py:291; the whitening/colouring
+//              apply  M * fc  of ops.py:73,77 (mode APPLY); and
+//              UpSampling2D() -> Conv2DReflect of model.py:291-293 (mode UP2).
 //
-// Formulation.  Activations are SPF16: two fp16 planes (hi, lo) of the reflect-padded
+// Formulation.  Activations are SPF16: two fp16 planes (hi, lo) of the padded
 // NHWC tensor, viewed as a 2-D matrix [P = N*(H+2)*(W+2) padded positions][C].  For an
 // output position p (padded coordinates) and filter tap (ky,kx) the input row is simply
 // p + (ky-1)*(W+2) + (kx-1): each tap of a 128-position output tile is ONE dense
@@ -13,200 +15,48 @@
 //
 //   D[128 pos][BN cout] = sum_{tap, cin-slice}  A_tap[128][64] * W_tap[BN][64]^T
 //
-// Precision.  fp32 accuracy from fp16 tensor-core inputs: x = x_hi + x_lo (22 bits),
-//   x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi     (3 x tcgen05.mma kind::f16, fp32 accumulate in TMEM)
-// the dropped lo*lo term is 2^-22 relative.
+// UP2 (nearest x2 upsampling folded into the conv that follows it).  Output pixel (2i+a, 2j+b) of
+// conv3x3(reflect_pad(upsample2(L))) only ever reads the 2x2 low-resolution neighbourhood
+// rows {i-1+a, i+a} x cols {j-1+b, j+b} of L, because two of the three filter rows (columns) land on the same
+// low-resolution row (column): a = 0 -> {w[-1]} on row i-1 and {w[0]+w[1]} on row i; a = 1 -> {w[-1]+w[0]} on
+// row i and {w[1]} on row i+1.  So each of the 4 output parities is a 2x2-tap conv over L with pre-summed
+// weights (wctb200_prep_conv_weights_up2): 16 instead of 36 tap-products per low-resolution pixel (4/9 of the
+// MACs), and the 4x larger upsampled tensor is never written or read.  At the border the reflect padding of the
+// UPSAMPLED image mirrors onto the same low-resolution pixel (u[-1] = u[1] = L[0]), i.e. L needs an EDGE-replicated
+// halo: its producer is launched with WCTB200_HALO_EDGE.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Precision.  fp32-class accuracy from fp16 tensor-core inputs: x = x_hi + x_lo,
+//   x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi     (3 x tcgen05.mma kind::f16, fp32 accumulate in TMEM)
+// the dropped lo*lo term is 2^-22 relative.  Weights are stored SCALED by a per-layer power of two
+// (max|w| -> [512,1024), undone exactly in the epilogue): He-initialised / trained conv weights are ~1e-2, so the
+// unscaled lo plane (~5e-6) fell into the fp16 subnormals and kept only ~16 bits of the weight -- measured as
+// 8x the reference's own fp32 noise on the free-running 5-level image (profiles/r02_noise_split.txt).
+//
+// Structure (persistent CTAs, 192 threads):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor 3-D, 128B swizzle, mbarrier complete_tx)
 //   warp 1   : MMA issuer     (one elected thread, tcgen05.mma / tcgen05.commit), owns TMEM alloc
-//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> +bias, ReLU -> split fp16 -> 16-byte stores
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> *scale +bias, ReLU -> split fp16 -> 16-byte stores
 //                              of the interior pixel AND the halo cells that mirror it)
 #include "common.cuh"
 
 namespace wctb {
 
 extern int g_conv_bn_override;
-extern int g_conv_impl;
 
 struct ConvParams {
-    int N, H, W, Cin, Cout, Hp, Wp;
+    int N, H, W, Cin, Cout, Hp, Wp;   // INPUT geometry (UP2: the low-resolution tensor)
     long long P;
-    int taps;             // 9 or 1
-    int per_image;        // tiles never straddle images; weight/bias set = image index if nsets > 1
+    int mode;             // ConvMode
+    int taps;             // 9 (3x3), 1 (apply), 4 (up2: per output parity)
+    int per_image;        // tiles never straddle images; weight/bias set = image index (APPLY with nsets > 1)
     int nsets;
     int tiles_per_image;
     int flags;
     const float* bias;    // [nsets][Cout] or nullptr
-    __half* out;          // SPF16, Cout channels, same N,H,W
+    const float* wscale;  // device scalar: 1 / (power-of-two scale the weights were stored with), or nullptr (= 1)
+    __half* out;          // SPF16, Cout channels; UP2: [N, 2H, 2W, Cout]
     unsigned int* err;
 };
-
-template <int BN>
-struct ConvCfg {
-    static constexpr int BM = 128;
-    static constexpr int BK = 64;
-    static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile
-    static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = BN == 64 ? 4 : (BN == 128 ? 3 : 2);
-    static constexpr int AUX_BYTES = 256 + BN * 4;       // barriers, tmem slot, abort flag, bias tile
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // + alignment slack
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvParams p) {
-    using Cfg = ConvCfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(aux);
-    uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* tmem_full = empty + Cfg::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-    float* sbias = reinterpret_cast<float*>(aux + 256);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    {   // an earlier CTA already timed out: leave (uniformly) instead of waiting 2 s per CTA
-        __shared__ unsigned int s_prev_err;
-        if (threadIdx.x == 0) s_prev_err = *reinterpret_cast<volatile unsigned int*>(p.err);
-        __syncthreads();
-        if (s_prev_err != 0u) return;
-    }
-
-    const long long HpWp = (long long)p.Hp * p.Wp;
-    long long p0, p_end;
-    int set = 0;
-    if (p.per_image) {
-        const int img = blockIdx.x / p.tiles_per_image;
-        const int t = blockIdx.x - img * p.tiles_per_image;
-        p0 = img * HpWp + (long long)t * Cfg::BM;
-        p_end = (img + 1) * HpWp;
-        set = p.nsets > 1 ? img : 0;
-    } else {
-        p0 = (long long)blockIdx.x * Cfg::BM;
-        p_end = p.P;
-    }
-    const int n0 = blockIdx.y * BN;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(tmem_full, 1);
-        *abort_flag = 0;
-        fence_barrier_init();
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapB);
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < BN; i += 128)
-            sbias[i] = p.bias ? p.bias[(long long)set * p.Cout + n0 + i] : 0.f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int ksl = p.Cin / Cfg::BK;
-    const int kiters = p.taps * ksl;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (it / Cfg::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1u, abort_flag, p.err, 0x100u + s);
-                const int tap = it / ksl;
-                const int ks = it - tap * ksl;
-                const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
-                const int row = (int)(p0 + off);
-                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                tma_load_3d(st, &mapA, &full[s], ks * Cfg::BK, row, 0);
-                tma_load_3d(st + Cfg::A_BYTES, &mapA, &full[s], ks * Cfg::BK, row, 1);
-                tma_load_3d(st + 2 * Cfg::A_BYTES, &mapB, &full[s], tap * p.Cin + ks * Cfg::BK, n0, set * 2);
-                tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB, &full[s], tap * p.Cin + ks * Cfg::BK, n0,
-                            set * 2 + 1);
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, BN);
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % Cfg::STAGES;
-                const uint32_t ph = (it / Cfg::STAGES) & 1;
-                mbar_wait(&full[s], ph, abort_flag, p.err, 0x200u + s);
-                tc_fence_after();
-                const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t a_hi = umma_desc_sw128(st);
-                const uint64_t a_lo = umma_desc_sw128(st + Cfg::A_BYTES);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * Cfg::A_BYTES);
-                const uint64_t b_lo = umma_desc_sw128(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
-#pragma unroll
-                for (int k = 0; k < Cfg::BK / 16; ++k) {
-                    const uint64_t ko = (uint64_t)(k * 32 >> 4);  // +32 bytes of K per UMMA_K=16 step
-                    umma_f16(tmem_base, a_hi + ko, b_lo + ko, idesc, (it | k) != 0 ? 1u : 0u);
-                    umma_f16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1u);
-                    umma_f16(tmem_base, a_hi + ko, b_hi + ko, idesc, 1u);
-                }
-                umma_commit(&empty[s]);   // frees the smem stage when these MMAs retire
-            }
-            umma_commit(tmem_full);       // accumulator complete
-        }
-        __syncwarp();
-    } else {
-        // ---- epilogue: TMEM -> regs -> bias/ReLU -> split fp16 -> global (+ reflect halo) ----
-        mbar_wait(tmem_full, 0u, abort_flag, p.err, 0x300u);
-        tc_fence_after();
-        const int g = warp & 3;                 // TMEM lanes [32g, 32g+32) belong to this warp
-        const long long pos = p0 + g * 32 + lane;
-        bool valid = pos < p_end;
-        int n = 0, y = 0, x = 0;
-        if (valid) {
-            n = (int)(pos / HpWp);
-            const int r = (int)(pos - n * HpWp);
-            const int yy = r / p.Wp;
-            const int xx = r - yy * p.Wp;
-            valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
-            y = yy - 1;
-            x = xx - 1;
-        }
-        const ActGeom go(p.N, p.H, p.W, p.Cout);
-        const bool relu = (p.flags & WCTB200_RELU) != 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
-            if (valid && !*abort_flag) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float t = __uint_as_float(r[q * 8 + j]) + sbias[c0 + q * 8 + j];
-                        v[j] = relu ? fmaxf(t, 0.f) : t;
-                    }
-                    Half8 hi, lo;
-                    split8(v, hi, lo);
-                    store8_with_halo(p.out, go, n, y, x, n0 + c0 + q * 8, hi, lo);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
-}
 
 // ===========================================================================
 // v2: persistent CTAs + chunked accumulation drained into registers
@@ -251,15 +101,24 @@ struct Conv2Cfg {
 struct TileCoord {
     long long p0, p_end;
     int n0, set;
+    int cls;              // UP2: output parity class a*2+b
 };
 
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, int n_tiles, int BN) {
     TileCoord t;
     const int nt = tile % n_tiles;
-    const int mt = tile / n_tiles;
+    int mt = tile / n_tiles;
     const long long HpWp = (long long)p.Hp * p.Wp;
     t.n0 = nt * BN;
-    if (p.per_image) {
+    t.cls = 0;
+    if (p.mode == CONV_UP2) {
+        // cout tile fastest, then the 4 parity classes: CTAs running together share one activation tile in L2
+        t.cls = mt & 3;
+        mt >>= 2;
+        t.p0 = (long long)mt * 128;
+        t.p_end = p.P;
+        t.set = t.cls;                       // weight set = parity class
+    } else if (p.per_image) {
         const int img = mt / p.tiles_per_image;
         const int r = mt - img * p.tiles_per_image;
         t.p0 = img * HpWp + (long long)r * 128;
@@ -332,7 +191,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     mbar_wait(&empty[s], ph ^ 1u, abort_flag, p.err, 0x100u + s);
                     const int tap = it / ksl;
                     const int ks = it - tap * ksl;
-                    const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
+                    int off = 0;
+                    if (p.mode == CONV_3X3) off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+                    else if (p.mode == CONV_UP2) off = ((tap >> 1) - 1 + (tc.cls >> 1)) * p.Wp + ((tap & 1) - 1 + (tc.cls & 1));
                     const int row = (int)(tc.p0 + off);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -397,8 +258,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int et = threadIdx.x - 64;                     // 0 .. 32*EPI_WARPS-1
         constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
         const long long HpWp = (long long)p.Hp * p.Wp;
-        const ActGeom go(p.N, p.H, p.W, p.Cout);
+        const bool up2 = p.mode == CONV_UP2;
+        ActGeom go(p.N, up2 ? 2 * p.H : p.H, up2 ? 2 * p.W : p.W, p.Cout);
+        go.edge = (p.flags & WCTB200_HALO_EDGE) ? 1 : 0;
         const bool relu = (p.flags & WCTB200_RELU) != 0;
+        const float wsc = p.wscale ? __ldg(p.wscale) : 1.f;
         uint32_t cg_ = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const TileCoord tc = tile_coord(p, tile, n_tiles, BN);
@@ -457,10 +321,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
                 y = yy - 1;
                 x = xx - 1;
+                if (up2) { y = 2 * y + (tc.cls >> 1); x = 2 * x + (tc.cls & 1); }
             }
             if (Cfg::STG_BYTES > 0) {
                 uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
-                store_tile_rows<Cfg::NACC>(acc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
+                store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
                                            tc.n0 + colbase);
             } else if (valid && !*abort_flag) {
 #pragma unroll
@@ -468,7 +333,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     float v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float t = acc[q * 8 + j] + sbias[colbase + q * 8 + j];
+                        const float t = fmaf(acc[q * 8 + j], wsc, sbias[colbase + q * 8 + j]);
                         v[j] = relu ? fmaxf(t, 0.f) : t;
                     }
                     Half8 hi, lo;
@@ -481,257 +346,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-}
-
-// ===========================================================================
-// v5: v2 on CTA PAIRS (tcgen05 cta_group::2).  A timeline probe of the MMA-issuing thread showed every
-// single-CTA tcgen05.mma (M=128, K=16) occupying the tensor pipe for >= 80 cycles (N=64) .. ~115 cycles (N=128):
-// 40-55 % of the nominal rate.  A pair of CTAs on the two SMs of a TPC executes ONE M=256 instruction: each CTA
-// supplies its own 128 activation rows and HALF of the weight tile (N/2 rows), accumulators stay in each CTA's own
-// TMEM.  Per CTA the weight traffic halves and the operand shared-memory reads per flop drop by a third.
-//   * both CTAs run the TMA producer (own A tile + own half of B); every load completes on the LEADER's `full`
-//     barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address mapped with mapa);
-//   * only the leader's elected thread issues tcgen05.mma.cta_group::2; stage release (`empty`) and chunk completion
-//     (`tfull`) are multicast commits to both CTAs;
-//   * both CTAs' epilogue warps drain their own TMEM and arrive on the leader's `tempty` (remote mbarrier arrive).
-// Everything else is v2 (persistent pairs, 4-k-iteration chunks summed in registers with RN adds, coalesced store).
-// ===========================================================================
-template <int BN>
-struct Conv5Cfg {
-    static constexpr int BM = 128;                              // rows per CTA (the MMA is M = 256)
-    static constexpr int BK = 64;
-    static constexpr int A_BYTES = BM * BK * 2;                 // one plane of this CTA's A tile
-    static constexpr int BH_BYTES = (BN / 2) * BK * 2;          // one plane of this CTA's HALF of the weight tile
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
-    static constexpr int STAGES = 4;
-    static constexpr int NBUF = 4;
-    static constexpr int TMEM_COLS = NBUF * BN;
-    static constexpr int CH = 4;
-    static constexpr int EPI_WARPS = 4;
-    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-    static constexpr int NACC = BN;
-    static constexpr int AUX_BYTES = 256 + BN * 4;
-    static constexpr int STG_BYTES = 4 * 8192;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + STG_BYTES + 1024;
-};
-
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion is signalled on a barrier that may live in the peer CTA of the pair
-__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* map, uint32_t bar_cluster_addr, int c0, int c1,
-                                                int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
-                 : "memory");
-}
-
-template <int BN>
-__global__ void __launch_bounds__(Conv5Cfg<BN>::THREADS, 1)
-conv_tc5_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvParams p,
-                const int total_q, const int n_tiles) {
-    using Cfg = Conv5Cfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(aux);
-    uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* tfull = empty + Cfg::STAGES;
-    uint64_t* tempty = tfull + Cfg::NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NBUF);
-    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
-    float* sbias = reinterpret_cast<float*>(aux + 256);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_rank();                     // 0 = leader (issues the MMAs)
-    // NOTE: no early exit on a previous error: both CTAs of a pair must take the same path
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) {
-            mbar_init(&full[s], 1);                            // leader's copy is the live one: 1 arrive (leader producer) + tx bytes of both CTAs
-            mbar_init(&empty[s], 1);                           // multicast commit
-        }
-        for (int b = 0; b < Cfg::NBUF; ++b) {
-            mbar_init(&tfull[b], 1);                           // multicast commit
-            mbar_init(&tempty[b], 2 * Cfg::EPI_WARPS);         // leader's copy: epilogue warps of both CTAs
-        }
-        *abort_flag = 0;
-        fence_barrier_init();
-        tma_prefetch_desc(&mapA);
-        tma_prefetch_desc(&mapB);
-    }
-    if (warp == 1) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    cluster_barrier();                                         // peer barriers initialised before any remote arrive / multicast
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int ksl = p.Cin / Cfg::BK;
-    const int kiters = p.taps * ksl;
-    const int nchunks = (kiters + Cfg::CH - 1) / Cfg::CH;
-    const int num_pairs = gridDim.x >> 1;
-    const int pid = blockIdx.x >> 1;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int q = pid; q < total_q; q += num_pairs) {
-                const int n0 = (q % n_tiles) * BN;
-                const long long p0 = (long long)(q / n_tiles) * 256 + rank * 128;
-                for (int it = 0; it < kiters; ++it) {
-                    mbar_wait(&empty[s], ph ^ 1u, abort_flag, p.err, 0x500u + s);
-                    const int tap = it / ksl;
-                    const int ks = it - tap * ksl;
-                    const int off = p.taps == 9 ? (tap / 3 - 1) * p.Wp + (tap % 3 - 1) : 0;
-                    const int row = (int)(p0 + off);
-                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                    const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0u);
-                    if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
-                    const int kc = tap * p.Cin + ks * Cfg::BK;
-                    const int nrow = n0 + (int)rank * (BN / 2);
-                    tma_load_3d_2sm(st, &mapA, lbar, ks * Cfg::BK, row, 0);
-                    tma_load_3d_2sm(st + Cfg::A_BYTES, &mapA, lbar, ks * Cfg::BK, row, 1);
-                    tma_load_3d_2sm(st + 2 * Cfg::A_BYTES, &mapB, lbar, kc, nrow, 0);
-                    tma_load_3d_2sm(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES, &mapB, lbar, kc, nrow, 1);
-                    if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(256, BN);
-            int s = 0, b = 0;
-            uint32_t ph = 0, pht = 0;
-            for (int q = pid; q < total_q; q += num_pairs) {
-                for (int c = 0; c < nchunks; ++c) {
-                    mbar_wait(&tempty[b], pht ^ 1u, abort_flag, p.err, 0x800u + b);   // both epilogues drained this buffer
-                    tc_fence_after();
-                    const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
-                    const int it_end = min(kiters, (c + 1) * Cfg::CH);
-                    for (int it = c * Cfg::CH; it < it_end; ++it) {
-                        mbar_wait(&full[s], ph, abort_flag, p.err, 0x600u + s);
-                        tc_fence_after();
-                        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                        const uint64_t a_hi = umma_desc_sw128(st);
-                        const uint64_t a_lo = umma_desc_sw128(st + Cfg::A_BYTES);
-                        const uint64_t b_hi = umma_desc_sw128(st + 2 * Cfg::A_BYTES);
-                        const uint64_t b_lo = umma_desc_sw128(st + 2 * Cfg::A_BYTES + Cfg::BH_BYTES);
-                        const bool first = (it == c * Cfg::CH);
-#pragma unroll
-                        for (int k = 0; k < Cfg::BK / 16; ++k) {
-                            const uint64_t ko = (uint64_t)(k * 32 >> 4);
-                            umma_f16_2sm(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
-                            umma_f16_2sm(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
-                            umma_f16_2sm(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
-                        }
-                        umma_commit_2sm(&empty[s]);
-                        if (++s == Cfg::STAGES) { s = 0; ph ^= 1u; }
-                    }
-                    umma_commit_2sm(&tfull[b]);
-                    if (++b == Cfg::NBUF) { b = 0; pht ^= 1u; }
-                }
-            }
-        }
-        __syncwarp();
-    } else {
-        const int e = warp - 2;
-        const int g = warp & 3;
-        const int et = threadIdx.x - 64;
-        constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
-        const long long HpWp = (long long)p.Hp * p.Wp;
-        const ActGeom go(p.N, p.H, p.W, p.Cout);
-        const bool relu = (p.flags & WCTB200_RELU) != 0;
-        int b = 0;
-        uint32_t pht = 0;
-        for (int q = pid; q < total_q; q += num_pairs) {
-            const int n0 = (q % n_tiles) * BN;
-            const long long p0 = (long long)(q / n_tiles) * 256 + rank * 128;
-            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
-            for (int i = et; i < BN; i += ETHREADS) sbias[i] = p.bias ? p.bias[n0 + i] : 0.f;
-            asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
-
-            float acc[Cfg::NACC];
-#pragma unroll
-            for (int i = 0; i < Cfg::NACC; ++i) acc[i] = 0.f;
-            for (int c = 0; c < nchunks; ++c) {
-                mbar_wait(&tfull[b], pht, abort_flag, p.err, 0x700u + b);
-                tc_fence_after();
-                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * BN);
-#pragma unroll
-                for (int c0 = 0; c0 < Cfg::NACC; c0 += 64) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tsrc + c0, r0);
-                    tmem_ld32(tsrc + c0 + 32, r1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty[b]), 0u));   // the leader's barrier counts both CTAs
-                if (++b == Cfg::NBUF) { b = 0; pht ^= 1u; }
-            }
-            const long long pos = p0 + g * 32 + lane;
-            bool valid = pos < p.P;
-            int n = 0, y = 0, x = 0;
-            if (valid) {
-                n = (int)(pos / HpWp);
-                const int r = (int)(pos - n * HpWp);
-                const int yy = r / p.Wp;
-                const int xx = r - yy * p.Wp;
-                valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
-                y = yy - 1;
-                x = xx - 1;
-            }
-            uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
-            store_tile_rows<Cfg::NACC>(acc, sbias, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go, n0);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_barrier();                                          // no CTA exits (or frees TMEM) while its peer may still signal it
-    if (warp == 1) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------
@@ -777,161 +391,75 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, 
     return 0;
 }
 
-template <int BN>
-static int launch_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, dim3 grid, cudaStream_t st) {
-    using Cfg = ConvCfg<BN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        WCTB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
-    }
-    conv_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(mA, mB, p);
-    WCTB_CHECK_LAUNCH("conv_tc_kernel");
-    return 0;
-}
-
 int g_conv_oversub = 4;
 
 template <int BN, bool FUSE_>
 static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_tiles, int n_tiles,
                       cudaStream_t st) {
     using Cfg = Conv2Cfg<BN, FUSE_>;
-    static bool attr_done = false;
-    static int sms = 0;
-    if (!attr_done) {
-        WCTB_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int dev = 0;
-        WCTB_CUDA(cudaGetDevice(&dev));
-        WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
-    }
+    WCTB_ENSURE_SMEM((conv_tc2_kernel<BN, FUSE_>), Cfg::SMEM_BYTES);
     // Over-subscribed persistent grid: with g_conv_oversub x #SMs CTAs (1 resident per SM) the
     // hardware block scheduler hands queued CTAs to whichever SMs are free, so a conv launched
     // while the Jacobi clusters of the other stream hold half the SMs still balances its tiles
     // (a grid of exactly #SMs would run as two unbalanced waves).
-    int grid = sms * (g_conv_oversub > 0 ? g_conv_oversub : 1);
+    int grid = device_sm_count() * (g_conv_oversub > 0 ? g_conv_oversub : 1);
     if (grid > total_tiles) grid = total_tiles;
     conv_tc2_kernel<BN, FUSE_><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p, total_tiles, n_tiles);
     WCTB_CHECK_LAUNCH("conv_tc2_kernel");
     return 0;
 }
 
-template <int BN>
-static int launch5_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_q, int n_tiles,
-                      cudaStream_t st) {
-    using Cfg = Conv5Cfg<BN>;
-    static bool attr_done = false;
-    static int sms = 0;
-    if (!attr_done) {
-        WCTB_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        int dev = 0;
-        WCTB_CUDA(cudaGetDevice(&dev));
-        WCTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
-    }
-    int pairs = (sms / 2) * (g_conv_oversub > 0 ? g_conv_oversub : 1);
-    if (pairs > total_q) pairs = total_q;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
-    cfg.blockDim = dim3(Cfg::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    WCTB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc5_kernel<BN>, mA, mB, p, total_q, n_tiles));
-    return 0;
-}
-
 int g_conv_fuse = -1;        // -1 auto, 0 never, 1 whenever the tile allows (wctb200_debug_set_conv_fuse)
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
-int g_conv_impl = 2;         // 1 = one tile per CTA, all-TMEM accumulation; 2 = persistent + chunked register accumulation; 3 = 2 + tap reuse + multicast (conv_tc3.cu); 4 = aligned tap reuse (conv_tc4.cu); 5 = v2 only; 6 = v2 on CTA pairs (cta_group::2)
 
-int launch_conv3x3_tc3(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
-                       int flags, __half* out, int bn_override, cudaStream_t st);
-int launch_conv3x3_tc4(const __half* in, int N, int H, int W, int Cin, const __half* w_split, const float* bias, int Cout,
-                       int flags, __half* out, int bn_override, cudaStream_t st);
-extern int g_conv4_cin_max;
-
-int launch_conv3x3_tc(const __half* in, int N, int H, int W, int Cin, const __half* w_split, int taps, int nsets,
-                      const float* bias, int Cout, int flags, __half* out, cudaStream_t st) {
-    WCTB_REQUIRE(N >= 1 && H >= 2 && W >= 2, "conv3x3: bad geometry N=%d H=%d W=%d", N, H, W);
-    WCTB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && Cin >= 64 && Cout >= 64, "conv3x3: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
-    WCTB_REQUIRE(taps == 9 || taps == 1, "conv3x3: taps must be 9 or 1");
-    WCTB_REQUIRE(nsets == 1 || nsets == N, "conv3x3: nsets must be 1 or N");
+// mode CONV_3X3  : in [N,H,W,Cin], w_split [2][Cout][9*Cin],          out [N,H,W,Cout]
+// mode CONV_APPLY: in [N,H,W,Cin], w_split [nsets][2][Cout][Cin],     out [N,H,W,Cout]   (per-image weight sets)
+// mode CONV_UP2  : in [N,H,W,Cin] (edge halo), w_split [4][2][Cout][4*Cin], out [N,2H,2W,Cout]
+int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, const __half* w_split, int nsets,
+                   const float* wscale, const float* bias, int Cout, int flags, __half* out, cudaStream_t st) {
+    WCTB_REQUIRE(N >= 1 && H >= 2 && W >= 2, "conv: bad geometry N=%d H=%d W=%d", N, H, W);
+    WCTB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && Cin >= 64 && Cout >= 64, "conv: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    WCTB_REQUIRE(mode == CONV_3X3 || mode == CONV_APPLY || mode == CONV_UP2, "conv: bad mode %d", mode);
+    WCTB_REQUIRE(nsets == 1 || (mode == CONV_APPLY && nsets == N), "conv: nsets must be 1 (or N in apply mode)");
     ActGeom gi(N, H, W, Cin);
-    WCTB_REQUIRE(gi.P < (1ll << 31) - 4096, "conv3x3: too many padded positions (%lld)", gi.P);
+    WCTB_REQUIRE(gi.P < (1ll << 31) - 4096, "conv: too many padded positions (%lld)", gi.P);
+    const int taps = mode == CONV_3X3 ? 9 : (mode == CONV_UP2 ? 4 : 1);
+    const int wsets = mode == CONV_UP2 ? 4 : nsets;
 
-    if (g_conv_impl == 3 && taps == 9 && nsets == 1) {
-        const int r = launch_conv3x3_tc3(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
-        if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v3 -> v2 below
-    }
-    // impl 4 = v4 for every shape it covers; impl 2 (default) sends only the L2-operand-bound layers (Cin <= 64) to v4
-    if ((g_conv_impl == 4 || (g_conv_impl == 2 && Cin <= g_conv4_cin_max)) && taps == 9 && nsets == 1) {
-        const int r = launch_conv3x3_tc4(in, N, H, W, Cin, w_split, bias, Cout, flags, out, g_conv_bn_override, st);
-        if (r != 0) return r < 0 ? r : 0;      // 0 = shape not covered by v4 -> v2 below
-    }
-    if (g_conv_impl == 6 && taps == 9 && nsets == 1) {   // CTA pairs (cta_group::2)
-        int BN5 = Cout % 128 == 0 ? 128 : 64;
-        if (g_conv_bn_override == 64) BN5 = 64;
-        CUtensorMap mA5, mB5;
-        int rc5 = make_map(&mA5, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
-        if (rc5) return rc5;
-        const uint64_t K5 = (uint64_t)9 * Cin;
-        rc5 = make_map(&mB5, w_split, K5, (uint64_t)Cout, 2, K5 * 2, K5 * Cout * 2, (uint32_t)(BN5 / 2));
-        if (rc5) return rc5;
-        ConvParams p5;
-        p5.N = N; p5.H = H; p5.W = W; p5.Cin = Cin; p5.Cout = Cout; p5.Hp = gi.Hp; p5.Wp = gi.Wp; p5.P = gi.P;
-        p5.taps = 9; p5.nsets = 1; p5.per_image = 0; p5.tiles_per_image = 0;
-        p5.flags = flags; p5.bias = bias; p5.out = out; p5.err = device_error_word();
-        const int n_tiles5 = Cout / BN5;
-        const int total_q = (int)cdiv(gi.P, 256) * n_tiles5;
-        return BN5 == 128 ? launch5_bn<128>(mA5, mB5, p5, total_q, n_tiles5, st) : launch5_bn<64>(mA5, mB5, p5, total_q, n_tiles5, st);
-    }
-    int BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
-    if (BN == 256) BN = 128;  // v1 default: 3-stage pipeline beats the 2-stage 256-wide tile until 2-CTA lands
+    int BN = Cout % 128 == 0 ? 128 : 64;   // 256-wide tiles leave only 2 pipeline stages: measured slower
     if (g_conv_bn_override && Cout % g_conv_bn_override == 0) BN = g_conv_bn_override;
 
     CUtensorMap mA, mB;
     int rc = make_map(&mA, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
     if (rc) return rc;
     const uint64_t K = (uint64_t)taps * Cin;
-    rc = make_map(&mB, w_split, K, (uint64_t)Cout, (uint64_t)2 * nsets, K * 2, K * Cout * 2, (uint32_t)BN);
+    rc = make_map(&mB, w_split, K, (uint64_t)Cout, (uint64_t)2 * wsets, K * 2, K * Cout * 2, (uint32_t)BN);
     if (rc) return rc;
 
     ConvParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Hp = gi.Hp; p.Wp = gi.Wp; p.P = gi.P;
+    p.mode = mode;
     p.taps = taps;
     p.nsets = nsets;
     p.per_image = nsets > 1 ? 1 : 0;
     p.tiles_per_image = cdiv((long long)gi.Hp * gi.Wp, 128);
     p.flags = flags;
     p.bias = bias;
+    p.wscale = wscale;
     p.out = out;
     p.err = device_error_word();
-    dim3 grid(p.per_image ? (unsigned)(N * p.tiles_per_image) : (unsigned)cdiv(gi.P, 128), (unsigned)(Cout / BN));
-    if (g_conv_impl >= 2) {
-        const int n_tiles = Cout / BN;
-        const int total = (int)grid.x * n_tiles;
-        switch (BN) {
-            // fused [b_hi|b_lo] MMAs (Conv2Cfg::FUSE): always at BN=64 (4 TMEM buffers stay); at BN=128 the ring shrinks to 2
-            // buffers, which only pays for long K loops (measured: Cin=128 -9 %, Cin>=256 +3..5 %)
-            case 64: return g_conv_fuse == 0 ? launch2_bn<64, false>(mA, mB, p, total, n_tiles, st)
-                                             : launch2_bn<64, true>(mA, mB, p, total, n_tiles, st);
-            case 128: return (g_conv_fuse == 1 || (g_conv_fuse < 0 && (long long)taps * Cin >= 9 * 256))
-                                 ? launch2_bn<128, true>(mA, mB, p, total, n_tiles, st)
-                                 : launch2_bn<128, false>(mA, mB, p, total, n_tiles, st);
-            default: return launch2_bn<256, false>(mA, mB, p, total, n_tiles, st);
-        }
-    }
+    const int m_tiles = p.per_image ? N * p.tiles_per_image : cdiv(gi.P, 128);
+    const int n_tiles = Cout / BN;
+    const int total = m_tiles * n_tiles * (mode == CONV_UP2 ? 4 : 1);
     switch (BN) {
-        case 64: return launch_bn<64>(mA, mB, p, grid, st);
-        case 128: return launch_bn<128>(mA, mB, p, grid, st);
-        default: return launch_bn<256>(mA, mB, p, grid, st);
+        // fused [b_hi|b_lo] MMAs (Conv2Cfg::FUSE): always at BN=64 (4 TMEM buffers stay); at BN=128 the ring shrinks to 2
+        // buffers, which only pays for long K loops (measured: Cin=128 -9 %, Cin>=256 +3..5 %)
+        case 64: return g_conv_fuse == 0 ? launch2_bn<64, false>(mA, mB, p, total, n_tiles, st)
+                                         : launch2_bn<64, true>(mA, mB, p, total, n_tiles, st);
+        case 128: return (g_conv_fuse == 1 || (g_conv_fuse < 0 && (long long)taps * Cin >= 9 * 256))
+                             ? launch2_bn<128, true>(mA, mB, p, total, n_tiles, st)
+                             : launch2_bn<128, false>(mA, mB, p, total, n_tiles, st);
+        default: return launch2_bn<256, false>(mA, mB, p, total, n_tiles, st);
     }
 }
 

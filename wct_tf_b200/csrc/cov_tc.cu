@@ -229,8 +229,6 @@ typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int g_cov_lbo = 8192;      // probe knobs (wctb200_debug_set_cov)
-int g_cov_sbo = 1024;
 
 int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
     static PFN_encodeTiledC enc = nullptr;
@@ -254,15 +252,15 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
     const int tiles_img = p.tiles_x * p.tiles_y;
     // aim for ~2 CTAs per SM in total (each CTA pays ~5 us of TMEM/barrier set-up and final atomics),
     // at least 8 tiles (512 pixels) per CTA
-    int ksplit = (148 * 2 + npairs * g.N - 1) / (npairs * g.N);
+    int ksplit = (device_sm_count() * 2 + npairs * g.N - 1) / (npairs * g.N);
     if (ksplit < 1) ksplit = 1;
     int tps = (tiles_img + ksplit - 1) / ksplit;
     if (tps < 8) tps = 8;
     ksplit = (tiles_img + tps - 1) / tps;
     p.ksplit = ksplit;
     p.tiles_per_split = tps;
-    p.lbo_bytes = g_cov_lbo;
-    p.sbo_bytes = g_cov_sbo;
+    p.lbo_bytes = 8192;      // MN-major descriptor strides, probed on B200 (profiles/r01_cov_mn_major_probe.txt)
+    p.sbo_bytes = 1024;
     p.cov = cov;
     p.err = device_error_word();
     // tensor map over the interior pixels only (see header comment)
@@ -280,11 +278,7 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
         set_error("cov_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return WCTB200_ECUDA;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        WCTB_CUDA(cudaFuncSetAttribute(cov_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CovCfg::SMEM_BYTES));
-        attr_done = true;
-    }
+    WCTB_ENSURE_SMEM(cov_tc_kernel, CovCfg::SMEM_BYTES);
     dim3 grid((unsigned)(npairs * ksplit), (unsigned)g.N);
     cov_tc_kernel<<<grid, CovCfg::THREADS, CovCfg::SMEM_BYTES, st>>>(mX, p);
     WCTB_CHECK_LAUNCH("cov_tc_kernel");

@@ -64,19 +64,74 @@ __global__ void k_act_to_f32(const __half* __restrict__ act, ActGeom g, float* _
 }
 
 // ---------------------------------------------------------------------------
-// weights: fp32 [taps][Cin][Cout] -> split fp16 [2][Cout][taps*Cin]
+// weights: fp32 [taps][Cin][Cout] -> split fp16 [2][Cout][taps*Cin], stored scaled by a power of two
+//   trailer (after the planes): float[0] = 1/scale (undone in the conv epilogue), uint[1] = max|w| bits (scratch).
+//   Why: conv weights are ~1e-2 (He-normal std sqrt(2/(9 Cin)), trained VGG alike): hi = fp16(w) keeps 11 bits, but
+//   lo = w - hi ~ 5e-6 is an fp16 SUBNORMAL (spacing 6e-8), so hi+lo kept only ~16 bits of the weight.  With max|w|
+//   scaled into [512,1024) every lo that matters is a normal fp16 number and hi+lo carries 22 bits.
 // ---------------------------------------------------------------------------
-__global__ void k_prep_weights(const float* __restrict__ w, int taps, int Cin, int Cout, __half* __restrict__ ws) {
+__global__ void k_absmax(const float* __restrict__ w, long long n, unsigned int* __restrict__ out_bits) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = fabsf(w[i]);
+        if (v < 3.0e38f) m = fmaxf(m, v);          // ignores inf / NaN
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));    // non-negative floats order like their bits
+}
+__device__ __forceinline__ float weight_scale(unsigned int absmax_bits) {
+    const float amax = __uint_as_float(absmax_bits);
+    if (!(amax > 0.f)) return 1.f;
+    int e;
+    frexpf(amax, &e);                               // amax = m * 2^e, m in [0.5, 1)
+    int S = 10 - e;                                 // amax * 2^S in [512, 1024)
+    S = S < -14 ? -14 : (S > 40 ? 40 : S);
+    return exp2f((float)S);                         // exact power of two
+}
+__global__ void k_prep_weights(const float* __restrict__ w, int taps, int Cin, int Cout, __half* __restrict__ ws,
+                               float* __restrict__ trailer) {
     const long long K = (long long)taps * Cin;
     const long long total = K * Cout;
+    const float sc = weight_scale(reinterpret_cast<const unsigned int*>(trailer)[1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = 1.f / sc;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i / K);
         const long long k = i - (long long)co * K;      // k = tap*Cin + cin
-        const float v = w[k * Cout + co];
+        const float v = w[k * Cout + co] * sc;
         __half hi, lo;
         split_f32(v, hi, lo);
         ws[i] = hi;
         ws[total + i] = lo;
+    }
+}
+// UpSampling2D -> Conv2DReflect as four 2x2-tap convs over the low-resolution input (conv_tc.cu, mode UP2):
+// [class a*2+b][plane][Cout][4*Cin], k = (ty*2+tx)*Cin + cin; the weight of class (a,b), tap (ty,tx) is the sum of the
+// 3x3 taps that land on low-resolution row i-1+a+ty / column j-1+b+tx:  a=0: ty=0 <- {ky=0}, ty=1 <- {1,2};
+// a=1: ty=0 <- {0,1}, ty=1 <- {2} (same for columns).  Sums in fp64, rounded once.
+__global__ void k_prep_weights_up2(const float* __restrict__ w, int Cin, int Cout, __half* __restrict__ ws,
+                                   float* __restrict__ trailer) {
+    const long long K = 4ll * Cin;
+    const long long per_plane = K * Cout;
+    const long long total = 4 * per_plane;
+    const float sc = weight_scale(reinterpret_cast<const unsigned int*>(trailer)[1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) trailer[0] = 1.f / sc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cls = (int)(i / per_plane);
+        const long long r = i - cls * per_plane;
+        const int co = (int)(r / K);
+        const int k = (int)(r - (long long)co * K);
+        const int tap = k / Cin, cin = k - tap * Cin;
+        const int a = cls >> 1, b = cls & 1, ty = tap >> 1, tx = tap & 1;
+        const int ky0 = a == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = a == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+        const int kx0 = b == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = b == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+        double v = 0.0;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += (double)w[((long long)(ky * 3 + kx) * Cin + cin) * Cout + co];
+        __half hi, lo;
+        split_f32((float)(v * (double)sc), hi, lo);
+        ws[(long long)(cls * 2) * per_plane + r] = hi;
+        ws[(long long)(cls * 2 + 1) * per_plane + r] = lo;
     }
 }
 
@@ -466,7 +521,7 @@ __global__ void k_upsample2(const __half* __restrict__ in, ActGeom gi, __half* _
 // ---------------------------------------------------------------------------
 static inline int grid_for(long long total, int block) {
     long long b = (total + block - 1) / block;
-    const long long cap = 148ll * 16;
+    const long long cap = (long long)device_sm_count() * 16;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -491,8 +546,23 @@ int launch_act_to_f32(const __half* act, ActGeom g, float* out, cudaStream_t st)
     return 0;
 }
 int launch_prep_weights(const float* w, int taps, int Cin, int Cout, __half* ws, cudaStream_t st) {
-    k_prep_weights<<<grid_for((long long)taps * Cin * Cout, 256), 256, 0, st>>>(w, taps, Cin, Cout, ws);
+    float* trailer = const_cast<float*>(weight_scale_ptr(ws, taps, Cin, Cout));
+    WCTB_CUDA(cudaMemsetAsync(trailer, 0, 256, st));
+    const long long n = (long long)taps * Cin * Cout;
+    k_absmax<<<grid_for(n, 256), 256, 0, st>>>(w, n, reinterpret_cast<unsigned int*>(trailer) + 1);
+    WCTB_CHECK_LAUNCH("k_absmax");
+    k_prep_weights<<<grid_for(n, 256), 256, 0, st>>>(w, taps, Cin, Cout, ws, trailer);
     WCTB_CHECK_LAUNCH("k_prep_weights");
+    return 0;
+}
+int launch_prep_weights_up2(const float* w, int Cin, int Cout, __half* ws, cudaStream_t st) {
+    float* trailer = const_cast<float*>(weight_scale_ptr(ws, 16, Cin, Cout));
+    WCTB_CUDA(cudaMemsetAsync(trailer, 0, 256, st));
+    const long long n = 9ll * Cin * Cout;
+    k_absmax<<<grid_for(n, 256), 256, 0, st>>>(w, n, reinterpret_cast<unsigned int*>(trailer) + 1);
+    WCTB_CHECK_LAUNCH("k_absmax");
+    k_prep_weights_up2<<<grid_for(16ll * Cin * Cout, 256), 256, 0, st>>>(w, Cin, Cout, ws, trailer);
+    WCTB_CHECK_LAUNCH("k_prep_weights_up2");
     return 0;
 }
 int launch_conv3x3_ref(const __half* in, ActGeom gi, const float* w, const float* bias, int Cout, int flags,
@@ -510,11 +580,8 @@ int g_conv_tail_impl = 2;      // 1 = per-pixel kernel, 2 = shared-memory tiles 
 int launch_conv_tail(const __half* in, ActGeom gi, const float* w, const float* b, int flags, float* img, cudaStream_t st) {
     if (g_conv_tail_impl == 2 && gi.C % TT_CH == 0 && gi.H >= TT_H && gi.W >= TT_W && gi.C <= 128) {
         const size_t tsmem = ((size_t)TT_ACT_F4 + TT_STAGE_F4 + (size_t)9 * (gi.C / 4) * 3) * sizeof(float4);
-        static size_t attr = 0;
-        if (tsmem > attr) {
-            WCTB_CUDA(cudaFuncSetAttribute(k_conv_tail_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
-            attr = tsmem;
-        }
+        constexpr size_t tsmem_max = ((size_t)TT_ACT_F4 + TT_STAGE_F4 + (size_t)9 * (128 / 4) * 3) * sizeof(float4);   // C = 128
+        WCTB_ENSURE_SMEM(k_conv_tail_tiled, tsmem_max);
         const int tiles_x = (gi.W + TT_W - 1) / TT_W, tiles_y = (gi.H + TT_H - 1) / TT_H;
         k_conv_tail_tiled<<<(unsigned)(gi.N * tiles_x * tiles_y), 128, tsmem, st>>>(in, gi, w, b, flags, img, tiles_x, tiles_y);
         WCTB_CHECK_LAUNCH("k_conv_tail_tiled");

@@ -75,89 +75,6 @@ __global__ void k_mean_finalize(const double* __restrict__ sum, const double* __
     if (var) var[i] = (float)fmax(sumsq[i] / (double)HW - m * m, 0.0);   // biased variance (tf.nn.moments)
 }
 
-// ---------------------------------------------------------------------------
-// Stage A.2: covariance partial sums  cov[i][j] += sum_p (x_pi - m_i)(x_pj - m_j)
-//   grid (upper-tri 64x64 block pairs, pixel chunks, problems); 256 threads, 4x4 per thread
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_cov_partial(const __half* __restrict__ act, ActGeom g, const float* __restrict__ mean, int chunk_pix,
-              double* __restrict__ cov) {
-    __shared__ __align__(16) float Xi[32][64];
-    __shared__ __align__(16) float Xj[32][64];
-    const int nb = g.C / 64;
-    // decode upper-triangular pair index
-    int bi = 0, rem = blockIdx.x;
-    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
-    const int bj = bi + rem;
-    const bool diag = (bi == bj);
-    const int n = blockIdx.z;
-    const long long HW = (long long)g.H * g.W;
-    const long long q0 = (long long)blockIdx.y * chunk_pix;
-    const long long q1 = min(q0 + chunk_pix, HW);
-    const float* mn = mean + (long long)n * g.C;
-
-    const int lp = threadIdx.x >> 3;           // pixel within the 32-pixel step
-    const int lg = threadIdx.x & 7;            // 8-channel group within the 64-channel block
-    float mi[8], mj[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        mi[j] = mn[bi * 64 + lg * 8 + j];
-        mj[j] = mn[bj * 64 + lg * 8 + j];
-    }
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    float acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-
-    for (long long qs = q0; qs < q1; qs += 32) {
-        const long long q = qs + lp;
-        float vi[8], vj[8];
-        if (q < q1) {
-            const int y = (int)((unsigned)q / (unsigned)g.W), x = (int)((unsigned)q - (unsigned)y * (unsigned)g.W);
-            const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
-            load8(act, g, pos, bi * 64 + lg * 8, vi);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vi[j] -= mi[j];
-            if (!diag) {
-                load8(act, g, pos, bj * 64 + lg * 8, vj);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) vj[j] -= mj[j];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { vi[j] = 0.f; vj[j] = 0.f; }
-        }
-        __syncthreads();   // previous step's reads done
-        *reinterpret_cast<float4*>(&Xi[lp][lg * 8]) = *reinterpret_cast<float4*>(vi);
-        *reinterpret_cast<float4*>(&Xi[lp][lg * 8 + 4]) = *reinterpret_cast<float4*>(vi + 4);
-        if (!diag) {
-            *reinterpret_cast<float4*>(&Xj[lp][lg * 8]) = *reinterpret_cast<float4*>(vj);
-            *reinterpret_cast<float4*>(&Xj[lp][lg * 8 + 4]) = *reinterpret_cast<float4*>(vj + 4);
-        }
-        __syncthreads();
-        const float (*XB)[64] = diag ? Xi : Xj;
-#pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&Xi[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&XB[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
-        }
-    }
-    double* cv = cov + (long long)n * g.C * g.C;
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            atomicAdd(&cv[(long long)(bi * 64 + ty * 4 + r) * g.C + bj * 64 + tx * 4 + c], (double)acc[r][c]);
-}
-
 // cov64 (upper blocks) -> full symmetric fp32 matrix, /(HW-1), + eps_cov*I   (ops.py:45,50,108,121)
 __global__ void k_cov_finalize(const double* __restrict__ cov, const double* __restrict__ sum, int C, long long HW,
                                float eps_cov, int count, float* __restrict__ G, float* __restrict__ A0) {
@@ -792,15 +709,6 @@ static WctWs wct_layout(int C, int Nc, int Ns) {
 }
 size_t wct_workspace_bytes(int C, int Nc, int Ns) { return wct_layout(C, Nc, Ns).total; }
 
-static int pick_chunk(long long HW, int nblk_pairs, int n) {
-    // 32-pixel steps; aim for >= ~600 blocks, cap the fp32 partial sums at 512 pixels
-    long long chunk = (HW * nblk_pairs * n + 599) / 600;
-    chunk = (chunk + 31) / 32 * 32;
-    if (chunk < 64) chunk = 64;
-    if (chunk > 512) chunk = 512;
-    return (int)chunk;
-}
-
 template <bool SQ>
 static int launch_sums(const __half* act, ActGeom g, double* sum, double* sumsq, cudaStream_t st) {
     const long long HW = (long long)g.H * g.W;
@@ -843,12 +751,7 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
     cfg.numAttrs = 1;
 #define WCTB_JACOBI_CASE(NN)                                                                                         \
     case NN: {                                                                                                       \
-        static bool done = false;                                                                                    \
-        if (!done) {                                                                                                 \
-            WCTB_CUDA(cudaFuncSetAttribute(k_jacobi<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,                \
-                                           JacobiCfg<NN>::SMEM_BYTES));                                              \
-            done = true;                                                                                             \
-        }                                                                                                            \
+        WCTB_ENSURE_SMEM(k_jacobi<NN>, JacobiCfg<NN>::SMEM_BYTES);                                                   \
         cfg.dynamicSmemBytes = JacobiCfg<NN>::SMEM_BYTES;                                                            \
         WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, lg, stagger));         \
         break;                                                                                                       \
@@ -881,34 +784,27 @@ int launch_eig_post(const float* G, const float* A0, float* lam, int C, int coun
     return 0;
 }
 
-int g_cov_impl = 2;   // 1 = fp32 FFMA centred covariance, 2 = tcgen05 uncentred covariance (default)
 int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st);
 
 static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float* A0,
                          float eps_cov, cudaStream_t st) {
     const long long HW = (long long)g.H * g.W;
+    WCTB_REQUIRE(g.C == 64 || g.C % 128 == 0, "covariance: C=%d must be 64 or a multiple of 128", g.C);
     int rc = launch_sums<false>(act, g, sum, nullptr, st);
     if (rc) return rc;
     k_mean_finalize<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(sum, nullptr, HW, g.N * g.C, mean, nullptr);
     WCTB_CHECK_LAUNCH("k_mean_finalize");
-    const bool tc = g_cov_impl == 2 && (g.C == 64 || g.C % 128 == 0);
-    if (tc) {
-        // tensor-core path (cov_tc.cu) on a centred SPF16 copy of the features (stream-ordered scratch)
+    {
+        // tensor-core covariance (cov_tc.cu) on a centred SPF16 copy of the features (stream-ordered scratch)
         __half* centred = nullptr;
         { int rc0 = scratch_alloc(reinterpret_cast<void**>(&centred), (size_t)g.plane * 2 * sizeof(__half), st, 0); if (rc0) return rc0; }
         const long long total = (long long)g.N * g.H * g.W * (g.C / 8);
         long long blocks = (total + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
         k_center<<<(unsigned)blocks, 256, 0, st>>>(act, g, mean, centred);
         cudaError_t le = cudaGetLastError();
         int rc2 = le == cudaSuccess ? launch_cov_tc(centred, g, cov, st) : cuda_fail(le, "k_center");
         if (rc2) return rc2;
-    } else {
-        const int nb = g.C / 64;
-        const int chunk = pick_chunk(HW, nb * (nb + 1) / 2, g.N);
-        dim3 grid((unsigned)(nb * (nb + 1) / 2), (unsigned)cdiv(HW, chunk), (unsigned)g.N);
-        k_cov_partial<<<grid, 256, 0, st>>>(act, g, mean, chunk, cov);
-        WCTB_CHECK_LAUNCH("k_cov_partial");
     }
     k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
         cov, nullptr, g.C, HW, eps_cov, g.N, G, A0);
@@ -969,7 +865,7 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     k_finalize_transform<<<gf, 256, 0, st>>>(T, C, Nc, Ns, alpha, readd, mean, mean + (long long)Nc * C, Msplit, bias);
     WCTB_CHECK_LAUNCH("k_finalize_transform");
     // out = M x + bias on the tensor cores (1-tap conv, per-frame weight set)
-    rc = launch_conv3x3_tc(content, Nc, Hc, Wc, C, Msplit, 1, Nc, bias, C, 0, out, st);
+    rc = launch_conv_tc(CONV_APPLY, content, Nc, Hc, Wc, C, Msplit, Nc, nullptr, bias, C, 0, out, st);
     if (rc) return rc;
     if (k_out) WCTB_CUDA(cudaMemcpyAsync(k_out, kc, (size_t)np * 2 * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -1080,7 +976,7 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
     dim3 gf((unsigned)cdiv(C, 8), (unsigned)Nc);
     k_finalize_transform<<<gf, 256, 0, st>>>(T, C, Nc, Ns, alpha, readd, mean, mean_s, Msplit, bias);
     WCTB_CHECK_LAUNCH("k_finalize_transform");
-    rc = launch_conv3x3_tc(content, Nc, Hc, Wc, C, Msplit, 1, Nc, bias, C, 0, out, st);
+    rc = launch_conv_tc(CONV_APPLY, content, Nc, Hc, Wc, C, Msplit, Nc, nullptr, bias, C, 0, out, st);
     if (rc) return rc;
     if (k_out) {
         // k_out: [k_c x Nc | k_s x Ns | sweeps_c x Nc | sweeps_s x Ns]  (same order as wct_level)
@@ -1095,7 +991,7 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
 // test / profiling hook: means and covariance of a feature batch (stage A of the transform)
 int launch_covariance(const __half* act, int N, int H, int W, int C, float eps_cov, float* mean_out, float* cov_out,
                       cudaStream_t st) {
-    WCTB_REQUIRE(C % 64 == 0 && C >= 64, "covariance: C=%d must be a multiple of 64", C);
+    WCTB_REQUIRE(C == 64 || (C % 128 == 0 && C >= 128), "covariance: C=%d must be 64 or a multiple of 128", C);
     double *sum = nullptr, *cov = nullptr;
     const size_t nsum = (size_t)N * C, ncov = (size_t)N * C * C;
     { int rc0 = scratch_alloc(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st, 1); if (rc0) return rc0; }
@@ -1137,7 +1033,7 @@ int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __ha
     WCTB_CHECK_LAUNCH("k_adain_coeffs");
     const long long total = (long long)Nc * Hc * Wc * (C / 8);
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
     k_affine_apply<<<(unsigned)blocks, 256, 0, st>>>(content, gc, scale, shift, out);
     WCTB_CHECK_LAUNCH("k_affine_apply");
     return 0;
@@ -1155,7 +1051,7 @@ int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __ha
 // ---------------------------------------------------------------------------
 static inline int swap_grid(long long total, int block) {
     long long b = (total + block - 1) / block;
-    return (int)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b));
+    return (int)(b < 1 ? 1 : (b > device_sm_count() * 32ll ? device_sm_count() * 32ll : b));
 }
 
 struct SwapWs {
@@ -1367,22 +1263,22 @@ int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half*
     k_finalize_transform<<<dim3((unsigned)cdiv(C, 8), 1), 256, 0, st>>>(mats + 2 * CC, C, 1, 1, 1.f, 0, zeros, mean + C, msplit + 4 * CC,
                                                                          bias3 + 2 * C);
     WCTB_CHECK_LAUNCH("k_finalize_transform(colour)");
-    rc = launch_conv3x3_tc(content, 1, Hc, Wc, C, msplit, 1, 1, bias3, C, 0, wc_feat, st);
+    rc = launch_conv_tc(CONV_APPLY, content, 1, Hc, Wc, C, msplit, 1, nullptr, bias3, C, 0, wc_feat, st);
     if (rc) return rc;
-    rc = launch_conv3x3_tc(style, 1, Hs, Ws, C, msplit + 2 * CC, 1, 1, bias3 + C, C, 0, ws_feat, st);
+    rc = launch_conv_tc(CONV_APPLY, style, 1, Hs, Ws, C, msplit + 2 * CC, 1, nullptr, bias3 + C, C, 0, ws_feat, st);
     if (rc) return rc;
     k_swap_tap_norms<<<dim3((unsigned)cdiv(C, 256), 9), 256, 0, st>>>(ws_feat, gs, norms);
     WCTB_CHECK_LAUNCH("k_swap_tap_norms");
     k_swap_patch_weights<<<swap_grid(9ll * C * S.cout_pad, 256), 256, 0, st>>>(ws_feat, gs, norms, S.n_patches, S.cout_pad, wsplit);
     WCTB_CHECK_LAUNCH("k_swap_patch_weights");
-    rc = launch_conv3x3_tc(wc_feat, 1, Hc, Wc, C, wsplit, 9, 1, nullptr, S.cout_pad, 0, scores, st);
+    rc = launch_conv_tc(CONV_3X3, wc_feat, 1, Hc, Wc, C, wsplit, 1, nullptr, nullptr, S.cout_pad, 0, scores, st);
     if (rc) return rc;
     const int npos = (Hc - 2) * (Wc - 2);
     k_swap_argmax<<<(unsigned)cdiv((long long)npos * 32, 256), 256, 0, st>>>(scores, ActGeom(1, Hc, Wc, S.cout_pad), S.n_patches, idx);
     WCTB_CHECK_LAUNCH("k_swap_argmax");
     k_swap_gather<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(ws_feat, gs, idx, gc, ss_feat);
     WCTB_CHECK_LAUNCH("k_swap_gather");
-    rc = launch_conv3x3_tc(ss_feat, 1, Hc, Wc, C, msplit + 4 * CC, 1, 1, bias3 + 2 * C, C, 0, tmp, st);
+    rc = launch_conv_tc(CONV_APPLY, ss_feat, 1, Hc, Wc, C, msplit + 4 * CC, 1, nullptr, bias3 + 2 * C, C, 0, tmp, st);
     if (rc) return rc;
     k_blend2<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(tmp, content, gc, alpha, 1.f - alpha, out);   // ops.py:210
     WCTB_CHECK_LAUNCH("k_blend2");

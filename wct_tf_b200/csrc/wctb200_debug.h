@@ -1,0 +1,22 @@
+/* Tuning / probe hooks of libwctb200 -- PRIVATE: used by tools/ and tests/ only, not part of the stable C-ABI
+ * (include/wctb200.h).  They set process-global knobs and are not thread-safe. */
+#ifndef WCTB200_DEBUG_H
+#define WCTB200_DEBUG_H
+#include "../../include/wctb200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* force the conv output-channel tile (64/128/256; 0 = built-in heuristic) */
+WCTB200_API int wctb200_debug_set_conv_bn(int bn);
+/* CTAs per SM in the persistent conv grid (default 4; 1 = exactly one CTA per SM) */
+WCTB200_API int wctb200_debug_set_conv_oversub(int k);
+/* fuse the a_hi*b_hi and a_hi*b_lo products into one N = 2*tile MMA: -1 auto (default), 0 never, 1 always */
+WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
+/* Jacobi cross-phase schedule: 2^lg_groups warp groups (0..4) started stagger_cycles apart; negative = per-size default */
+WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
+/* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4) */
+WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
+#ifdef __cplusplus
+}
+#endif
+#endif

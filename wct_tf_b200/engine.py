@@ -32,7 +32,7 @@ class Act(object):
 
 
 class Engine(object):
-    def __init__(self, weights, relu_targets, device="cuda:0", semantics="tf"):
+    def __init__(self, weights, relu_targets, device="cuda:0", semantics="tf", fuse_upsample=True):
         if not torch.cuda.is_available():
             raise _capi.WctB200Error("no CUDA device: the WCT engine has no CPU fallback")
         self.lib = _capi.load()
@@ -49,8 +49,10 @@ class Engine(object):
         self._group = 0
         self._style_streams = {}
         self._group_streams = {}
+        self.fuse_upsample = bool(fuse_upsample)  # UpSampling2D folded into the next conv (4 parity kernels, 4/9 of the MACs); fixed at construction
         self.launches = 0          # kernels launched through the C-ABI (bench.py "gpu_launches")
         self.profile = None        # optional dict: key -> [torch.cuda.Event pairs, flops, bytes]
+        self._tag = None           # profiling only: "style" / relu target of the level being enqueued
         with torch.cuda.device(self.device):
             self._upload(weights)
 
@@ -58,13 +60,23 @@ class Engine(object):
     def _dev(self, a, dtype=torch.float32):
         return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
 
-    def _prep_split(self, w_hwio):
-        """fp32 (kH,kW,Cin,Cout) -> device split-fp16 GEMM operand."""
+    def _prep_split(self, w_hwio, up2=False):
+        """fp32 (kH,kW,Cin,Cout) -> device split-fp16 GEMM operand (``up2``: the four 2x2-tap parity kernels of
+        UpSampling2D -> Conv2DReflect, see csrc/conv_tc.cu)."""
         kh, kw, cin, cout = w_hwio.shape
         src = self._dev(w_hwio.astype(np.float32))
+        if up2:
+            dst = torch.empty(self.lib.wctb200_conv_weight_bytes(16, cin, cout), dtype=torch.uint8, device=self.device)
+            _capi.check(self.lib.wctb200_prep_conv_weights_up2(src.data_ptr(), cin, cout, dst.data_ptr(), self._stream()))
+            return dst
         dst = torch.empty(self.lib.wctb200_conv_weight_bytes(kh * kw, cin, cout), dtype=torch.uint8, device=self.device)
         _capi.check(self.lib.wctb200_prep_conv_weights(src.data_ptr(), kh * kw, cin, cout, dst.data_ptr(), self._stream()))
         return dst
+
+    @staticmethod
+    def _fused_up(ops, i):
+        """True when ops[i] is an 'up' that the engine folds into the conv that follows it (model.py:291-293)."""
+        return ops[i].kind == "up" and i + 1 < len(ops) and ops[i + 1].kind == "conv" and ops[i + 1].act
 
     def _upload(self, weights):
         vgg = {l["name"]: l for l in weights["vgg"]}
@@ -93,14 +105,15 @@ class Engine(object):
             if relu not in weights["decoders"]:
                 raise Exception("No checkpoint found for target {}".format(relu))  # wct.py:57-58
             layers = {l["name"]: l for l in weights["decoders"][relu]}
-            for op in self.model.decoder_plan(lvl.index):
+            ops = self.model.decoder_plan(lvl.index)
+            for i, op in enumerate(ops):
                 if op.kind != "conv":
                     continue
                 l = layers[op.name]
                 k = np.asarray(l["kernel"], dtype=np.float32)
                 assert k.shape == (3, 3, op.cin, op.cout), (op.name, k.shape)
                 if op.act:
-                    self.dec_w[op.name] = self._prep_split(k)
+                    self.dec_w[op.name] = self._prep_split(k, up2=(self.fuse_upsample and i > 0 and self._fused_up(ops, i - 1)))
                     self.dec_b[op.name] = self._dev(np.asarray(l["bias"], dtype=np.float32))
                 else:
                     self.tail_w[relu] = self._dev(k.reshape(9 * op.cin, 3))
@@ -115,6 +128,8 @@ class Engine(object):
         if self.profile is None:
             _capi.check(fn(*args))
             return
+        if self._tag:
+            key = "%s:%s" % (self._tag, key)      # level the call belongs to (bench.py: per-level conv rates)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _capi.check(fn(*args))
@@ -181,20 +196,37 @@ class Engine(object):
         relu = self.model.levels[level_index].relu_target
         x = feat
         N = x.N
-        for op in self.model.decoder_plan(level_index):
+        ops = self.model.decoder_plan(level_index)
+        pending_up = False                     # an UpSampling2D waiting to be folded into the next conv
+        for i, op in enumerate(ops):
             if op.kind == "up":
+                if self.fuse_upsample and self._fused_up(ops, i):
+                    pending_up = True          # x stays low-resolution (its producer wrote an edge halo)
+                    continue
                 y = self._act(N, x.H * 2, x.W * 2, x.C)
                 self._call("upsample2", 1, lib.wctb200_upsample2, x.ptr, N, x.H, x.W, x.C, y.ptr, st,
                            bytes_=4.0 * N * x.C * x.H * x.W * 5)
                 x = y
             elif op.act:
-                y = self._act(N, x.H, x.W, op.cout)
-                self._call("conv3x3_tc[%dx%d@%d]" % (op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr, N, x.H, x.W,
-                           op.cin, self.dec_w[op.name].data_ptr(), self.dec_b[op.name].data_ptr(), op.cout,
-                           _capi.RELU, y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
-                           bytes_=4.0 * N * x.H * x.W * (op.cin + op.cout))
+                # a conv whose output feeds a folded upsample writes an EDGE-replicated halo (conv_tc.cu, mode UP2)
+                edge = self.fuse_upsample and i + 1 < len(ops) and self._fused_up(ops, i + 1)
+                flags = _capi.RELU | (_capi.HALO_EDGE if edge else 0)
+                if pending_up:
+                    y = self._act(N, 2 * x.H, 2 * x.W, op.cout)
+                    self._call("conv3x3_up2[%dx%d@%d]" % (op.cin, op.cout, y.H), 1, lib.wctb200_conv3x3_up2, x.ptr, N, x.H, x.W,
+                               op.cin, self.dec_w[op.name].data_ptr(), self.dec_b[op.name].data_ptr(), op.cout,
+                               flags, y.ptr, st, flops=2.0 * 4 * op.cin * op.cout * N * y.H * y.W,
+                               bytes_=4.0 * N * (x.H * x.W * op.cin + y.H * y.W * op.cout))
+                    pending_up = False
+                else:
+                    y = self._act(N, x.H, x.W, op.cout)
+                    self._call("conv3x3_tc[%dx%d@%d]" % (op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr, N, x.H, x.W,
+                               op.cin, self.dec_w[op.name].data_ptr(), self.dec_b[op.name].data_ptr(), op.cout,
+                               flags, y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
+                               bytes_=4.0 * N * x.H * x.W * (op.cin + op.cout))
                 x = y
             else:
+                assert not pending_up
                 img = torch.empty((N, x.H, x.W, 3), dtype=torch.float32, device=self.device)
                 self._call("conv_tail", 1, lib.wctb200_conv_tail, x.ptr, N, x.H, x.W, op.cin, self.tail_w[relu].data_ptr(),
                            self.tail_b[relu].data_ptr(), _capi.CLIP01 if clip else 0, img.data_ptr(), st,
@@ -240,8 +272,7 @@ class Engine(object):
         self._call("style_swap[C%d]" % C, 22, self.lib.wctb200_style_swap_level, content.ptr, content.H, content.W, style.ptr,
                    style.H, style.W, C, float(ss_alpha), sem["eps_cov"], sem["thresh"], out.ptr,
                    kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st)
-        self._keep = getattr(self, "_keep", [])
-        self._keep.append(ws)                  # the workspace must outlive the asynchronous launches of this step
+        ws.record_stream(torch.cuda.current_stream(self.device))   # freed by the caching allocator only after this stream is done
         return out, kbuf
 
     def style_prepare(self, style):
@@ -287,7 +318,6 @@ class Engine(object):
         if swap5:
             if N != 1 or style_u8.shape[0] != 1:
                 raise ValueError("swap5 works on one content/style pair per call (ops.py:146)")
-            self._keep = []
             return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture, True, ss_alpha)
         G = min(self.groups, N) if (capture is None and not want_info) else 1
         if G > 1:
@@ -336,6 +366,7 @@ class Engine(object):
             side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
         style_states, style_events, style_feats = {}, {}, None
         with torch.cuda.stream(side):
+            self._tag = "style"
             style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
             self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(),
                        self._stream())
@@ -353,6 +384,7 @@ class Engine(object):
         nlev = len(self.model.levels)
         n_style = style_u8.shape[0]
         for lvl in self.model.levels:
+            self._tag = lvl.relu_target
             cf, _ = self.encode(x, lvl.relu_target)
             if swap5 and lvl.relu_target == "relu5_1":     # model.py:148-152: style swap wins over AdaIN / WCT at relu5_1
                 f, kbuf = self.style_swap(cf, style_feats[lvl.relu_target], ss_alpha, want_info)
@@ -371,6 +403,7 @@ class Engine(object):
             x = self.decode(f, lvl.index, clip=(lvl.index < nlev - 1))
             if capture is not None:
                 capture.setdefault("level_output", []).append(x)
+        self._tag = None
         if side is not main:
             side.wait_stream(main)             # buffers handed across streams may be recycled only after both are done
             main.wait_stream(side)

@@ -22,10 +22,14 @@ from .engine import Engine
 
 def _torch_device(device):
     """'/gpu:0' (stylize.py:23) -> 'cuda:0'."""
+    if isinstance(device, int):
+        return "cuda:%d" % device
     if isinstance(device, str):
         m = re.match(r"^/?(?:device:)?gpu:(\d+)$", device.strip().lower())
         if m:
             return "cuda:%s" % m.group(1)
+        if re.match(r"^\d+$", device.strip()):          # a bare ordinal, as the CLI help advertises
+            return "cuda:%s" % device.strip()
         if device.strip().lower() in ("/cpu:0", "cpu"):
             raise ValueError("the B200 engine has no CPU path (device=%r)" % (device,))
     return device
@@ -101,14 +105,19 @@ class WCT(object):
                 out_f = eng.stylize(out_dev, s, alpha=alpha, adain=adain)
                 out_dev = eng.to_u8(out_f)
             if return_device:
-                torch.cuda.current_stream(dev).synchronize()
+                eng.check_device()            # synchronises; raises WctB200Error if a kernel recorded a pipeline time-out
                 return (out_dev, out_f) if return_float else out_dev
             if out is not None:
                 out.copy_(out_dev, non_blocking=True)
-                torch.cuda.current_stream(dev).synchronize()
                 out_u8 = out
             else:
-                out_u8 = out_dev.cpu().numpy()
+                out_u8 = torch.empty(out_dev.shape, dtype=torch.uint8, pin_memory=True)
+                out_u8.copy_(out_dev, non_blocking=True)
+            # the call is synchronous like sess.run (wct.py:97); a device-side time-out would otherwise leave every
+            # later frame silently wrong (kernels skip their stores once the error word is set)
+            eng.check_device()
+            if out is None:
+                out_u8 = out_u8.numpy().copy()
         if return_float:
             return out_u8, out_f.cpu().numpy()
         return out_u8
