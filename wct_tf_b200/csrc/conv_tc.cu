@@ -268,7 +268,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const TileCoord tc = tile_coord(p, tile, n_tiles, BN);
             // stage this tile's bias slice (named barrier 1: epilogue warps only)
             asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
-            for (int i = et; i < BN; i += ETHREADS) sbias[i] = p.bias ? p.bias[(long long)tc.set * p.Cout + tc.n0 + i] : 0.f;
+            for (int i = et; i < BN; i += ETHREADS) sbias[i] = p.bias ? p.bias[(long long)(p.mode == CONV_APPLY ? tc.set : 0) * p.Cout + tc.n0 + i] : 0.f;   // UP2: set = weight parity class, ONE bias
             asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
 
             float acc[Cfg::NACC];

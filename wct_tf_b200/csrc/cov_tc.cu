@@ -1,4 +1,5 @@
-// Covariance GEMM  S = sum_p x_p x_p^T  (C x HW . HW x C, ops.py:45,50,108,121) on the tensor cores.
+// Covariance GEMM  S = sum_p (x_p - t)(x_p - t)^T  (C x HW . HW x C, ops.py:43-45,48-50,105-108) on the tensor cores,
+// with the centring and the per-channel sums fused in: ONE pass over the features.
 //
 // The features are SPF16 [pixel][channel]: for the product X^T X the contraction index K is the
 // PIXEL, so both operands are "MN-major" (for a fixed k the 64 channels of a slice are the 128
@@ -8,12 +9,20 @@
 // reflect-padded plane (base pointer at pixel (0,0), padded strides, dims W x H): boxes that stick
 // out at a ragged edge are zero-filled by TMA and add nothing to the sums, halo cells are never read.
 //
-//   The input is the CENTRED feature copy fc = x - mean written by k_center (wct.cu): products
-//   in fp32 (split-fp16 x3), drained from TMEM every 128 pixels into registers (the tensor core
-//   accumulates with truncation and the diagonals are all-positive sums), per-CTA partials
-//   combined with fp64 atomics.  (An uncentred variant with the HW m m^T term removed in fp64 was
-//   measured first: it cancels in fp32 and produced a spurious eigenvalue above the 1e-5 cut on a
-//   rank-deficient map, so centring happens before the product, like ops.py:44-45.)
+// Centring (ops.py:44,49,106: fc = f - mean BEFORE the product).  Round 1 ran three extra passes for it (channel sums,
+// a centred SPF16 copy written to HBM, the product over the copy).  Now a tiny pre-kernel estimates a per-channel SHIFT t
+// (the mean of <= 1024 strided pixels; the exact mean when HW <= 1024), four "centring" warps subtract t from every staged
+// tile IN SHARED MEMORY (hi+lo -> fp32 -> minus t -> re-split, zero-filled out-of-range pixels stay zero) before the MMA warp
+// may read it, and accumulate s = sum_p (x_p - t) on the way.  The finalize kernel forms
+//     cov = (S - s s^T / HW) / (HW - 1),   mean = t + s / HW
+// in fp64: exact algebra for ANY t, and with t within sigma/32 of the mean the subtracted term is ~1e-3 of S, so nothing
+// cancels (the fully uncentred form, t = 0, was measured in round 1: it produced a spurious eigenvalue above the 1e-5 cut).
+//
+// Determinism.  Products in fp32 (split-fp16 x3), drained from TMEM every 128 pixels into registers (the tensor core
+// accumulates with truncation and the diagonals are all-positive sums).  Every CTA writes its partial block and partial sums
+// to its OWN slot; the finalize kernel adds the slots in a fixed order.  The split of an image into CTAs depends on (C, H, W)
+// only -- not on the batch size or the SM count -- so a frame's covariance is bit-identical whatever batch or GPU it is in
+// (tests: 2-GPU shards == 1 GPU, batch == single frames).
 //
 // One CTA = one 128 x 128 block pair (bi <= bj) of the C x C matrix x one range of pixel tiles.
 #include "common.cuh"
@@ -25,8 +34,10 @@ struct CovParams {
     int tiles_x, tiles_y;        // 32 x 2 pixel tiles per image
     int ksplit, tiles_per_split;
     int nb;                      // 128-channel blocks (C=64: 1 block, rows duplicated)
-    int lbo_bytes, sbo_bytes;    // MN-major descriptor strides (probe knobs)
-    double* cov;                 // [N][C][C] fp64 partial sums (upper block triangle)
+    int nslots;                  // partial slots per image: ksplit (C=64: 2*ksplit)
+    const float* shift;          // [N][C]
+    float* part;                 // [N][nslots][C][C] fp32 partial products (upper block triangle)
+    float* psum;                 // [N][ksplit][C] fp32 partial sums of (x - shift)
     unsigned int* err;
 };
 
@@ -37,8 +48,10 @@ struct CovCfg {
     static constexpr int STAGES = 3;
     static constexpr int NBUF = 4;
     static constexpr int CH = 2;                            // 64-pixel tiles per TMEM accumulation chunk (24 truncating adds)
-    static constexpr int THREADS = 192;
-    static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + 1024;
+    static constexpr int THREADS = 320;                     // producer, MMA, 4 epilogue warps, 4 centring warps
+    static constexpr int RED_BYTES = 16 * 128 * 4;          // centring warps: [16 row groups][128 channels] partial sums
+    static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + RED_BYTES + 1024;
+    static constexpr int LBO = 8192, SBO = 1024;            // MN-major descriptor strides (probed on B200, profiles/r01_cov_mn_major_probe.txt)
 };
 
 __device__ __forceinline__ void tma_load_5d_cov(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
@@ -53,11 +66,11 @@ __device__ __forceinline__ void tma_load_5d_cov(void* smem_dst, const void* map,
 // MN-major SWIZZLE_128B operand: 64 MN elements (128 B) per row, rows = K; LBO = stride between
 // 64-wide MN groups, SBO = stride between 8-row K groups (cute::UMMA canonical layout
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, int lbo_bytes, int sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)((CovCfg::LBO >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((CovCfg::SBO >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -74,10 +87,12 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE;
     uint64_t* full = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty = full + Cfg::STAGES;
-    uint64_t* tfull = empty + Cfg::STAGES;
+    uint64_t* ready = empty + Cfg::STAGES;
+    uint64_t* tfull = ready + Cfg::STAGES;
     uint64_t* tempty = tfull + Cfg::NBUF;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NBUF);
     volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* red = reinterpret_cast<float*>(aux + 512);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // block pair / k-split / image of this CTA
@@ -95,12 +110,11 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     const int ntiles = max(t1 - t0, 0);
     // C = 64: a single 64-channel slice.  The 128-row operand is [hi plane | lo plane] of that slice and is used as BOTH
     // A and B: ONE MMA per 16 pixels yields hi.hi, hi.lo, lo.hi (and lo.lo) as the four 64x64 quadrants of the 128x128
-    // accumulator; the epilogue adds the quadrants.  (The first version loaded the slice twice to fill M = N = 128 and
-    // issued the three split products separately: 3x the MMAs and 2x the TMA bytes for the same result.)
+    // accumulator; the epilogue adds the quadrants.
     const bool dup = (p.C == 64);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
         for (int b = 0; b < Cfg::NBUF; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
         *abort_flag = 0;
         fence_barrier_init();
@@ -152,7 +166,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
                 const int it_end = min(ntiles, (c + 1) * Cfg::CH);
                 for (; it < it_end; ++it) {
                     const int s = it % Cfg::STAGES;
-                    mbar_wait(&full[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x520u + s);
+                    mbar_wait(&ready[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x520u + s);   // tile landed AND centred
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
                     const uint32_t b0 = diag ? a0 : a0 + Cfg::OPER;
@@ -161,14 +175,14 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
                     for (int k = 0; k < 4; ++k) {           // 64 pixels = 4 x UMMA_K(16): 16 rows of 128 B = 2048 B per step
                         const uint32_t ko = k * 2048;
                         if (dup) {
-                            const uint64_t d = umma_desc_mn_sw128(a0 + ko, p.lbo_bytes, p.sbo_bytes);   // [hi | lo] x [hi | lo]^T
+                            const uint64_t d = umma_desc_mn_sw128(a0 + ko);   // [hi | lo] x [hi | lo]^T
                             umma_f16(tacc, d, d, idesc, (first && k == 0) ? 0u : 1u);
                             continue;
                         }
-                        const uint64_t a_hi = umma_desc_mn_sw128(a0 + ko, p.lbo_bytes, p.sbo_bytes);
-                        const uint64_t a_lo = umma_desc_mn_sw128(a0 + 2 * Cfg::SLICE + ko, p.lbo_bytes, p.sbo_bytes);
-                        const uint64_t b_hi = umma_desc_mn_sw128(b0 + ko, p.lbo_bytes, p.sbo_bytes);
-                        const uint64_t b_lo = umma_desc_mn_sw128(b0 + 2 * Cfg::SLICE + ko, p.lbo_bytes, p.sbo_bytes);
+                        const uint64_t a_hi = umma_desc_mn_sw128(a0 + ko);
+                        const uint64_t a_lo = umma_desc_mn_sw128(a0 + 2 * Cfg::SLICE + ko);
+                        const uint64_t b_hi = umma_desc_mn_sw128(b0 + ko);
+                        const uint64_t b_lo = umma_desc_mn_sw128(b0 + 2 * Cfg::SLICE + ko);
                         umma_f16(tacc, a_hi, b_lo, idesc, (first && k == 0) ? 0u : 1u);
                         umma_f16(tacc, a_lo, b_hi, idesc, 1u);
                         umma_f16(tacc, a_hi, b_hi, idesc, 1u);
@@ -179,7 +193,8 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < 6) {
+        // ---- epilogue warps: drain TMEM chunks into registers, write this CTA's partial block to its own slot ----
         const int g = warp & 3;
         float acc[128];
 #pragma unroll
@@ -204,18 +219,101 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
         }
-        // this CTA's partial block -> fp64 accumulation buffer (row = channel bi*128 + m)
-        const int m = g * 32 + lane;
-        if (ntiles > 0 && !*abort_flag) {
+        const int m = g * 32 + lane;          // accumulator row
+        if (!*abort_flag) {
             if (dup) {
-                // accumulator rows m and m+64 both belong to channel m & 63; columns j and 64+j to channel j
-                double* dst = p.cov + ((long long)img * p.C + (m & 63)) * p.C;
-#pragma unroll 8
-                for (int j = 0; j < 64; ++j) atomicAdd(dst + j, (double)acc[j] + (double)acc[64 + j]);
+                // accumulator rows m and m+64 both belong to channel m & 63, columns j and 64+j to channel j:
+                // the two row halves go to two slots, the finalize kernel adds them
+                float* dst = p.part + (((long long)img * p.nslots + split * 2 + (m >> 6)) * p.C + (m & 63)) * p.C;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] + acc[64 + j], acc[j + 1] + acc[65 + j],
+                                                                      acc[j + 2] + acc[66 + j], acc[j + 3] + acc[67 + j]);
             } else {
-                double* dst = p.cov + ((long long)img * p.C + bi * 128 + m) * p.C + bj * 128;
-#pragma unroll 8
-                for (int j = 0; j < 128; ++j) atomicAdd(dst + j, (double)acc[j]);
+                float* dst = p.part + (((long long)img * p.nslots + split) * p.C + bi * 128 + m) * p.C + bj * 128;
+#pragma unroll
+                for (int j = 0; j < 128; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
+        }
+    } else {
+        // ---- centring warps: x -> x - shift in place on the staged tile, sums of the shifted values ----
+        const int ct = threadIdx.x - 192;     // 0..127
+        const int chunk = ct & 7;             // logical 16-byte chunk of a 128-byte row = channels chunk*8 .. +7 of the slice
+        const int rg = ct >> 3;               // rows rg, rg+16, rg+32, rg+48 of every 64-pixel slice
+        const int pchunk = (chunk ^ (rg & 7)) << 4;      // SWIZZLE_128B: physical chunk = logical ^ (row & 7); row & 7 == rg & 7
+        const int nops = dup ? 1 : (diag ? 1 : 2);
+        const int nsl = dup ? 1 : 2;
+        const bool want_sums = dup || diag;   // every channel block has exactly one diagonal pair
+        float sh[2][2][8], sums[2][8];
+#pragma unroll
+        for (int op = 0; op < 2; ++op)
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int blk = op == 0 ? bi : bj;
+                const int c0 = dup ? chunk * 8 : blk * 128 + sl * 64 + chunk * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sh[op][sl][j] = (op < nops && sl < nsl) ? __ldg(p.shift + (long long)img * p.C + c0 + j) : 0.f;
+            }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sums[sl][j] = 0.f;
+        for (int it = 0; it < ntiles; ++it) {
+            const int s = it % Cfg::STAGES;
+            mbar_wait(&full[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x550u + s);
+            const int t = t0 + it;
+            const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            uint8_t* st = smem + s * Cfg::STAGE;
+#pragma unroll
+            for (int op = 0; op < 2; ++op) {
+                if (op >= nops) break;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl >= nsl) break;
+                    uint8_t* hi_base = dup ? st : st + op * Cfg::OPER + sl * Cfg::SLICE;
+                    uint8_t* lo_base = dup ? st + Cfg::SLICE : st + op * Cfg::OPER + (2 + sl) * Cfg::SLICE;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int r = rg + 16 * k;
+                        const int x = tx * 32 + (r & 31), y = ty * 2 + (r >> 5);
+                        if (x < p.W && y < p.H) {           // out-of-range pixels were zero-filled by TMA and must stay zero
+                            const int off = r * 128 + pchunk;
+                            const Half8 h = *reinterpret_cast<const Half8*>(hi_base + off);
+                            const Half8 l = *reinterpret_cast<const Half8*>(lo_base + off);
+                            float v[8];
+                            merge8(h, l, v);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] -= sh[op][sl][j];
+                            if (op == 0) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) sums[sl][j] += v[j];
+                            }
+                            Half8 nh, nl;
+                            split8(v, nh, nl);
+                            *reinterpret_cast<Half8*>(hi_base + off) = nh;
+                            *reinterpret_cast<Half8*>(lo_base + off) = nl;
+                        }
+                    }
+                }
+            }
+            fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+        }
+        if (want_sums) {
+            // fixed-order reduction over the 16 row groups, then one partial per (image, split, channel)
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) red[rg * 128 + sl * 64 + chunk * 8 + j] = sums[sl][j];
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int nch = dup ? 64 : 128;
+            if (ct < nch && !*abort_flag) {
+                float a = 0.f;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) a += red[r * 128 + ct];
+                p.psum[((long long)img * p.ksplit + split) * p.C + (dup ? 0 : bi * 128) + ct] = a;
             }
         }
     }
@@ -224,13 +322,81 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// shift[n][c] = mean of <= ~1024 strided interior pixels (all pixels when HW <= 1024): fixed-order reduction
+__global__ void __launch_bounds__(256)
+k_sample_shift(const __half* __restrict__ act, ActGeom g, int stride, float* __restrict__ shift) {
+    __shared__ float red[256 * 8];
+    const int cgs = g.C / 8;                    // 8..64 channel groups
+    const int rows = 256 / cgs;
+    const int grp = threadIdx.x % cgs, rl = threadIdx.x / cgs;
+    const int n = blockIdx.x;
+    const long long HW = (long long)g.H * g.W;
+    const long long ns = (HW + stride - 1) / stride;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (rl < rows) {
+        for (long long k = rl; k < ns; k += rows) {
+            const long long q = k * stride;
+            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+            float v[8];
+            load8(act, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, grp * 8, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < g.C; c += 256) {
+        const int gq = c / 8, j = c % 8;
+        float a = 0.f;
+        for (int r = 0; r < rows; ++r) a += red[(r * cgs + gq) * 8 + j];
+        shift[(long long)n * g.C + c] = a / (float)ns;
+    }
+}
+
+// dsum[n][c] = sum over splits of psum (fp64, fixed order); mean = shift + dsum / HW
+__global__ void k_cov_sums(const float* __restrict__ psum, const float* __restrict__ shift, int C, int ksplit, long long HW,
+                           int total, double* __restrict__ dsum, float* __restrict__ mean) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int n = i / C, c = i - n * C;
+    double a = 0.0;
+    for (int s = 0; s < ksplit; ++s) a += (double)psum[((long long)n * ksplit + s) * C + c];
+    dsum[i] = a;
+    mean[i] = (float)((double)shift[i] + a / (double)HW);
+}
+
+// G = (sum_slots part - s s^T / HW) / (HW - 1) + eps_cov * I   (ops.py:45,50,108,121), exactly symmetric
+__global__ void k_cov_finalize(const float* __restrict__ part, const double* __restrict__ dsum, int C, int nslots, long long HW,
+                               float eps_cov, int count, float* __restrict__ G, float* __restrict__ A0) {
+    const long long total = (long long)count * C * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % C);
+        const int i = (int)((t / C) % C);
+        const long long n = t / ((long long)C * C);
+        // every (min,max) entry lies in a stored upper block: reading it for both (i,j) and (j,i) makes G exactly symmetric
+        const long long e = (i <= j) ? (long long)i * C + j : (long long)j * C + i;
+        const float* pp = part + n * nslots * (long long)C * C + e;
+        double v = 0.0;
+        for (int s = 0; s < nslots; ++s) v += (double)pp[(long long)s * C * C];
+        v -= dsum[n * C + i] * dsum[n * C + j] / (double)HW;
+        float r = (float)(v / (double)(HW - 1));
+        if (i == j) r += eps_cov;
+        G[t] = r;
+        if (A0) A0[t] = r;          // pristine copy: the Jacobi kernel overwrites G, the Rayleigh quotients need A
+    }
+}
+
 // ---------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-
-int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
+// Means and covariance (+ eps_cov I) of a feature batch: mean [N][C], G [N][C][C] (and a copy A0 if not null), fp32.
+// dsum: [N][C] fp64 scratch (caller's workspace); partial products live in the per-stream scratch cache.
+int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, float* G, float* A0, double* dsum, cudaStream_t st) {
     static PFN_encodeTiledC enc = nullptr;
     if (!enc) {
         void* ptr = nullptr;
@@ -242,7 +408,8 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
         }
         enc = reinterpret_cast<PFN_encodeTiledC>(ptr);
     }
-    WCTB_REQUIRE(g.C == 64 || g.C % 128 == 0, "cov_tc: C=%d must be 64 or a multiple of 128", g.C);
+    WCTB_REQUIRE(g.C == 64 || (g.C % 128 == 0 && g.C <= 2048), "covariance: C=%d must be 64 or a multiple of 128 (<= 2048)", g.C);
+    const long long HW = (long long)g.H * g.W;
     CovParams p;
     p.C = g.C; p.W = g.W; p.H = g.H; p.N = g.N;
     p.tiles_x = (g.W + 31) / 32;
@@ -250,19 +417,31 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
     p.nb = g.C == 64 ? 1 : g.C / 128;
     const int npairs = p.nb * (p.nb + 1) / 2;
     const int tiles_img = p.tiles_x * p.tiles_y;
-    // aim for ~2 CTAs per SM in total (each CTA pays ~5 us of TMEM/barrier set-up and final atomics),
-    // at least 8 tiles (512 pixels) per CTA
-    int ksplit = (device_sm_count() * 2 + npairs * g.N - 1) / (npairs * g.N);
-    if (ksplit < 1) ksplit = 1;
-    int tps = (tiles_img + ksplit - 1) / ksplit;
+    // Split of one image into CTAs: a function of (C, H, W) ONLY (batch- and device-invariant results).  Up to 64 tiles
+    // (4096 pixels) per CTA keeps the ~5 us of TMEM/barrier set-up per CTA below 20 % and still gives a single
+    // 512x512 frame 64 CTAs per block pair.
+    int tps = 64;
+    if (tiles_img < 64 * 8) tps = (tiles_img + 7) / 8;        // small maps: 8 splits
     if (tps < 8) tps = 8;
-    ksplit = (tiles_img + tps - 1) / tps;
-    p.ksplit = ksplit;
     p.tiles_per_split = tps;
-    p.lbo_bytes = 8192;      // MN-major descriptor strides, probed on B200 (profiles/r01_cov_mn_major_probe.txt)
-    p.sbo_bytes = 1024;
-    p.cov = cov;
+    p.ksplit = (tiles_img + tps - 1) / tps;
+    p.nslots = g.C == 64 ? 2 * p.ksplit : p.ksplit;
+    // scratch: shift [N][C] | psum [N][ksplit][C] | part [N][nslots][C][C]
+    const size_t n_shift = (size_t)g.N * g.C, n_psum = (size_t)g.N * p.ksplit * g.C;
+    const size_t n_part = (size_t)g.N * p.nslots * g.C * g.C;
+    float* scratch = nullptr;
+    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&scratch), (n_shift + n_psum + n_part + 64) * sizeof(float), st, 0); if (rc0) return rc0; }
+    float* shift = scratch;
+    float* psum = shift + ((n_shift + 3) & ~(size_t)3);
+    float* part = psum + ((n_psum + 3) & ~(size_t)3);
+    p.shift = shift; p.psum = psum; p.part = part;
     p.err = device_error_word();
+    // (blocks below the diagonal are never written -- and never read: k_cov_finalize only touches (min,max) entries)
+
+    const int stride = HW <= 1024 ? 1 : (int)(HW / 1024);
+    k_sample_shift<<<(unsigned)g.N, 256, 0, st>>>(act, g, stride, shift);
+    WCTB_CHECK_LAUNCH("k_sample_shift");
+
     // tensor map over the interior pixels only (see header comment)
     CUtensorMap mX;
     const __half* base = act + ((long long)g.Wp + 1) * g.C;
@@ -279,9 +458,15 @@ int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st) {
         return WCTB200_ECUDA;
     }
     WCTB_ENSURE_SMEM(cov_tc_kernel, CovCfg::SMEM_BYTES);
-    dim3 grid((unsigned)(npairs * ksplit), (unsigned)g.N);
+    dim3 grid((unsigned)(npairs * p.ksplit), (unsigned)g.N);
     cov_tc_kernel<<<grid, CovCfg::THREADS, CovCfg::SMEM_BYTES, st>>>(mX, p);
     WCTB_CHECK_LAUNCH("cov_tc_kernel");
+    k_cov_sums<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(psum, shift, g.C, p.ksplit, HW, g.N * g.C, dsum, mean);
+    WCTB_CHECK_LAUNCH("k_cov_sums");
+    const long long tot = (long long)g.N * g.C * g.C;
+    k_cov_finalize<<<(unsigned)(cdiv(tot, 256) > 4096 ? 4096 : cdiv(tot, 256)), 256, 0, st>>>(part, dsum, g.C, p.nslots, HW,
+                                                                                               eps_cov, g.N, G, A0);
+    WCTB_CHECK_LAUNCH("k_cov_finalize");
     return 0;
 }
 

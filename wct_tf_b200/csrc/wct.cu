@@ -75,25 +75,6 @@ __global__ void k_mean_finalize(const double* __restrict__ sum, const double* __
     if (var) var[i] = (float)fmax(sumsq[i] / (double)HW - m * m, 0.0);   // biased variance (tf.nn.moments)
 }
 
-// cov64 (upper blocks) -> full symmetric fp32 matrix, /(HW-1), + eps_cov*I   (ops.py:45,50,108,121)
-__global__ void k_cov_finalize(const double* __restrict__ cov, const double* __restrict__ sum, int C, long long HW,
-                               float eps_cov, int count, float* __restrict__ G, float* __restrict__ A0) {
-    const long long total = (long long)count * C * C;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(t % C);
-        const int i = (int)((t / C) % C);
-        const long long n = t / ((long long)C * C);
-        const double* cv = cov + n * C * C;
-        // every (min,max) entry lies in a stored upper block: reading it for both (i,j) and (j,i) makes G exactly symmetric
-        double v = (i <= j) ? cv[(long long)i * C + j] : cv[(long long)j * C + i];
-        if (sum) v -= sum[n * C + i] * sum[n * C + j] / (double)HW;    // uncentred sums: remove HW*m_i*m_j in fp64
-        float r = (float)(v / (double)(HW - 1));
-        if (i == j) r += eps_cov;
-        G[t] = r;
-        if (A0) A0[t] = r;          // pristine copy: the Jacobi kernel overwrites G, the Rayleigh quotients need A
-    }
-}
-
 // ---------------------------------------------------------------------------
 // Stage B: one-sided Jacobi.  Matrix n x n (n = 64*P), columns contiguous
 //   (symmetric input, so row-major == column-major).  A cluster of P CTAs owns one
@@ -645,49 +626,22 @@ __global__ void k_affine_apply(const __half* __restrict__ in, ActGeom g, const f
     }
 }
 
-// centred copy fc = x - mean (ops.py:44,49,106) as SPF16, interior cells only: the operand of the
-// tensor-core covariance.  Centring BEFORE the product matters: the uncentred form
-// sum x x^T - HW m m^T cancels in fp32 (measured: a rank-deficient 64-pixel map produced a
-// spurious eigenvalue above the 1e-5 cut).
-__global__ void k_center(const __half* __restrict__ in, ActGeom g, const float* __restrict__ mean, __half* __restrict__ out) {
-    const int cgs = g.C / 8;
-    const long long total = (long long)g.N * g.H * g.W * cgs;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)total; i += gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % (unsigned)cgs) * 8;
-        unsigned pix = i / (unsigned)cgs;
-        const int x = (int)(pix % (unsigned)g.W); pix /= (unsigned)g.W;
-        const int y = (int)(pix % (unsigned)g.H);
-        const int n = (int)(pix / (unsigned)g.H);
-        const long long pos = ((long long)n * g.Hp + y + 1) * g.Wp + x + 1;
-        float v[8];
-        load8(in, g, pos, c0, v);
-        const float* m = mean + (long long)n * g.C + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] -= m[j];
-        Half8 hi, lo;
-        split8(v, hi, lo);
-        const long long off = pos * g.C + c0;
-        *reinterpret_cast<Half8*>(out + off) = hi;
-        *reinterpret_cast<Half8*>(out + g.plane + off) = lo;
-    }
-}
-
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WctWs {
-    size_t sum, sumsq, mean, var, cov, G, A0, lam, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
+    size_t sum, sumsq, dsum, mean, var, G, A0, lam, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
 };
 static WctWs wct_layout(int C, int Nc, int Ns) {
     WctWs w;
     const size_t np = (size_t)Nc + Ns;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    w.sum = take(np * C * 8);
+    w.sum = take(np * C * 8);          // AdaIN: fp64 sums / sums of squares (contiguous: one memset clears both)
     w.sumsq = take(np * C * 8);
-    w.cov = take(np * C * C * 8);      // contiguous with sum/sumsq: one memset clears all three
+    w.dsum = take(np * C * 8);         // WCT: fp64 sums of the shifted features (cov_tc.cu)
     w.mean = take(np * C * 4);
     w.var = take(np * C * 4);
     w.G = take(np * C * C * 4);
@@ -784,33 +738,8 @@ int launch_eig_post(const float* G, const float* A0, float* lam, int C, int coun
     return 0;
 }
 
-int launch_cov_tc(const __half* act, ActGeom g, double* cov, cudaStream_t st);
-
-static int stats_and_cov(const __half* act, ActGeom g, double* sum, double* cov, float* mean, float* G, float* A0,
-                         float eps_cov, cudaStream_t st) {
-    const long long HW = (long long)g.H * g.W;
-    WCTB_REQUIRE(g.C == 64 || g.C % 128 == 0, "covariance: C=%d must be 64 or a multiple of 128", g.C);
-    int rc = launch_sums<false>(act, g, sum, nullptr, st);
-    if (rc) return rc;
-    k_mean_finalize<<<cdiv((long long)g.N * g.C, 256), 256, 0, st>>>(sum, nullptr, HW, g.N * g.C, mean, nullptr);
-    WCTB_CHECK_LAUNCH("k_mean_finalize");
-    {
-        // tensor-core covariance (cov_tc.cu) on a centred SPF16 copy of the features (stream-ordered scratch)
-        __half* centred = nullptr;
-        { int rc0 = scratch_alloc(reinterpret_cast<void**>(&centred), (size_t)g.plane * 2 * sizeof(__half), st, 0); if (rc0) return rc0; }
-        const long long total = (long long)g.N * g.H * g.W * (g.C / 8);
-        long long blocks = (total + 255) / 256;
-        if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
-        k_center<<<(unsigned)blocks, 256, 0, st>>>(act, g, mean, centred);
-        cudaError_t le = cudaGetLastError();
-        int rc2 = le == cudaSuccess ? launch_cov_tc(centred, g, cov, st) : cuda_fail(le, "k_center");
-        if (rc2) return rc2;
-    }
-    k_cov_finalize<<<cdiv((long long)g.N * g.C * g.C, 256) > 4096 ? 4096 : cdiv((long long)g.N * g.C * g.C, 256), 256, 0, st>>>(
-        cov, nullptr, g.C, HW, eps_cov, g.N, G, A0);
-    WCTB_CHECK_LAUNCH("k_cov_finalize");
-    return 0;
-}
+// cov_tc.cu: per-channel means and covariance (+ eps_cov I) in one pass over the features
+int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, float* G, float* A0, double* dsum, cudaStream_t st);
 
 int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
                      float alpha, float eps_cov, float eps_eig, float thresh, int readd, __half* out, int32_t* k_out,
@@ -825,8 +754,7 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     }
     uint8_t* w = static_cast<uint8_t*>(ws);
     const int np = Nc + Ns;
-    double* sum = reinterpret_cast<double*>(w + L.sum);
-    double* cov = reinterpret_cast<double*>(w + L.cov);
+    double* dsum = reinterpret_cast<double*>(w + L.dsum);
     float* mean = reinterpret_cast<float*>(w + L.mean);
     float* G = reinterpret_cast<float*>(w + L.G);
     float* sigma = reinterpret_cast<float*>(w + L.sigma);
@@ -840,15 +768,13 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     int* kc = reinterpret_cast<int*>(w + L.kcount);
     const long long CC = (long long)C * C;
 
-    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));          // sum, sumsq, cov
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)np * 2 * 4, st));
     ActGeom gc(Nc, Hc, Wc, C), gs(Ns, Hs, Ws, C);
     float* A0 = reinterpret_cast<float*>(w + L.A0);
     float* lam = reinterpret_cast<float*>(w + L.lam);
-    int rc = stats_and_cov(content, gc, sum, cov, mean, G, A0, eps_cov, st);
+    int rc = launch_mean_cov(content, gc, eps_cov, mean, G, A0, dsum, st);
     if (rc) return rc;
-    rc = stats_and_cov(style, gs, sum + (long long)Nc * C, cov + Nc * CC, mean + (long long)Nc * C, G + Nc * CC, A0 + Nc * CC,
-                       eps_cov, st);
+    rc = launch_mean_cov(style, gs, eps_cov, mean + (long long)Nc * C, G + Nc * CC, A0 + Nc * CC, dsum + (long long)Nc * C, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, np, conv, kc + np, st);
     if (rc) return rc;
@@ -905,18 +831,16 @@ int launch_wct_style_prepare(const __half* style, int Ns, int Hs, int Ws, int C,
     float* mean_s = reinterpret_cast<float*>(sp);
     float* Cs = reinterpret_cast<float*>(sp + off_cs);
     int* kc = reinterpret_cast<int*>(sp + off_k);
-    double* sum = reinterpret_cast<double*>(w + L.sum);
-    double* cov = reinterpret_cast<double*>(w + L.cov);
+    double* dsum = reinterpret_cast<double*>(w + L.dsum);
     float* G = reinterpret_cast<float*>(w + L.G);
     float* sigma = reinterpret_cast<float*>(w + L.sigma);
     float* dvec = reinterpret_cast<float*>(w + L.dvec);
     float* conv = reinterpret_cast<float*>(w + L.conv);
     const long long CC = (long long)C * C;
-    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Ns * 2 * 4, st));
     float* A0 = reinterpret_cast<float*>(w + L.A0);
     float* lam = reinterpret_cast<float*>(w + L.lam);
-    int rc = stats_and_cov(style, ActGeom(Ns, Hs, Ws, C), sum, cov, mean_s, G, A0, eps_cov, st);
+    int rc = launch_mean_cov(style, ActGeom(Ns, Hs, Ws, C), eps_cov, mean_s, G, A0, dsum, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, Ns, conv, kc + Ns, st);
     if (rc) return rc;
@@ -945,8 +869,7 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
     const float* mean_s = reinterpret_cast<const float*>(sp);
     const float* Cs = reinterpret_cast<const float*>(sp + off_cs);
     const int* ks = reinterpret_cast<const int*>(sp + off_k);
-    double* sum = reinterpret_cast<double*>(w + L.sum);
-    double* cov = reinterpret_cast<double*>(w + L.cov);
+    double* dsum = reinterpret_cast<double*>(w + L.dsum);
     float* mean = reinterpret_cast<float*>(w + L.mean);
     float* G = reinterpret_cast<float*>(w + L.G);
     float* sigma = reinterpret_cast<float*>(w + L.sigma);
@@ -958,11 +881,10 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
     float* conv = reinterpret_cast<float*>(w + L.conv);
     int* kc = reinterpret_cast<int*>(w + L.kcount);
     const long long CC = (long long)C * C;
-    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
     WCTB_CUDA(cudaMemsetAsync(kc, 0, (size_t)Nc * 2 * 4, st));
     float* A0 = reinterpret_cast<float*>(w + L.A0);
     float* lam = reinterpret_cast<float*>(w + L.lam);
-    int rc = stats_and_cov(content, ActGeom(Nc, Hc, Wc, C), sum, cov, mean, G, A0, eps_cov, st);
+    int rc = launch_mean_cov(content, ActGeom(Nc, Hc, Wc, C), eps_cov, mean, G, A0, dsum, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, Nc, conv, kc + Nc, st);
     if (rc) return rc;
@@ -992,12 +914,9 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
 int launch_covariance(const __half* act, int N, int H, int W, int C, float eps_cov, float* mean_out, float* cov_out,
                       cudaStream_t st) {
     WCTB_REQUIRE(C == 64 || (C % 128 == 0 && C >= 128), "covariance: C=%d must be 64 or a multiple of 128", C);
-    double *sum = nullptr, *cov = nullptr;
-    const size_t nsum = (size_t)N * C, ncov = (size_t)N * C * C;
-    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&sum), (nsum + ncov) * sizeof(double), st, 1); if (rc0) return rc0; }
-    cov = sum + nsum;
-    WCTB_CUDA(cudaMemsetAsync(sum, 0, (nsum + ncov) * sizeof(double), st));
-    return stats_and_cov(act, ActGeom(N, H, W, C), sum, cov, mean_out, cov_out, nullptr, eps_cov, st);
+    double* dsum = nullptr;
+    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&dsum), (size_t)N * C * sizeof(double), st, 1); if (rc0) return rc0; }
+    return launch_mean_cov(act, ActGeom(N, H, W, C), eps_cov, mean_out, cov_out, nullptr, dsum, st);
 }
 
 int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __half* style, int Ns, int Hs, int Ws, int C,
@@ -1016,7 +935,7 @@ int launch_adain_level(const __half* content, int Nc, int Hc, int Wc, const __ha
     float* var = reinterpret_cast<float*>(w + L.var);
     float* scale = reinterpret_cast<float*>(w + L.scale);
     float* shift = reinterpret_cast<float*>(w + L.shift);
-    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.cov - L.sum, st));
+    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.dsum - L.sum, st));
     ActGeom gc(Nc, Hc, Wc, C), gs(Ns, Hs, Ws, C);
     int rc = launch_sums<true>(content, gc, sum, sumsq, st);
     if (rc) return rc;
@@ -1212,8 +1131,7 @@ int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half*
     uint8_t* sw = static_cast<uint8_t*>(ws);
     const WctWs L = wct_layout(C, 1, 1);
     uint8_t* w = sw + S.base;
-    double* sum = reinterpret_cast<double*>(w + L.sum);
-    double* cov = reinterpret_cast<double*>(w + L.cov);
+    double* dsum = reinterpret_cast<double*>(w + L.dsum);
     float* mean = reinterpret_cast<float*>(w + L.mean);          // [mc, ms]
     float* G = reinterpret_cast<float*>(w + L.G);
     float* A0 = reinterpret_cast<float*>(w + L.A0);
@@ -1238,13 +1156,12 @@ int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half*
     __half* wsplit = reinterpret_cast<__half*>(sw + S.wsplit);
     const long long CC = (long long)C * C;
 
-    WCTB_CUDA(cudaMemsetAsync(w + L.sum, 0, L.mean - L.sum, st));
     WCTB_CUDA(cudaMemsetAsync(kc, 0, 4 * 4, st));
     WCTB_CUDA(cudaMemsetAsync(zeros, 0, (size_t)C * 4, st));
     ActGeom gc(1, Hc, Wc, C), gs(1, Hs, Ws, C);
-    int rc = stats_and_cov(content, gc, sum, cov, mean, G, A0, eps_cov, st);
+    int rc = launch_mean_cov(content, gc, eps_cov, mean, G, A0, dsum, st);
     if (rc) return rc;
-    rc = stats_and_cov(style, gs, sum + C, cov + CC, mean + C, G + CC, A0 + CC, eps_cov, st);
+    rc = launch_mean_cov(style, gs, eps_cov, mean + C, G + CC, A0 + CC, dsum + C, st);
     if (rc) return rc;
     rc = launch_jacobi(G, C, 2, conv, kc + 2, st);
     if (rc) return rc;
