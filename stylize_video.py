@@ -156,7 +156,10 @@ def main(argv=None, wct_factory=None):
             n = stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool)
             total += n
             print("Stylized {} frames with {} -> {}".format(n, style_prefix, frames_dir))
-            if have_ffmpeg():                                  # stylize_video.py:137-149
+            # stylize_video.py:137-149 re-encodes "frame_%d.png".  Frames extracted by ffmpeg carry that name; a user-supplied
+            # directory of frames keeps its own basenames, so it is only re-encoded when they follow the same pattern
+            named_like_ffmpeg = all(os.path.basename(f) == 'frame_%d.png' % (i + 1) for i, f in enumerate(out_files))
+            if have_ffmpeg() and named_like_ffmpeg:
                 pattern = os.path.join(frames_dir, 'frame_%d.png')
                 subprocess.check_call(['ffmpeg', '-y', '-i', pattern, '-f', 'mp4', '-q:v', '0', '-vcodec', 'mpeg4',
                                        '-r', str(args.fps), out_v])

@@ -241,8 +241,14 @@ def test_tf_checkpoint_reader_and_reference_loading_protocol(tmp_path):
     open(prefix + ".data-00000-of-00001", "wb").write(bytes(blob))
     with pytest.raises(T.TFCheckpointError, match="checksum"):
         T.read_bundle(prefix, verify=True)
-    with pytest.warns(UserWarning, match="checksum"):                            # default: warn, still return the data
-        assert len(T.read_bundle(prefix)) > 0
+    with pytest.raises(T.TFCheckpointError, match="checksum"):                   # default too: a corrupt TENSOR is always fatal
+        T.read_bundle(prefix)                                                    # (only index-block CRCs merely warn)
+    assert len(T.read_bundle(prefix, verify=False)) > 0
+    # a decoder checkpoint that lacks a layer is reported as such, not as a KeyError later in the engine
+    short = {k: v for k, v in tensors.items() if "/%s_0/" % targets[-1] not in k}
+    write_bundle(str(tmp_path / "short" / "model.ckpt-1"), short)
+    with pytest.raises(T.TFCheckpointError, match="lacks layer"):
+        T.load_decoder_checkpoint(str(tmp_path / "short"), targets[-1])
 
 
 def test_tf_checkpoint_snappy_block_decoder():

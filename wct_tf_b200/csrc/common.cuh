@@ -208,6 +208,50 @@ __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const 
     }
 }
 
+// Variant for EIGHT epilogue warps (two per TMEM lane quadrant, each owning NACC consecutive columns): 32 channels per
+// pass through a 4 KB staging buffer, 4 lanes write one position's 64 contiguous bytes per plane.  Why eight warps:
+// with one epilogue warp per scheduler the ~1100-instruction epilogue of a 128 x 64 tile ran at the latency of its own
+// dependent instruction chain (measured: tile time independent of the number of k-iterations for Cin = 64, ~7k cycles);
+// two warps per scheduler halve the instructions per warp and overlap each other's latencies.
+//   stg: this warp's private 4 KB buffer.  Bank check: 16-byte unit index = row*4 + slot with slot = q ^ ((row>>1)&3):
+//   any 8 consecutive lanes (one wavefront of a 128-bit access) hit 8 distinct units mod 8, writing and reading.
+template <int NACC>
+__device__ __forceinline__ void store_tile_rows32(const float (&acc)[NACC], const float oscale, const float* __restrict__ sbias,
+                                                  bool relu, uint8_t* __restrict__ stg, int lane, bool valid, int n, int y, int x,
+                                                  __half* __restrict__ out, const ActGeom& go, int cbase) {
+    const int packed = valid ? ((y << 16) | x) : -1;
+#pragma unroll
+    for (int h = 0; h < NACC / 32; ++h) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(acc[h * 32 + q * 8 + j], oscale, sbias[h * 32 + q * 8 + j]);
+                v[j] = relu ? fmaxf(t, 0.f) : t;
+            }
+            Half8 hi, lo;
+            split8(v, hi, lo);
+            const int slot = q ^ ((lane >> 1) & 3);
+            *reinterpret_cast<Half8*>(stg + (lane * 4 + slot) * 16) = hi;
+            *reinterpret_cast<Half8*>(stg + 2048 + (lane * 4 + slot) * 16) = lo;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = j * 8 + (lane >> 2);
+            const int c = lane & 3;
+            const int info = __shfl_sync(0xffffffffu, packed, row);
+            const int nn = __shfl_sync(0xffffffffu, n, row);
+            const int slot = c ^ ((row >> 1) & 3);
+            const Half8 hi = *reinterpret_cast<const Half8*>(stg + (row * 4 + slot) * 16);
+            const Half8 lo = *reinterpret_cast<const Half8*>(stg + 2048 + (row * 4 + slot) * 16);
+            if (info >= 0) store8_with_halo(out, go, nn, info >> 16, info & 0xffff, cbase + h * 32 + c * 8, hi, lo);
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // packed fp32 pairs: fma.rn.f32x2 does two FMAs per instruction on sm_100 (same FMA-pipe time, half the issue slots)
 // ---------------------------------------------------------------------------

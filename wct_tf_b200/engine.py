@@ -324,6 +324,15 @@ class Engine(object):
             main = torch.cuda.current_stream(self.device)
             bounds = [(g * N) // G for g in range(G + 1)]
             outs = []
+            shared = None
+            if style_u8.shape[0] == 1 and not adain:
+                # ONE style for the whole batch (video, configs[2]): its encoder pass and eigendecompositions run once,
+                # every sub-batch group waits for the per-level events
+                self._group = 1
+                try:
+                    shared = self._style_side(style_u8, True, main)
+                finally:
+                    self._group = 0
             for g in range(G):
                 lo, hi = bounds[g], bounds[g + 1]
                 if g not in self._group_streams:
@@ -337,7 +346,7 @@ class Engine(object):
                 try:
                     with torch.cuda.stream(gs):
                         sg = style_u8 if style_u8.shape[0] == 1 else style_u8[lo:hi]
-                        outs.append(self._stylize_one(content_u8[lo:hi], sg, alpha, adain, False, None))
+                        outs.append(self._stylize_one(content_u8[lo:hi], sg, alpha, adain, False, None, shared_style=shared))
                 finally:
                     self._group = 0
             for g in range(G):
@@ -345,10 +354,40 @@ class Engine(object):
             out = torch.cat(outs, dim=0)
             for g in range(G):                      # sub-batch buffers die here: their streams wait for the cat
                 self._group_streams[g].wait_stream(main)
+            if shared is not None and shared["side"] is not main:
+                shared["side"].wait_stream(main)    # the shared style states are recycled only after every group used them
             return out
         return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture)
 
-    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture, swap5=False, ss_alpha=0.6):
+    def _style_side(self, style_u8, split, main):
+        """Style side of one call (model.py:70-72: ONE encoder pass emitting every target; ops.py:48-55,76 per level when
+        ``split``): enqueued on this group's style stream when overlap is on.  Returns the states / events / features."""
+        lib = self.lib
+        side = main
+        if split and self.overlap_style:
+            if self._group not in self._style_streams:
+                prio = -1 if (self.group_priorities and self._group <= 1) else 0
+                self._style_streams[self._group] = torch.cuda.Stream(device=self.device, priority=prio)
+            side = self._style_streams[self._group]
+            side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
+        states, events, feats = {}, {}, None
+        with torch.cuda.stream(side):
+            tag, self._tag = self._tag, "style"
+            style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
+            self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(),
+                       self._stream())
+            _, feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
+            if split:
+                for relu in self.model.style_taps:
+                    if relu not in states:
+                        states[relu] = self.style_prepare(feats[relu])
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        events[relu] = ev
+            self._tag = tag
+        return dict(states=states, events=events, feats=feats, side=side)
+
+    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture, swap5=False, ss_alpha=0.6, shared_style=None):
         lib, st = self.lib, self._stream()
         N = content_u8.shape[0]
         assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
@@ -357,28 +396,8 @@ class Engine(object):
         self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, content_u8.data_ptr(), content_u8.numel(), content.data_ptr(), st)
         main = torch.cuda.current_stream(self.device)
         split = not adain and not swap5        # WCT: style side on its own stream; AdaIN / style swap: keep it inline
-        side = main
-        if split and self.overlap_style:
-            if self._group not in self._style_streams:
-                prio = -1 if (self.group_priorities and self._group <= 1) else 0
-                self._style_streams[self._group] = torch.cuda.Stream(device=self.device, priority=prio)
-            side = self._style_streams[self._group]
-            side.wait_stream(main)             # style_u8 (and last step's buffers) are ready
-        style_states, style_events, style_feats = {}, {}, None
-        with torch.cuda.stream(side):
-            self._tag = "style"
-            style = torch.empty(style_u8.shape, dtype=torch.float32, device=self.device)
-            self._call("u8_to_f32", 1, lib.wctb200_image_u8_to_f32, style_u8.data_ptr(), style_u8.numel(), style.data_ptr(),
-                       self._stream())
-            # model.py:70-72: one style pass emitting every target
-            _, style_feats = self.encode(style, self.model.deepest_target, taps=self.model.style_taps)
-            if split:
-                for relu in self.model.style_taps:
-                    if relu not in style_states:
-                        style_states[relu] = self.style_prepare(style_feats[relu])
-                        ev = torch.cuda.Event()
-                        ev.record(side)
-                        style_events[relu] = ev
+        ss = shared_style if (shared_style is not None and split) else self._style_side(style_u8, split, main)
+        side, style_states, style_events, style_feats = ss["side"], ss["states"], ss["events"], ss["feats"]
         infos = []
         x = content
         nlev = len(self.model.levels)
@@ -404,7 +423,7 @@ class Engine(object):
             if capture is not None:
                 capture.setdefault("level_output", []).append(x)
         self._tag = None
-        if side is not main:
+        if side is not main and shared_style is None:
             side.wait_stream(main)             # buffers handed across streams may be recycled only after both are done
             main.wait_stream(side)
         if want_info:

@@ -237,7 +237,9 @@ def read_bundle(prefix, verify="warn"):
         if len(raw) != e["size"] or e["size"] != want:
             raise TFCheckpointError("tensor %r: %d bytes in the shard, shape %s needs %d" % (key.decode(), len(raw), e["shape"], want))
         if verify and e["crc32c"] is not None and e["crc32c"] != masked_crc32c(raw):
-            _checksum_problem(verify, "tensor %r: checksum mismatch" % key.decode())
+            # a tensor whose bytes do not match its own checksum would load garbage weights: always fatal
+            raise TFCheckpointError("tensor %r: checksum mismatch (corrupt shard %s.data-%05d-of-%05d)"
+                                    % (key.decode(), prefix, sid, num_shards))
         out[key.decode()] = np.frombuffer(raw, dtype=dt).reshape(e["shape"]).copy()
     return out
 
@@ -280,4 +282,17 @@ def load_decoder_checkpoint(path, relu_target):
         out.append(dict(name="%s_%d" % (relu_target, count), kernel=l["kernel"], bias=l["bias"]))
     if not out:
         raise Exception("No checkpoint found for target {} in dir {}".format(relu_target, path))
-    return out
+    # the layer set and every shape must be the decoder model.py:245-304 builds for this target
+    from .model import decoder_plan
+    want = [op for op in decoder_plan(relu_target) if op.kind == "conv"]
+    have = {l["name"]: l for l in out}
+    missing = [op.name for op in want if op.name not in have]
+    if missing:
+        raise TFCheckpointError("%s: decoder %s lacks layer(s) %s (found %s)" % (prefix, relu_target, ", ".join(missing),
+                                                                              ", ".join(sorted(have)) or "none"))
+    for op in want:
+        k, bb = have[op.name]["kernel"], have[op.name]["bias"]
+        if tuple(k.shape) != (3, 3, op.cin, op.cout) or tuple(bb.shape) != (op.cout,):
+            raise TFCheckpointError("%s: layer %s has kernel %s / bias %s, the decoder needs (3, 3, %d, %d) / (%d,)"
+                                    % (prefix, op.name, tuple(k.shape), tuple(bb.shape), op.cin, op.cout, op.cout))
+    return [have[op.name] for op in want]
