@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwctb200.so")
-SOURCES = ["capi.cu", "layers.cu", "conv_tc.cu", "cov_tc.cu", "wct.cu"]
+SOURCES = ["capi.cu", "layers.cu", "conv_tc.cu", "cov_tc.cu", "wct.cu", "jacobi_s.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 NVCC_FLAGS += os.environ.get("WCTB_NVCC_EXTRA", "").split()      # experiments, e.g. -DWCTB_MBAR_TEST_WAIT
@@ -28,7 +28,7 @@ def _newer(src, dst):
 def build(force=False, verbose=False):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "wctb200_debug.h"),
+    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "jacobi_common.cuh"), os.path.join(CSRC, "wctb200_debug.h"),
             os.path.join(os.path.dirname(HERE), "include", "wctb200.h")]
     objs, relink = [], force or not os.path.exists(LIB)
     procs = []

@@ -208,50 +208,6 @@ __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const 
     }
 }
 
-// Variant for EIGHT epilogue warps (two per TMEM lane quadrant, each owning NACC consecutive columns): 32 channels per
-// pass through a 4 KB staging buffer, 4 lanes write one position's 64 contiguous bytes per plane.  Why eight warps:
-// with one epilogue warp per scheduler the ~1100-instruction epilogue of a 128 x 64 tile ran at the latency of its own
-// dependent instruction chain (measured: tile time independent of the number of k-iterations for Cin = 64, ~7k cycles);
-// two warps per scheduler halve the instructions per warp and overlap each other's latencies.
-//   stg: this warp's private 4 KB buffer.  Bank check: 16-byte unit index = row*4 + slot with slot = q ^ ((row>>1)&3):
-//   any 8 consecutive lanes (one wavefront of a 128-bit access) hit 8 distinct units mod 8, writing and reading.
-template <int NACC>
-__device__ __forceinline__ void store_tile_rows32(const float (&acc)[NACC], const float oscale, const float* __restrict__ sbias,
-                                                  bool relu, uint8_t* __restrict__ stg, int lane, bool valid, int n, int y, int x,
-                                                  __half* __restrict__ out, const ActGeom& go, int cbase) {
-    const int packed = valid ? ((y << 16) | x) : -1;
-#pragma unroll
-    for (int h = 0; h < NACC / 32; ++h) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float t = fmaf(acc[h * 32 + q * 8 + j], oscale, sbias[h * 32 + q * 8 + j]);
-                v[j] = relu ? fmaxf(t, 0.f) : t;
-            }
-            Half8 hi, lo;
-            split8(v, hi, lo);
-            const int slot = q ^ ((lane >> 1) & 3);
-            *reinterpret_cast<Half8*>(stg + (lane * 4 + slot) * 16) = hi;
-            *reinterpret_cast<Half8*>(stg + 2048 + (lane * 4 + slot) * 16) = lo;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int row = j * 8 + (lane >> 2);
-            const int c = lane & 3;
-            const int info = __shfl_sync(0xffffffffu, packed, row);
-            const int nn = __shfl_sync(0xffffffffu, n, row);
-            const int slot = c ^ ((row >> 1) & 3);
-            const Half8 hi = *reinterpret_cast<const Half8*>(stg + (row * 4 + slot) * 16);
-            const Half8 lo = *reinterpret_cast<const Half8*>(stg + 2048 + (row * 4 + slot) * 16);
-            if (info >= 0) store8_with_halo(out, go, nn, info >> 16, info & 0xffff, cbase + h * 32 + c * 8, hi, lo);
-        }
-        __syncwarp();
-    }
-}
-
 // ---------------------------------------------------------------------------
 // packed fp32 pairs: fma.rn.f32x2 does two FMAs per instruction on sm_100 (same FMA-pipe time, half the issue slots)
 // ---------------------------------------------------------------------------
@@ -394,6 +350,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
            | (0u << 15) | (0u << 16)      // a_major = b_major = K
            | ((uint32_t)(N >> 3) << 17)   // n_dim
            | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+// MN-major SWIZZLE_128B operand (used when the contraction index is the slow one: covariance X^T X, Gram G^T G):
+// 64 MN elements (128 B) per row, rows = K; LBO = stride between 64-wide MN groups (8 KB: the next slice / the lo plane),
+// SBO = stride between 8-row K groups (1 KB)  (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
+// units; strides probed on B200, profiles/r01_cov_mn_major_probe.txt)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((8192 >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(int M, int N) {
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 }
 #endif  // __CUDACC__
 

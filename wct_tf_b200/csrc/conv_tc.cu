@@ -32,10 +32,10 @@
 // unscaled lo plane (~5e-6) fell into the fp16 subnormals and kept only ~16 bits of the weight -- measured as
 // 8x the reference's own fp32 noise on the free-running 5-level image (profiles/r02_noise_split.txt).
 //
-// Structure (persistent CTAs, 320 threads):
+// Structure (persistent CTAs, 192 threads):
 //   warp 0   : TMA producer   (cp.async.bulk.tensor 3-D, 128B swizzle, mbarrier complete_tx)
 //   warp 1   : MMA issuer     (one elected thread, tcgen05.mma / tcgen05.commit), owns TMEM alloc
-//   warps 2-9: epilogue       (tcgen05.ld 32x32b -> *scale +bias, ReLU -> split fp16 -> 16-byte stores
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> *scale +bias, ReLU -> split fp16 -> 16-byte stores
 //                              of the interior pixel AND the halo cells that mirror it)
 #include "common.cuh"
 
@@ -90,13 +90,13 @@ struct Conv2Cfg {
     static constexpr int NBUF = 512 / ACC_COLS >= 4 ? 4 : 2;
     static constexpr int TMEM_COLS = NBUF * ACC_COLS;           // 512 / 512 / 512
     static constexpr int CH = 4;                                // k-iterations per accumulation chunk
-    // EIGHT epilogue warps: two per TMEM lane quadrant, each owning half of the tile's columns (see store_tile_rows32:
-    // one warp per scheduler made the epilogue, not the MMAs, the bound of every layer with a short K loop)
-    static constexpr int EPI_WARPS = 8;
+    // (8 epilogue warps -- two per TMEM lane quadrant, 32-channel staging, 64-byte stores -- were measured in round 2:
+    //  slower on every short-K layer, e.g. UP2 64->64 841 -> 1002 us; profiles/r02_conv_layer_bench.txt)
+    static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
-    static constexpr int NACC = BN / 2;                         // accumulators per epilogue thread (<= 128)
+    static constexpr int NACC = BN / (EPI_WARPS / 4);           // accumulators per epilogue thread (<= 128)
     static constexpr int AUX_BYTES = 256 + BN * 4;
-    static constexpr int STG_BYTES = BN <= 128 ? 8 * 4096 : 0;  // per-epilogue-warp store staging (coalesced stores)
+    static constexpr int STG_BYTES = BN <= 128 ? 4 * 8192 : 0;  // per-epilogue-warp store staging (coalesced stores)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + STG_BYTES + 1024;
 };
 
@@ -326,8 +326,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (up2) { y = 2 * y + (tc.cls >> 1); x = 2 * x + (tc.cls & 1); }
             }
             if (Cfg::STG_BYTES > 0) {
-                uint8_t* stg = aux + Cfg::AUX_BYTES + e * 4096;
-                store_tile_rows32<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
+                uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
+                store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
                                            tc.n0 + colbase);
             } else if (valid && !*abort_flag) {
 #pragma unroll

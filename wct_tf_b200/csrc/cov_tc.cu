@@ -51,7 +51,6 @@ struct CovCfg {
     static constexpr int THREADS = 320;                     // producer, MMA, 4 epilogue warps, 4 centring warps
     static constexpr int RED_BYTES = 16 * 128 * 4;          // centring warps: [16 row groups][128 channels] partial sums
     static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + RED_BYTES + 1024;
-    static constexpr int LBO = 8192, SBO = 1024;            // MN-major descriptor strides (probed on B200, profiles/r01_cov_mn_major_probe.txt)
 };
 
 __device__ __forceinline__ void tma_load_5d_cov(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
@@ -61,22 +60,6 @@ __device__ __forceinline__ void tma_load_5d_cov(void* smem_dst, const void* map,
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
         "r"(c3), "r"(c4)
         : "memory");
-}
-
-// MN-major SWIZZLE_128B operand: 64 MN elements (128 B) per row, rows = K; LBO = stride between
-// 64-wide MN groups, SBO = stride between 8-row K groups (cute::UMMA canonical layout
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((CovCfg::LBO >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((CovCfg::SBO >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(int M, int N) {
-    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(CovCfg::THREADS, 1)
