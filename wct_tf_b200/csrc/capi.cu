@@ -111,7 +111,6 @@ extern int g_conv_fuse;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
 extern int g_jacobi_stagger;
-extern int g_jacobi_impl;
 
 // kernels index elements with 32-bit arithmetic: keep every element count (incl. a 2x upsampled output) below 2^32
 static bool geom_ok(int N, int H, int W, int C) {
@@ -315,10 +314,7 @@ int wctb200_debug_set_conv_fuse(int mode) {
     return g_conv_fuse;
 }
 int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
-int wctb200_debug_set_jacobi_impl(int impl) {
-    if (impl == 1 || impl == 2) g_jacobi_impl = impl;
-    return g_jacobi_impl;
-}
+
 int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
     if (lg_groups <= 4) g_jacobi_lg = lg_groups < 0 ? -1 : lg_groups;              // negative: back to the per-size default
     g_jacobi_stagger = stagger_cycles < 0 ? -1 : stagger_cycles;

@@ -16,9 +16,6 @@ WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
 WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
 /* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4) */
 WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
-/* C = 512 eigensolver: 1 = k_jacobi<512> (columns in shared memory, one pair per warp), 2 = k_jacobi_s (default:
- * columns in registers, Gram matrix on tcgen05 + two-sided updates); returns the implementation now selected */
-WCTB200_API int wctb200_debug_set_jacobi_impl(int impl);
 #ifdef __cplusplus
 }
 #endif
