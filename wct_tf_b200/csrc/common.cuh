@@ -91,15 +91,20 @@ __device__ __forceinline__ float merge_f32(__half hi, __half lo) { return __half
 // 8 channels = one 16-byte vector per plane
 struct alignas(16) Half8 { __half2 v[4]; };
 
+// two fp32 -> (hi pair, lo pair).  cvt.rn.satfinite.f16x2.f32 (F2FP.SATFINITE.F16.F32.PACK_AB) converts, saturates to
+// +-65504 and packs two values in ONE instruction: 6 instructions per pair instead of the 11 of two clamped scalar splits
+// (the conv epilogue is instruction bound on every short-K layer, profiles/r02_ncu_conv_epilogue.txt)
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+    unsigned int h, l;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));       // a -> low half, b -> high half
+    hi = *reinterpret_cast<__half2*>(&h);
+    const float2 hf = __half22float2(hi);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(b - hf.y), "f"(a - hf.x));
+    lo = *reinterpret_cast<__half2*>(&l);
+}
 __device__ __forceinline__ void split8(const float* x, Half8& hi, Half8& lo) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __half h0, l0, h1, l1;
-        split_f32(x[2 * i], h0, l0);
-        split_f32(x[2 * i + 1], h1, l1);
-        hi.v[i] = __halves2half2(h0, h1);
-        lo.v[i] = __halves2half2(l0, l1);
-    }
+    for (int i = 0; i < 4; ++i) split2(x[2 * i], x[2 * i + 1], hi.v[i], lo.v[i]);
 }
 __device__ __forceinline__ void merge8(const Half8& hi, const Half8& lo, float* x) {
 #pragma unroll
@@ -153,6 +158,37 @@ __device__ __forceinline__ void store8_with_halo(__half* __restrict__ act, const
     }
 }
 
+// Epilogue variant: the pixel's padded position `ppos` = (n*Hp + y+1)*Wp + x+1 (fits 31 bits) and its border flags
+// (bit0: the pixel mirrors into padded row 0, bit1: into row H+1, bit2: into column 0, bit3: into column W+1) were computed
+// ONCE by the thread that owns the pixel; the 8 lanes that store its channels only add the channel offset.
+__device__ __forceinline__ int halo_flags(const ActGeom& g, int y, int x) {
+    const int m = g.edge ? 0 : 1;
+    return (y == m ? 1 : 0) | (y == g.H - 1 - m ? 2 : 0) | (x == m ? 4 : 0) | (x == g.W - 1 - m ? 8 : 0);
+}
+__device__ __forceinline__ void store8_at(__half* __restrict__ act, const ActGeom& g, unsigned int ppos, int flags, int c0,
+                                          const Half8& hi, const Half8& lo) {
+    __half* p0 = act + (long long)ppos * g.C + c0;
+    *reinterpret_cast<Half8*>(p0) = hi;
+    *reinterpret_cast<Half8*>(p0 + g.plane) = lo;
+    if (flags == 0) return;
+    // a mirrored cell sits (m+1) rows / columns beyond the pixel: reflect m = 1 -> 2 away, edge m = 0 -> 1 away
+    const int d = g.edge ? 1 : 2;
+    const long long pitch = (long long)g.Wp * g.C;
+    const long long dy[3] = {0, (flags & 1) ? -d * pitch : 0, (flags & 2) ? d * pitch : 0};
+    const long long dx[3] = {0, (flags & 4) ? -(long long)d * g.C : 0, (flags & 8) ? (long long)d * g.C : 0};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (a && dy[a] == 0) continue;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if ((b && dx[b] == 0) || (a == 0 && b == 0)) continue;
+            __half* q = p0 + dy[a] + dx[b];
+            *reinterpret_cast<Half8*>(q) = hi;
+            *reinterpret_cast<Half8*>(q + g.plane) = lo;
+        }
+    }
+}
+
 __device__ __forceinline__ void load8(const __half* __restrict__ act, const ActGeom& g, long long pos, int c0,
                                       float* x) {
     long long off = pos * g.C + c0;
@@ -173,9 +209,9 @@ __device__ __forceinline__ void load8(const __half* __restrict__ act, const ActG
 // ---------------------------------------------------------------------------
 template <int NACC>
 __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const float oscale, const float* __restrict__ sbias, bool relu,
-                                                uint8_t* __restrict__ stg, int lane, bool valid, int n, int y, int x,
+                                                uint8_t* __restrict__ stg, int lane, unsigned int ppos, int flags,
                                                 __half* __restrict__ out, const ActGeom& go, int cbase) {
-    const int packed = valid ? ((y << 16) | x) : -1;
+    // flags < 0: this thread's position is not an interior pixel (halo / junk row of the padded tiling): nothing is stored
 #pragma unroll
     for (int h = 0; h < NACC / 64; ++h) {
 #pragma unroll
@@ -197,12 +233,12 @@ __device__ __forceinline__ void store_tile_rows(const float (&acc)[NACC], const 
         for (int j = 0; j < 8; ++j) {
             const int row = j * 4 + (lane >> 3);
             const int c = lane & 7;
-            const int info = __shfl_sync(0xffffffffu, packed, row);
-            const int nn = __shfl_sync(0xffffffffu, n, row);
+            const unsigned int pp = __shfl_sync(0xffffffffu, ppos, row);
+            const int fl = __shfl_sync(0xffffffffu, flags, row);
             const int slot = c ^ (row & 7);
             const Half8 hi = *reinterpret_cast<const Half8*>(stg + (row * 8 + slot) * 16);
             const Half8 lo = *reinterpret_cast<const Half8*>(stg + 4096 + (row * 8 + slot) * 16);
-            if (info >= 0) store8_with_halo(out, go, nn, info >> 16, info & 0xffff, cbase + h * 64 + c * 8, hi, lo);
+            if (fl >= 0) store8_at(out, go, pp, fl, cbase + h * 64 + c * 8, hi, lo);
         }
         __syncwarp();
     }

@@ -259,7 +259,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int colbase = (e >> 2) * Cfg::NACC;            // BN=256: warps 6..9 take the upper half
         const int et = threadIdx.x - 64;                     // 0 .. 32*EPI_WARPS-1
         constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
-        const long long HpWp = (long long)p.Hp * p.Wp;
         const bool up2 = p.mode == CONV_UP2;
         ActGeom go(p.N, up2 ? 2 * p.H : p.H, up2 ? 2 * p.W : p.W, p.Cout);
         go.edge = (p.flags & WCTB200_HALO_EDGE) ? 1 : 0;
@@ -312,24 +311,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 if (lane == 0) mbar_arrive(&tempty[b]);      // buffer may be overwritten
             }
             // ---- store: interior pixel + the halo cells that mirror it ----
-            const long long pos = tc.p0 + g * 32 + lane;
-            bool valid = pos < tc.p_end;
-            int n = 0, y = 0, x = 0;
-            if (valid) {
-                n = (int)(pos / HpWp);
-                const int r = (int)(pos - n * HpWp);
-                const int yy = r / p.Wp;
-                const int xx = r - yy * p.Wp;
-                valid = (yy >= 1) && (yy <= p.H) && (xx >= 1) && (xx <= p.W);
-                y = yy - 1;
-                x = xx - 1;
-                if (up2) { y = 2 * y + (tc.cls >> 1); x = 2 * x + (tc.cls & 1); }
+            // (32-bit position arithmetic: P < 2^31 is checked by the launcher; 64-bit divisions cost ~60 instructions each)
+            const unsigned int pos = (unsigned int)tc.p0 + (unsigned int)(g * 32 + lane);
+            int flags = -1;                                      // < 0: nothing to store for this row
+            unsigned int ppos = 0;
+            if (pos < (unsigned int)tc.p_end) {
+                const unsigned int hpwp = (unsigned int)(p.Hp * p.Wp);
+                const unsigned int n = pos / hpwp;
+                const unsigned int r = pos - n * hpwp;
+                const int yy = (int)(r / (unsigned int)p.Wp);
+                const int xx = (int)(r - (unsigned int)yy * (unsigned int)p.Wp);
+                if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W && !*abort_flag) {
+                    int y = yy - 1, x = xx - 1;
+                    if (up2) { y = 2 * y + (tc.cls >> 1); x = 2 * x + (tc.cls & 1); }
+                    flags = halo_flags(go, y, x);
+                    ppos = ((unsigned int)n * (unsigned int)go.Hp + (unsigned int)(y + 1)) * (unsigned int)go.Wp + (unsigned int)(x + 1);
+                }
             }
             if (Cfg::STG_BYTES > 0) {
                 uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
-                store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, valid && !*abort_flag, n, y, x, p.out, go,
-                                           tc.n0 + colbase);
-            } else if (valid && !*abort_flag) {
+                store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, ppos, flags, p.out, go, tc.n0 + colbase);
+            } else if (flags >= 0) {
 #pragma unroll
                 for (int q = 0; q < Cfg::NACC / 8; ++q) {
                     float v[8];
@@ -340,7 +342,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                     Half8 hi, lo;
                     split8(v, hi, lo);
-                    store8_with_halo(p.out, go, n, y, x, tc.n0 + colbase + q * 8, hi, lo);
+                    store8_at(p.out, go, ppos, flags, tc.n0 + colbase + q * 8, hi, lo);
                 }
             }
         }
@@ -425,6 +427,7 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     WCTB_REQUIRE(nsets == 1 || (mode == CONV_APPLY && nsets == N), "conv: nsets must be 1 (or N in apply mode)");
     ActGeom gi(N, H, W, Cin);
     WCTB_REQUIRE(gi.P < (1ll << 31) - 4096, "conv: too many padded positions (%lld)", gi.P);
+    WCTB_REQUIRE(mode != CONV_UP2 || ActGeom(N, 2 * H, 2 * W, Cout).P < (1ll << 31), "conv: too many output positions");
     const int taps = mode == CONV_3X3 ? 9 : (mode == CONV_UP2 ? 4 : 1);
     const int wsets = mode == CONV_UP2 ? 4 : nsets;
 
