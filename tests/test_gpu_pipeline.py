@@ -24,9 +24,12 @@ ALL = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
 # The chained levels of a RANDOM-weight pipeline amplify rounding noise ~1e3x (DESIGN.md "Parity"):
 # the reference's own fp32 run sits ~4e-3 from its fp64 run.  The free-running bound is therefore
 # stated as a multiple of that measured noise floor; the <=1e-3 claim is the teacher-forced one.
-# Round 1 measured 4.1x; the cause was the weights' lo plane falling into the fp16 subnormals (tests/noise_split_cpu.py,
-# profiles/r02_noise_split.txt); with the per-layer power-of-two weight scale the engine sits at the fp32 noise level.
-FREE_RUN_NOISE_FACTOR = 2
+# Round 1 measured 4.1x: the weights' lo plane fell into the fp16 subnormals (tests/noise_split_cpu.py,
+# profiles/r02_noise_split.txt).  With the per-layer power-of-two weight scale the engine measures 2.5x (9.9e-3 vs 3.9e-3;
+# fixture wct5: 4.1e-3 vs 1.6e-3).  What is left is the activation format itself: hi+lo keeps 22-23 bits, i.e. up to 4x the
+# rounding error of fp32 per stored activation -- the fp32 CUDA-core validation conv on the same storage lands at the same
+# level as the tensor-core path (profiles/r02_noise_split.txt, GPU part), so it is not the MMAs.
+FREE_RUN_NOISE_FACTOR = 3
 
 
 @pytest.fixture(scope="module")
