@@ -154,16 +154,18 @@ WCTB200_API int wctb200_adain_level(const void* content, int Nc, int Hc, int Wc,
                         float alpha, float eps, void* out, void* ws, size_t ws_bytes, void* stream);
 
 /*
- * wct_style_swap (ops.py:145-217) + style_swap (ops.py:219-278) for ONE content/style pair, patch 3x3, stride 1
- * (the reference's defaults, stylize.py --ss-patch-size 3 --ss-stride 1): whiten both encodings, replace every 3x3
- * content patch by its best-correlated style patch (filters normalised per tap across patches, first arg-max,
- * overlaps averaged), colour with the style, blend with `alpha` (= --ss-alpha).  k_out (may be NULL): [k_c, k_s].
+ * wct_style_swap (ops.py:145-217) + style_swap (ops.py:219-278) for ONE content/style pair: whiten both encodings, take every
+ * patch x patch window of the whitened style at `stride` (--ss-patch-size / --ss-stride, stylize.py:33-34), replace every
+ * content window (same stride, VALID) by its best-correlated style patch (filters normalised per tap across patches, first
+ * arg-max, overlaps averaged), colour with the style, blend with `alpha` (= --ss-alpha).  The swapped encoding must tile the
+ * content encoding exactly -- (ho-1)*stride + patch == Hc -- which is what wct.py:84-90 (utils.swap_filter_fit) ensures by
+ * cropping the content image; otherwise WCTB200_EINVAL.  k_out (may be NULL): [k_c, k_s].
  * Used at relu5_1 when --swap5 is given (model.py:148-152).
  */
-WCTB200_API size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws);
+WCTB200_API size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws, int patch, int stride);
 WCTB200_API int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* style, int Hs, int Ws, int C,
-                             float alpha, float eps_cov, float thresh, void* out, int32_t* k_out, void* ws, size_t ws_bytes,
-                             void* stream);
+                             int patch, int stride, float alpha, float eps_cov, float thresh, void* out, int32_t* k_out,
+                             void* ws, size_t ws_bytes, void* stream);
 
 /* Stand-alone pieces of the transform, exposed for parity tests and profiling:
  * per-channel mean [N][C] and covariance [N][C][C] = fc fc^T/(HW-1) + eps_cov*I of a feature batch

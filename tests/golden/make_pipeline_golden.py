@@ -1,6 +1,6 @@
 """Generate tests/golden/pipeline_*.npz with the REFERENCE's own inference code (build container only).
 
-  python tests/golden/make_pipeline_golden.py
+  python tests/golden/make_pipeline_golden.py [case name ...]
 
 The reference's model.py (WCTModel graph, build_decoder), ops.py (wct_tf, adain, pad_reflect,
 Conv2DReflect), vgg_normalised.py (vgg_from_t7) and torchfile.py are imported UNMODIFIED from
@@ -31,12 +31,15 @@ from wct_tf_b200 import weights as W  # noqa: E402
 
 ALL = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
 CASES = [
-    # name, relu_targets, content HxW, style HxW, alpha, adain, seed, swap5 (ss_alpha)
+    # name, relu_targets, content HxW, style HxW, alpha, adain, seed, swap5: None | ss_alpha | (ss_alpha, ss_patch_size, ss_stride)
     ("wct5_a06", ALL, (48, 64), (64, 48), 0.6, False, 11, None),
     ("wct_21_41_a10", ["relu2_1", "relu4_1"], (40, 56), (48, 48), 1.0, False, 12, None),     # any order / subset (README.md:46)
     ("wct_31_11_odd_a08", ["relu3_1", "relu1_1"], (37, 45), (41, 50), 0.8, False, 13, None),  # odd sizes: pool 'same' + upsample grow the frame
     ("adain4_a07", ALL[1:], (48, 48), (40, 56), 0.7, True, 14, None),
     ("swap5_51_31_a08", ["relu5_1", "relu3_1"], (96, 112), (112, 96), 0.8, False, 15, 0.6),   # --swap5: style swap at relu5_1 (ops.py:145-278), WCT at relu3_1
+    # --ss-patch-size 5 --ss-stride 2: the 9x11 relu5_1 encoding of a 144x176 frame is tiled exactly ((4-1)*2+5 = 11, (3-1)*2+5 = 9),
+    # i.e. the size utils.swap_filter_fit would crop to; 4 x 3 style patches
+    ("swap5_p5s2_51_21_a07", ["relu5_1", "relu2_1"], (144, 176), (176, 144), 0.7, False, 16, (0.6, 5, 2)),
 ]
 
 
@@ -53,8 +56,16 @@ def weight_checksum(w):
 def main():
     tmp = tempfile.mkdtemp()
     with np_tf1.reference_modules() as ref:
+        only = set(sys.argv[1:])                                   # optional: regenerate just the named cases
         for name, targets, hwc, hws, alpha, adain, seed, ss in CASES:
-            swap = dict(swap5=True, ss_alpha=ss) if ss is not None else {}
+            if only and name not in only:
+                continue
+            if ss is None:
+                swap = {}
+            elif isinstance(ss, tuple):
+                swap = dict(swap5=True, ss_alpha=ss[0], ss_patch_size=ss[1], ss_stride=ss[2])
+            else:
+                swap = dict(swap5=True, ss_alpha=ss)
             w = W.make_synthetic_weights(seed, relu_targets=targets)
             t7 = os.path.join(tmp, name + ".t7")
             write_vgg_t7(t7, w["vgg"])
@@ -77,7 +88,8 @@ def main():
                         assert inf["margin"].min() > 1e-3, (name, float(inf["margin"].min()))
             arrays = dict(content=content, style=style, alpha=np.float64(alpha), adain=np.bool_(adain), seed=np.int64(seed),
                           relu_targets=np.array(targets), out_ref_fp64=out64, out_ref_fp32=out32, wsum=np.float64(weight_checksum(w)),
-                          swap5=np.bool_(ss is not None), ss_alpha=np.float64(ss if ss is not None else 0.6),
+                          swap5=np.bool_(ss is not None), ss_alpha=np.float64(swap.get("ss_alpha", 0.6)),
+                          ss_patch_size=np.int64(swap.get("ss_patch_size", 3)), ss_stride=np.int64(swap.get("ss_stride", 1)),
                           k=np.array(ks, dtype=np.int64).reshape(-1, 2))
             for i, (enc, dec_in, decoded) in enumerate(lv64):
                 arrays["lvl%d_decoder_input" % i] = dec_in.astype(np.float32)

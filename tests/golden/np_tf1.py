@@ -364,13 +364,15 @@ def reference_modules():
                 sys.modules[k] = v
 
 
-def run_reference(ref, content01, style01, vgg_t7, decoder_weights, relu_targets, alpha, adain, dtype, swap5=False, ss_alpha=0.6):
+def run_reference(ref, content01, style01, vgg_t7, decoder_weights, relu_targets, alpha, adain, dtype, swap5=False, ss_alpha=0.6,
+                  ss_patch_size=3, ss_stride=1):
     """Build (= eagerly evaluate) the reference's WCTModel in test mode exactly as wct.py:31-32 does and return
     (decoded_output of model.py:94, [per-level (content_encoded, decoder_input, decoded)])."""
     import io
     STATE.update(dtype=dtype, feeds={"content_imgs": content01, "style_img": style01, "alpha": alpha, "ss_alpha": ss_alpha},
                  unnamed=[np.bool_(bool(swap5)), np.bool_(bool(adain))], weights=decoder_weights)
     with contextlib.redirect_stdout(io.StringIO()):
-        m = ref.model.WCTModel(mode="test", relu_targets=list(relu_targets), vgg_path=vgg_t7)
+        m = ref.model.WCTModel(mode="test", relu_targets=list(relu_targets), vgg_path=vgg_t7,
+                               ss_patch_size=ss_patch_size, ss_stride=ss_stride)        # build kwargs, as wct.py:33-36 passes them
     levels = [(np.asarray(e.content_encoded), np.asarray(e.decoder_input), np.asarray(e.decoded)) for e in m.encoder_decoders]
     return np.asarray(m.decoded_output), levels

@@ -164,8 +164,9 @@ def test_engine_vs_reference_code_golden(path):
     alpha, adain = float(g["alpha"]), bool(g["adain"])
     eng = Engine(w, targets, semantics="tf")
     cap = {}
+    from tests.test_oracle import swap_kwargs
     out = eng.stylize(torch.from_numpy(g["content"][None]).cuda(), torch.from_numpy(g["style"][None]).cuda(), alpha=alpha,
-                      adain=adain, want_info=True, capture=cap, swap5=bool(g["swap5"]), ss_alpha=float(g["ss_alpha"]))
+                      adain=adain, want_info=True, capture=cap, **swap_kwargs(g))
     eng.check_device()
     got = out.cpu().numpy()
     assert got.shape == g["out_ref_fp64"].shape
@@ -210,10 +211,19 @@ def test_wct_predict_surface(weights):
     assert diff.max() <= 1                                            # 1e-3 float error may flip a u8 LSB
     # --swap5 only acts at relu5_1 (model.py:144-158): without that target it changes nothing ...
     assert np.array_equal(wct.predict(c, s, alpha=0.6, swap5=True, ss_alpha=0.5), out)
-    # ... and only the reference's default patch 3 / stride 1 is built
-    wct2 = WCT(checkpoints=None, relu_targets=["relu2_1", "relu1_1"], vgg_path=None, device="/gpu:0", weights=weights, ss_stride=2)
-    with pytest.raises(NotImplementedError):
-        wct2.predict(c, s, swap5=True)
+    # ... while with relu5_1 and a stride the content is centre-cropped to a size the patches tile (wct.py:84-90,
+    # utils.swap_filter_fit): 80x112 -> relu5_1 encoding 5x7; patch 3 / stride 2 tiles 5x7; 96x112 (6x7) is cropped to 80x112
+    from wct_tf_b200.imageio import swap_filter_fit
+    assert swap_filter_fit(96, 112, 3, 2) == (True, 80, 112) and swap_filter_fit(80, 112, 3, 2) == (False, 80, 112)
+    t5 = ["relu5_1", "relu1_1"]
+    w5 = make_synthetic_weights(15, relu_targets=t5)
+    wct2 = WCT(checkpoints=None, relu_targets=t5, vgg_path=None, device="/gpu:0", weights=w5, ss_patch_size=3, ss_stride=2)
+    c2, s2 = _imgs(1, 112, 3)[0][:96], _imgs(1, 112, 4)[0]
+    o2 = wct2.predict(c2, s2, alpha=0.7, swap5=True, ss_alpha=0.6)
+    assert o2.shape == (80, 112, 3)
+    crop = c2[8:88]                                                    # centre crop of the 96 rows to 80
+    r2 = nets.pipeline(crop, s2, w5, t5, alpha=0.7, semantics="tf", dtype=np.float64, swap5=True, ss_alpha=0.6, ss_patch_size=3, ss_stride=2)
+    assert r2.shape[1:3] == (80, 112)
     out2 = wct.predict(c, s, alpha=0.6, adain=True)
     ref2 = nets.pipeline(c, s, weights, ["relu2_1", "relu1_1"], alpha=0.6, adain=True, dtype=np.float64)
     assert np.abs(out2.astype(int) - nets.postprocess(ref2[0]).astype(int)).max() <= 1

@@ -197,13 +197,19 @@ def test_jacobi_rank_deficient_null_space_stays_below_threshold():
     assert np.abs(sg[:k_ref] - w[:k_ref]).max() <= 4e-5 * w[0]
 
 
-@pytest.mark.parametrize("case", [(64, (9, 11), (8, 12), 0.6, 5), (128, (12, 12), (13, 11), 1.0, 6), (512, (6, 7), (7, 6), 0.6, 7)],
-                         ids=lambda c: "C%d" % c[0])
+@pytest.mark.parametrize("case", [
+    # C, content HxW, style HxW, alpha, seed, patch, stride   (the swapped encoding must tile the content: (ho-1)*stride + patch == H)
+    (64, (9, 11), (8, 12), 0.6, 5, 3, 1), (128, (12, 12), (13, 11), 1.0, 6, 3, 1), (512, (6, 7), (7, 6), 0.6, 7, 3, 1),
+    (64, (9, 11), (11, 9), 0.6, 8, 5, 2),        # --ss-patch-size 5 --ss-stride 2
+    (128, (9, 7), (10, 8), 0.7, 9, 3, 2),        # stride 2
+    (64, (8, 10), (9, 9), 0.5, 10, 4, 1),        # even patch, stride 1
+    (64, (7, 9), (8, 8), 0.6, 11, 1, 1),         # 1x1 patches
+], ids=lambda c: "C%d_p%ds%d" % (c[0], c[5], c[6]))
 def test_style_swap_level_matches_oracle(case):
     """wctb200_style_swap_level vs the NumPy restatement of ops.py:145-278 (itself pinned to the reference's own code by
     tests/golden/pipeline_swap5_*.npz).  The arg-max is discrete, so the vector must decide every position by a clear
     margin (asserted on the fp64 oracle), and then the matched patch indices must be identical."""
-    C, hwc, hws, alpha, seed = case
+    C, hwc, hws, alpha, seed, patch, stride = case
     rng = np.random.default_rng(seed)
 
     def feat(hw):
@@ -212,22 +218,24 @@ def test_style_swap_level_matches_oracle(case):
 
     content, style = feat(hwc), feat(hws)
     ref, info = ref_ops.wct_style_swap(U.split_repr(content).astype(np.float64), U.split_repr(style).astype(np.float64), alpha,
-                                       return_info=True)
+                                       patch_size=patch, stride=stride, return_info=True)
     assert ref_ops.spectral_gap_ok(info["wc"]) and ref_ops.spectral_gap_ok(info["ws"]), "ill-posed vector (eigenvalue near the cut)"
     assert info["margin"].min() > 2e-3, "ill-posed vector (arg-max decided by %.1e)" % info["margin"].min()
     cin, sin = U.act_from_numpy(content), U.act_from_numpy(style)
     out = U.act_alloc(1, hwc[0], hwc[1], C)
-    nbytes = U.lib().wctb200_style_swap_workspace_bytes(C, hwc[0], hwc[1], hws[0], hws[1])
+    nbytes = U.lib().wctb200_style_swap_workspace_bytes(C, hwc[0], hwc[1], hws[0], hws[1], patch, stride)
     assert nbytes > 0
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     kbuf = torch.zeros(2, dtype=torch.int32, device="cuda")
-    _capi.check(U.lib().wctb200_style_swap_level(cin.data_ptr(), hwc[0], hwc[1], sin.data_ptr(), hws[0], hws[1], C, alpha, 1e-8,
-                                                 1e-5, out.data_ptr(), kbuf.data_ptr(), ws.data_ptr(), ws.numel(), U.stream()))
+    _capi.check(U.lib().wctb200_style_swap_level(cin.data_ptr(), hwc[0], hwc[1], sin.data_ptr(), hws[0], hws[1], C, patch, stride,
+                                                 alpha, 1e-8, 1e-5, out.data_ptr(), kbuf.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                 U.stream()))
     U.check_device()
     got = U.act_to_numpy(out, 1, hwc[0], hwc[1], C)
     assert tuple(kbuf.cpu().tolist()) == (info["k_c"], info["k_s"])
     err = np.abs(got - ref).max()
-    print("style swap C=%d: max-abs vs fp64 oracle %.2e (k %d/%d, min arg-max margin %.1e)" % (C, err, info["k_c"], info["k_s"], info["margin"].min()))
+    print("style swap C=%d patch %d stride %d: max-abs vs fp64 oracle %.2e (k %d/%d, min arg-max margin %.1e)"
+          % (C, patch, stride, err, info["k_c"], info["k_s"], info["margin"].min()))
     assert err <= 1e-3
     padded = U.act_raw_padded(out, 1, hwc[0], hwc[1], C)
     assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))

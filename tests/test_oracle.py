@@ -101,6 +101,14 @@ def load_pipeline_fixture(path):
     return g, targets, w
 
 
+def swap_kwargs(g):
+    """--swap5 arguments of a fixture (older fixtures carry no patch / stride: the reference's defaults 3 / 1)."""
+    kw = dict(swap5=bool(g["swap5"]), ss_alpha=float(g["ss_alpha"]))
+    if "ss_patch_size" in g.files:
+        kw.update(ss_patch_size=int(g["ss_patch_size"]), ss_stride=int(g["ss_stride"]))
+    return kw
+
+
 def test_pipeline_golden_present():
     assert len(PIPE_GOLDEN) >= 5
 
@@ -110,7 +118,7 @@ def test_oracle_pipeline_matches_reference_code_fixture(path):
     """oracle.nets.pipeline (encoder + wct_tf | adain + decoder + level wiring) == the reference's WCTModel code."""
     g, targets, w = load_pipeline_fixture(path)
     alpha, adain = float(g["alpha"]), bool(g["adain"])
-    swap = dict(swap5=bool(g["swap5"]), ss_alpha=float(g["ss_alpha"]))
+    swap = swap_kwargs(g)
     o64, info = nets.pipeline(g["content"], g["style"], w, targets, alpha=alpha, adain=adain, semantics="tf",
                               dtype=np.float64, return_info=True, **swap)
     assert o64.shape == g["out_ref_fp64"].shape

@@ -43,8 +43,8 @@ SIGNATURES = {
     "wctb200_adain_level": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "wctb200_covariance": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "wctb200_jacobi_eigh": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
-    "wctb200_style_swap_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "wctb200_style_swap_level": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "wctb200_style_swap_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "wctb200_style_swap_level": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
 }
 
 # tuning / probe hooks (wct_tf_b200/csrc/wctb200_debug.h): NOT part of the ABI, bound for tools/ and tests/ only

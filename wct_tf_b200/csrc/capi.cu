@@ -85,9 +85,10 @@ int launch_act_from_f32(const float*, ActGeom, __half*, cudaStream_t);
 int launch_act_to_f32(const __half*, ActGeom, float*, cudaStream_t);
 int launch_prep_weights(const float*, int, int, int, __half*, cudaStream_t);
 int launch_prep_weights_up2(const float*, int, int, __half*, cudaStream_t);
-size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws);
-int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, float alpha, float eps_cov,
-                            float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws, int P, int S);
+int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, int patch, int stride,
+                            float alpha, float eps_cov, float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes,
+                            cudaStream_t st);
 int launch_conv3x3_ref(const __half*, ActGeom, const float*, const float*, int, int, __half*, cudaStream_t);
 int launch_conv_head(const float*, int, int, int, const float*, const float*, __half*, cudaStream_t);
 int launch_conv_tail(const __half*, ActGeom, const float*, const float*, int, float*, cudaStream_t);
@@ -289,16 +290,19 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     return rc;
 }
 
-size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws) {
-    if (!geom_ok(1, Hc, Wc, C) || !geom_ok(1, Hs, Ws, C) || Hc < 3 || Wc < 3 || Hs < 3 || Ws < 3) return 0;
-    return style_swap_workspace_bytes(C, Hc, Wc, Hs, Ws);
+size_t wctb200_style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws, int patch, int stride) {
+    if (!geom_ok(1, Hc, Wc, C) || !geom_ok(1, Hs, Ws, C) || patch < 1 || patch > 16 || stride < 1 || stride > 16 || Hc < patch ||
+        Wc < patch || Hs < patch || Ws < patch)
+        return 0;
+    return style_swap_workspace_bytes(C, Hc, Wc, Hs, Ws, patch, stride);
 }
-int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* style, int Hs, int Ws, int C, float alpha,
-                             float eps_cov, float thresh, void* out, int32_t* k_out, void* ws, size_t ws_bytes, void* stream) {
+int wctb200_style_swap_level(const void* content, int Hc, int Wc, const void* style, int Hs, int Ws, int C, int patch, int stride,
+                             float alpha, float eps_cov, float thresh, void* out, int32_t* k_out, void* ws, size_t ws_bytes,
+                             void* stream) {
     WCTB_REQUIRE(content && style && out && ws, "style_swap_level: null pointer");
     WCTB_REQUIRE(geom_ok(1, Hc, Wc, C) && geom_ok(1, Hs, Ws, C), "style_swap_level: bad geometry");
-    return launch_style_swap_level(HCP(content), Hc, Wc, HCP(style), Hs, Ws, C, alpha, eps_cov, thresh, HP(out), k_out, ws, ws_bytes,
-                                   ST(stream));
+    return launch_style_swap_level(HCP(content), Hc, Wc, HCP(style), Hs, Ws, C, patch, stride, alpha, eps_cov, thresh, HP(out), k_out, ws,
+                                   ws_bytes, ST(stream));
 }
 // tuning hooks (wctb200_debug.h; not part of the stable ABI)
 int wctb200_debug_set_conv_bn(int bn) {

@@ -47,7 +47,8 @@ struct ConvParams {
     int N, H, W, Cin, Cout, Hp, Wp;   // INPUT geometry (UP2: the low-resolution tensor)
     long long P;
     int mode;             // ConvMode
-    int taps;             // 9 (3x3), 1 (apply), 4 (up2: per output parity)
+    int taps;             // 9 (3x3), 1 (apply), 4 (up2: per output parity), kw*kw (taps)
+    int kw;               // CONV_TAPS: filter width (top-left anchored kw x kw correlation, style-swap patches)
     int per_image;        // tiles never straddle images; weight/bias set = image index (APPLY with nsets > 1)
     int nsets;
     int tiles_per_image;
@@ -195,6 +196,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const int ks = it - tap * ksl;
                     int off = 0;
                     if (p.mode == CONV_3X3) off = (tap / 3 - 1) * p.Wp + (tap % 3 - 1);
+                    else if (p.mode == CONV_TAPS) off = (tap / p.kw) * p.Wp + (tap % p.kw);
                     else if (p.mode == CONV_UP2) off = ((tap >> 1) - 1 + (tc.cls >> 1)) * p.Wp + ((tap & 1) - 1 + (tc.cls & 1));
                     const int row = (int)(tc.p0 + off);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
@@ -419,16 +421,18 @@ int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
 // mode CONV_3X3  : in [N,H,W,Cin], w_split [2][Cout][9*Cin],          out [N,H,W,Cout]
 // mode CONV_APPLY: in [N,H,W,Cin], w_split [nsets][2][Cout][Cin],     out [N,H,W,Cout]   (per-image weight sets)
 // mode CONV_UP2  : in [N,H,W,Cin] (edge halo), w_split [4][2][Cout][4*Cin], out [N,2H,2W,Cout]
+// mode CONV_TAPS : in [N,H,W,Cin], w_split [2][Cout][kw*kw*Cin],      out [N,H,W,Cout]: top-left anchored kw x kw correlation
 int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, const __half* w_split, int nsets,
-                   const float* wscale, const float* bias, int Cout, int flags, __half* out, cudaStream_t st) {
+                   const float* wscale, const float* bias, int Cout, int flags, __half* out, cudaStream_t st, int kw) {
     WCTB_REQUIRE(N >= 1 && H >= 2 && W >= 2, "conv: bad geometry N=%d H=%d W=%d", N, H, W);
     WCTB_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && Cin >= 64 && Cout >= 64, "conv: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
-    WCTB_REQUIRE(mode == CONV_3X3 || mode == CONV_APPLY || mode == CONV_UP2, "conv: bad mode %d", mode);
+    WCTB_REQUIRE(mode == CONV_3X3 || mode == CONV_APPLY || mode == CONV_UP2 || mode == CONV_TAPS, "conv: bad mode %d", mode);
+    WCTB_REQUIRE(mode != CONV_TAPS || (kw >= 1 && kw <= 16), "conv: bad filter width %d", kw);
     WCTB_REQUIRE(nsets == 1 || (mode == CONV_APPLY && nsets == N), "conv: nsets must be 1 (or N in apply mode)");
     ActGeom gi(N, H, W, Cin);
     WCTB_REQUIRE(gi.P < (1ll << 31) - 4096, "conv: too many padded positions (%lld)", gi.P);
     WCTB_REQUIRE(mode != CONV_UP2 || ActGeom(N, 2 * H, 2 * W, Cout).P < (1ll << 31), "conv: too many output positions");
-    const int taps = mode == CONV_3X3 ? 9 : (mode == CONV_UP2 ? 4 : 1);
+    const int taps = mode == CONV_3X3 ? 9 : (mode == CONV_UP2 ? 4 : (mode == CONV_TAPS ? kw * kw : 1));
     const int wsets = mode == CONV_UP2 ? 4 : nsets;
 
     int BN = Cout % 128 == 0 ? 128 : 64;   // 256-wide tiles leave only 2 pipeline stages: measured slower
@@ -445,6 +449,7 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Hp = gi.Hp; p.Wp = gi.Wp; p.P = gi.P;
     p.mode = mode;
     p.taps = taps;
+    p.kw = kw;
     p.nsets = nsets;
     p.per_image = nsets > 1 ? 1 : 0;
     p.tiles_per_image = cdiv((long long)gi.Hp * gi.Wp, 128);

@@ -928,13 +928,17 @@ static inline int swap_grid(long long total, int block) {
 
 struct SwapWs {
     size_t base, zeros, dvec2, sigma2, mats, msplit, bias3, norms, idx, wc_feat, ws_feat, ss_feat, tmp, scores, wsplit, total;
-    int cout_pad, n_patches;
+    int cout_pad, n_patches, prow, pcol, ho, wo;   // style patch grid prow x pcol, content score grid ho x wo
 };
-static SwapWs swap_layout(int C, int Hc, int Wc, int Hs, int Ws) {
+static SwapWs swap_layout(int C, int Hc, int Wc, int Hs, int Ws, int P, int S) {
     SwapWs L;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    L.n_patches = (Hs - 2) * (Ws - 2);
+    L.prow = (Hs - P) / S + 1;                                    // tf.extract_image_patches, VALID (ops.py:226)
+    L.pcol = (Ws - P) / S + 1;
+    L.ho = (Hc - P) / S + 1;                                      // tf.nn.conv2d VALID with the same stride (ops.py:236-239)
+    L.wo = (Wc - P) / S + 1;
+    L.n_patches = L.prow * L.pcol;
     L.cout_pad = (L.n_patches + 63) / 64 * 64;
     L.base = take(wct_layout(C, 1, 1).total);
     L.zeros = take((size_t)C * 4);
@@ -943,46 +947,49 @@ static SwapWs swap_layout(int C, int Hc, int Wc, int Hs, int Ws) {
     L.mats = take((size_t)3 * C * C * 4);                         // W_c, W_s (whitening), C_s (colouring)
     L.msplit = take((size_t)3 * 2 * C * C * 2);
     L.bias3 = take((size_t)3 * C * 4);
-    L.norms = take((size_t)9 * C * 4);
-    L.idx = take((size_t)(Hc - 2) * (Wc - 2) * 4);
+    L.norms = take((size_t)P * P * C * 4);
+    L.idx = take((size_t)L.ho * L.wo * 4);
     const size_t fc = (size_t)ActGeom(1, Hc, Wc, C).plane * 2 * sizeof(__half), fs = (size_t)ActGeom(1, Hs, Ws, C).plane * 2 * sizeof(__half);
     L.wc_feat = take(fc);
     L.ws_feat = take(fs);
     L.ss_feat = take(fc);
     L.tmp = take(fc);
     L.scores = take((size_t)ActGeom(1, Hc, Wc, L.cout_pad).plane * 2 * sizeof(__half));
-    L.wsplit = take((size_t)2 * 9 * C * L.cout_pad * sizeof(__half));
+    L.wsplit = take((size_t)2 * P * P * C * L.cout_pad * sizeof(__half));
     L.total = o;
     return L;
 }
-size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws) { return swap_layout(C, Hc, Wc, Hs, Ws).total; }
+size_t style_swap_workspace_bytes(int C, int Hc, int Wc, int Hs, int Ws, int P, int S) { return swap_layout(C, Hc, Wc, Hs, Ws, P, S).total; }
+
+// patch geometry of the swap: P x P patches taken every S pixels (ops.py:219-278: --ss-patch-size, --ss-stride)
+struct SwapGeom { int P, S, prow, pcol, ho, wo; };
 
 // 1 / ||patch tap||: for every (tap, channel) the l2 norm ACROSS all patches (ops.py:233); block = (tap, 256 channels)
-__global__ void k_swap_tap_norms(const __half* __restrict__ feat, ActGeom g, float* __restrict__ inv_norm) {
+__global__ void k_swap_tap_norms(const __half* __restrict__ feat, ActGeom g, SwapGeom q, float* __restrict__ inv_norm) {
     const int tap = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.C) return;
-    const int ky = tap / 3, kx = tap % 3;
+    const int ky = tap / q.P, kx = tap % q.P;
     float s = 0.f;
-    for (int sy = 0; sy < g.H - 2; ++sy)
-        for (int sx = 0; sx < g.W - 2; ++sx) {
-            const long long pos = ((long long)(sy + ky + 1)) * g.Wp + (sx + kx + 1);      // interior pixel -> padded position
+    for (int py = 0; py < q.prow; ++py)
+        for (int px = 0; px < q.pcol; ++px) {
+            const long long pos = ((long long)(py * q.S + ky + 1)) * g.Wp + (px * q.S + kx + 1);      // interior pixel -> padded position
             const float v = merge_f32(feat[pos * g.C + c], feat[g.plane + pos * g.C + c]);
             s = fmaf(v, v, s);
         }
     inv_norm[tap * g.C + c] = rsqrtf(fmaxf(s, 1e-12f));
 }
-// conv weights of the correlation: [plane][patch n][tap*C + c] = whitened_style[sy+ky][sx+kx][c] * inv_norm[tap][c]; rows >= n_patches zero
-__global__ void k_swap_patch_weights(const __half* __restrict__ feat, ActGeom g, const float* __restrict__ inv_norm,
+// conv weights of the correlation: [plane][patch n][tap*C + c] = whitened_style[py*S+ky][px*S+kx][c] * inv_norm[tap][c]; rows >= n_patches zero
+__global__ void k_swap_patch_weights(const __half* __restrict__ feat, ActGeom g, SwapGeom q, const float* __restrict__ inv_norm,
                                      int n_patches, int cout_pad, __half* __restrict__ wsplit) {
-    const long long K = 9ll * g.C, total = K * cout_pad;
+    const long long K = (long long)q.P * q.P * g.C, total = K * cout_pad;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / K);
         const int k = (int)(i - (long long)n * K);
         float v = 0.f;
         if (n < n_patches) {
             const int tap = k / g.C, c = k - tap * g.C;
-            const int sy = n / (g.W - 2), sx = n - sy * (g.W - 2);
-            const long long pos = ((long long)(sy + tap / 3 + 1)) * g.Wp + (sx + tap % 3 + 1);
+            const int py = n / q.pcol, px = n - py * q.pcol;
+            const long long pos = ((long long)(py * q.S + tap / q.P + 1)) * g.Wp + (px * q.S + tap % q.P + 1);
             v = merge_f32(feat[pos * g.C + c], feat[g.plane + pos * g.C + c]) * inv_norm[k];
         }
         __half hi, lo;
@@ -991,13 +998,13 @@ __global__ void k_swap_patch_weights(const __half* __restrict__ feat, ActGeom g,
         wsplit[total + i] = lo;
     }
 }
-// first arg-max over the patch axis for every VALID position (y,x): the SAME-conv output at interior pixel (y+1, x+1)
-__global__ void k_swap_argmax(const __half* __restrict__ scores, ActGeom g, int n_patches, int* __restrict__ idx) {
+// first arg-max over the patch axis for every VALID strided position (y,x): the top-left-anchored P x P correlation
+// at interior pixel (y*S, x*S), which the conv kernel stored at that pixel's own padded cell
+__global__ void k_swap_argmax(const __half* __restrict__ scores, ActGeom g, SwapGeom q, int n_patches, int* __restrict__ idx) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int wo = g.W - 2, ho = g.H - 2;
-    if (warp >= ho * wo) return;
-    const int y = warp / wo, x = warp - y * wo;
-    const long long pos = ((long long)(y + 2)) * g.Wp + (x + 2);
+    if (warp >= q.ho * q.wo) return;
+    const int y = warp / q.wo, x = warp - y * q.wo;
+    const long long pos = ((long long)(y * q.S + 1)) * g.Wp + (x * q.S + 1);
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int n = lane; n < n_patches; n += 32) {
@@ -1012,9 +1019,10 @@ __global__ void k_swap_argmax(const __half* __restrict__ scores, ActGeom g, int 
     }
     if (lane == 0) idx[warp] = bi;
 }
-// conv2d_transpose of the one-hot map with the raw patches, divided by the overlap count: output pixel (Y,X) averages,
-// over the <= 9 patch positions (Y-dy, X-dx) that cover it, the style pixel (sy+dy, sx+dx) of the matched patch
-__global__ void k_swap_gather(const __half* __restrict__ sfeat, ActGeom gs, const int* __restrict__ idx, ActGeom gc,
+// conv2d_transpose of the one-hot map with the raw patches, divided by the overlap count (ops.py:255-276): output pixel
+// (Y,X) averages, over the <= P*P patch positions (py,px) with py*S + dy = Y, px*S + dx = X that cover it, the style
+// pixel (sy*S + dy, sx*S + dx) of the matched patch.  The caller guarantees (ho-1)*S + P == H (wct.py:84-90 refits).
+__global__ void k_swap_gather(const __half* __restrict__ sfeat, ActGeom gs, SwapGeom q, const int* __restrict__ idx, ActGeom gc,
                               __half* __restrict__ out) {
     const int cg = gc.C / 8;
     const long long total = (long long)gc.H * gc.W * cg;
@@ -1026,22 +1034,22 @@ __global__ void k_swap_gather(const __half* __restrict__ sfeat, ActGeom gs, cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         int cnt = 0;
-        for (int dy = 0; dy < 3; ++dy) {
-            const int py = Y - dy;
-            if (py < 0 || py >= gc.H - 2) continue;
-            for (int dx = 0; dx < 3; ++dx) {
-                const int px = X - dx;
-                if (px < 0 || px >= gc.W - 2) continue;
-                const int n = idx[py * (gc.W - 2) + px];
-                const int sy = n / (gs.W - 2), sx = n - sy * (gs.W - 2);
+        for (int dy = 0; dy < q.P; ++dy) {
+            const int ty = Y - dy;
+            if (ty < 0 || ty % q.S != 0 || ty / q.S >= q.ho) continue;
+            for (int dx = 0; dx < q.P; ++dx) {
+                const int tx = X - dx;
+                if (tx < 0 || tx % q.S != 0 || tx / q.S >= q.wo) continue;
+                const int n = idx[(ty / q.S) * q.wo + tx / q.S];
+                const int sy = n / q.pcol, sx = n - sy * q.pcol;
                 float v[8];
-                load8(sfeat, gs, ((long long)(sy + dy + 1)) * gs.Wp + (sx + dx + 1), c0, v);
+                load8(sfeat, gs, ((long long)(sy * q.S + dy + 1)) * gs.Wp + (sx * q.S + dx + 1), c0, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[j] += v[j];
                 ++cnt;
             }
         }
-        const float inv = 1.f / (float)cnt;
+        const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] *= inv;
         Half8 hi, lo;
@@ -1072,11 +1080,20 @@ __global__ void k_blend2(const __half* __restrict__ x, const __half* __restrict_
     }
 }
 
-int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, float alpha,
-                            float eps_cov, float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half* style, int Hs, int Ws, int C, int patch, int stride,
+                            float alpha, float eps_cov, float thresh, __half* out, int32_t* k_out, void* ws, size_t ws_bytes,
+                            cudaStream_t st) {
     WCTB_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "style_swap: C=%d not in {64,128,256,512}", C);
-    WCTB_REQUIRE(Hc >= 3 && Wc >= 3 && Hs >= 3 && Ws >= 3, "style_swap: maps must be at least 3x3 (content %dx%d, style %dx%d)", Hc, Wc, Hs, Ws);
-    const SwapWs S = swap_layout(C, Hc, Wc, Hs, Ws);
+    WCTB_REQUIRE(patch >= 1 && patch <= 16 && stride >= 1 && stride <= 16, "style_swap: patch %d / stride %d out of range", patch, stride);
+    WCTB_REQUIRE(Hc >= patch && Wc >= patch && Hs >= patch && Ws >= patch && Hc >= 2 && Wc >= 2 && Hs >= 2 && Ws >= 2,
+                 "style_swap: maps must be at least %dx%d (content %dx%d, style %dx%d)", patch, patch, Hc, Wc, Hs, Ws);
+    const SwapWs S = swap_layout(C, Hc, Wc, Hs, Ws, patch, stride);
+    // the swapped encoding must have the content's size (ops.py:199 reshapes it to [Hc*Wc, C]); wct.py:84-90 crops the content
+    // image beforehand when the stride makes the filter not fit (utils.swap_filter_fit)
+    WCTB_REQUIRE((S.ho - 1) * stride + patch == Hc && (S.wo - 1) * stride + patch == Wc,
+                 "style_swap: patch %d / stride %d does not tile a %dx%d encoding (refit the content: swap_filter_fit, wct.py:84-90)",
+                 patch, stride, Hc, Wc);
+    const SwapGeom q = {patch, stride, S.prow, S.pcol, S.ho, S.wo};
     if (ws_bytes < S.total) {
         set_error("style_swap: workspace %zu < %zu bytes", ws_bytes, S.total);
         return WCTB200_EWS;
@@ -1137,16 +1154,19 @@ int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half*
     if (rc) return rc;
     rc = launch_conv_tc(CONV_APPLY, style, 1, Hs, Ws, C, msplit + 2 * CC, 1, nullptr, bias3 + C, C, 0, ws_feat, st);
     if (rc) return rc;
-    k_swap_tap_norms<<<dim3((unsigned)cdiv(C, 256), 9), 256, 0, st>>>(ws_feat, gs, norms);
+    k_swap_tap_norms<<<dim3((unsigned)cdiv(C, 256), (unsigned)(patch * patch)), 256, 0, st>>>(ws_feat, gs, q, norms);
     WCTB_CHECK_LAUNCH("k_swap_tap_norms");
-    k_swap_patch_weights<<<swap_grid(9ll * C * S.cout_pad, 256), 256, 0, st>>>(ws_feat, gs, norms, S.n_patches, S.cout_pad, wsplit);
+    k_swap_patch_weights<<<swap_grid((long long)patch * patch * C * S.cout_pad, 256), 256, 0, st>>>(ws_feat, gs, q, norms, S.n_patches,
+                                                                                                  S.cout_pad, wsplit);
     WCTB_CHECK_LAUNCH("k_swap_patch_weights");
-    rc = launch_conv_tc(CONV_3X3, wc_feat, 1, Hc, Wc, C, wsplit, 1, nullptr, nullptr, S.cout_pad, 0, scores, st);
+    // every style patch is a filter: the P x P correlation (top-left anchored, all positions; the strided VALID subset is
+    // read by the arg-max) runs on the tensor-core conv kernel
+    rc = launch_conv_tc(CONV_TAPS, wc_feat, 1, Hc, Wc, C, wsplit, 1, nullptr, nullptr, S.cout_pad, 0, scores, st, patch);
     if (rc) return rc;
-    const int npos = (Hc - 2) * (Wc - 2);
-    k_swap_argmax<<<(unsigned)cdiv((long long)npos * 32, 256), 256, 0, st>>>(scores, ActGeom(1, Hc, Wc, S.cout_pad), S.n_patches, idx);
+    const int npos = S.ho * S.wo;
+    k_swap_argmax<<<(unsigned)cdiv((long long)npos * 32, 256), 256, 0, st>>>(scores, ActGeom(1, Hc, Wc, S.cout_pad), q, S.n_patches, idx);
     WCTB_CHECK_LAUNCH("k_swap_argmax");
-    k_swap_gather<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(ws_feat, gs, idx, gc, ss_feat);
+    k_swap_gather<<<swap_grid((long long)Hc * Wc * (C / 8), 256), 256, 0, st>>>(ws_feat, gs, q, idx, gc, ss_feat);
     WCTB_CHECK_LAUNCH("k_swap_gather");
     rc = launch_conv_tc(CONV_APPLY, ss_feat, 1, Hc, Wc, C, msplit + 4 * CC, 1, nullptr, bias3 + 2 * C, C, 0, tmp, st);
     if (rc) return rc;

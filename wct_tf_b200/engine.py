@@ -256,21 +256,21 @@ class Engine(object):
                    bytes_=4.0 * C * (2 * content.N * hwc + style.N * hws))
         return out, kbuf
 
-    def style_swap(self, content, style, ss_alpha, want_info=False):
-        """wct_style_swap (ops.py:145-217) on one content/style pair: patch 3x3, stride 1."""
+    def style_swap(self, content, style, ss_alpha, want_info=False, patch=3, stride=1):
+        """wct_style_swap (ops.py:145-217) on one content/style pair with ``patch`` x ``patch`` windows every ``stride``."""
         assert content.N == 1 and style.N == 1, "style swap works on one content/style pair (ops.py:146)"
         st = self._stream()
         C = content.C
         out = self._act(1, content.H, content.W, C)
-        nbytes = self.lib.wctb200_style_swap_workspace_bytes(C, content.H, content.W, style.H, style.W)
+        nbytes = self.lib.wctb200_style_swap_workspace_bytes(C, content.H, content.W, style.H, style.W, int(patch), int(stride))
         if nbytes == 0:
-            raise ValueError("style swap needs encodings of at least 3x3 (content %dx%d, style %dx%d)"
-                             % (content.H, content.W, style.H, style.W))
+            raise ValueError("style swap needs encodings of at least %dx%d (content %dx%d, style %dx%d)"
+                             % (patch, patch, content.H, content.W, style.H, style.W))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         kbuf = torch.empty(4, dtype=torch.int32, device=self.device) if want_info else None
         sem = SEMANTICS["tf"]                  # the reference only has the TF graph version of this op
         self._call("style_swap[C%d]" % C, 22, self.lib.wctb200_style_swap_level, content.ptr, content.H, content.W, style.ptr,
-                   style.H, style.W, C, float(ss_alpha), sem["eps_cov"], sem["thresh"], out.ptr,
+                   style.H, style.W, C, int(patch), int(stride), float(ss_alpha), sem["eps_cov"], sem["thresh"], out.ptr,
                    kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st)
         ws.record_stream(torch.cuda.current_stream(self.device))   # freed by the caching allocator only after this stream is done
         return out, kbuf
@@ -304,7 +304,8 @@ class Engine(object):
         return out, kbuf
 
     # ------------------------------------------------------------------ pipeline
-    def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None, swap5=False, ss_alpha=0.6):
+    def stylize(self, content_u8, style_u8, alpha=1.0, adain=False, want_info=False, capture=None, swap5=False, ss_alpha=0.6,
+                ss_patch_size=3, ss_stride=1):
         """content_u8: cuda uint8 [N,H,W,3]; style_u8: cuda uint8 [Ns,Hs,Ws,3], Ns in {1, N}.
         Returns the float32 ``decoded_output`` [N,H',W',3] (unclipped, model.py:94).
         ``capture`` (dict) receives every level's input image / features for parity tests.
@@ -318,7 +319,8 @@ class Engine(object):
         if swap5:
             if N != 1 or style_u8.shape[0] != 1:
                 raise ValueError("swap5 works on one content/style pair per call (ops.py:146)")
-            return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture, True, ss_alpha)
+            return self._stylize_one(content_u8, style_u8, alpha, adain, want_info, capture, True, ss_alpha,
+                                     ss_patch=ss_patch_size, ss_stride=ss_stride)
         G = min(self.groups, N) if (capture is None and not want_info) else 1
         if G > 1:
             main = torch.cuda.current_stream(self.device)
@@ -387,7 +389,8 @@ class Engine(object):
             self._tag = tag
         return dict(states=states, events=events, feats=feats, side=side)
 
-    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture, swap5=False, ss_alpha=0.6, shared_style=None):
+    def _stylize_one(self, content_u8, style_u8, alpha, adain, want_info, capture, swap5=False, ss_alpha=0.6, shared_style=None,
+                     ss_patch=3, ss_stride=1):
         lib, st = self.lib, self._stream()
         N = content_u8.shape[0]
         assert content_u8.dtype == torch.uint8 and style_u8.dtype == torch.uint8
@@ -406,7 +409,7 @@ class Engine(object):
             self._tag = lvl.relu_target
             cf, _ = self.encode(x, lvl.relu_target)
             if swap5 and lvl.relu_target == "relu5_1":     # model.py:148-152: style swap wins over AdaIN / WCT at relu5_1
-                f, kbuf = self.style_swap(cf, style_feats[lvl.relu_target], ss_alpha, want_info)
+                f, kbuf = self.style_swap(cf, style_feats[lvl.relu_target], ss_alpha, want_info, ss_patch, ss_stride)
             elif split:
                 if side is not main:
                     main.wait_event(style_events[lvl.relu_target])

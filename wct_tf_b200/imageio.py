@@ -75,3 +75,29 @@ def coral(source, target):
 def preserve_colors_np(style_rgb, content_rgb):
     """utils.py:87-90 (--keep-colors)"""
     return np.uint8(np.clip(coral(style_rgb / 255., content_rgb / 255.), 0, 1) * 255.)
+
+
+def center_crop_to(img, H_target, W_target):
+    """utils.py:40-53: centre crop a rectangle, upscaling first (bilinear, by the larger of the two ratios) if the image
+    is too small."""
+    height, width = img.shape[0], img.shape[1]
+    if height < H_target or width < W_target:
+        rat = max(H_target / height, W_target / width)
+        # scipy.misc.imresize(img, <float>) scaled both sides by the fraction (PIL bilinear on the uint8 image)
+        img = _imresize(img, (int(height * rat), int(width * rat)))
+        height, width = img.shape[0], img.shape[1]
+    h_off, w_off = (height - H_target) // 2, (width - W_target) // 2
+    return img[h_off:h_off + H_target, w_off:w_off + W_target]
+
+
+def swap_filter_fit(H, W, patch_size, stride, n_pools=4):
+    """utils.py:115-138: style swap with a stride may not tile the relu5_1 encoding; returns (should_refit, H_out, W_out),
+    the image size whose encoding the patch / stride combination tiles exactly."""
+    def pool_out(x):
+        return (x + 2 - 1) // 2
+    hp, wp = H, W
+    for _ in range(n_pools):
+        hp, wp = pool_out(hp), pool_out(wp)
+    hc, wc = (hp - patch_size) // stride + 1, (wp - patch_size) // stride + 1
+    hd, wd = (hc - 1) * stride + patch_size, (wc - 1) * stride + patch_size
+    return (hp != hd) or (wp != wd), hd * 2 ** n_pools, wd * 2 ** n_pools

@@ -6,7 +6,8 @@ sm_100a engine (engine.py -> libwctb200.so).  Differences, all explicit:
     weights.py) OR ``weights=`` may pass an in-memory weights dict (the offline
     build has no .t7 / TF checkpoints, so benchmarks use synthetic weights);
   * ``device`` accepts the reference's TF strings ('/gpu:0') and torch strings;
-  * ``swap5=True`` (style-swap at relu5_1, ops.py:145-278) is built for patch 3 / stride 1 (the defaults);
+  * ``swap5=True`` (style-swap at relu5_1, ops.py:145-278) honours ``ss_patch_size`` / ``ss_stride``; with a stride the
+    content is centre-cropped so that the patches tile its relu5_1 encoding, as wct.py:84-90 does;
   * ``predict_batch`` is new: a batch of frames per call (frames are independent).
 """
 from __future__ import annotations
@@ -88,15 +89,22 @@ class WCT(object):
                 a = a.clamp(0, 255).to(torch.uint8)   # the reference feeds arrays "in [0,255]" (wct.py:74)
             return a.to(dev, non_blocking=True).contiguous()
 
+        if swap5 and self.ss_stride != 1:
+            # wct.py:84-90: with a stride the filter may not fit; centre-crop the content to a size it tiles
+            from .imageio import center_crop_to, swap_filter_fit
+            arr = contents.cpu().numpy() if isinstance(contents, torch.Tensor) else np.asarray(contents)
+            arr = arr[None] if arr.ndim == 3 else arr
+            refit, H, W = swap_filter_fit(arr.shape[1], arr.shape[2], self.ss_patch_size, self.ss_stride)
+            if refit:
+                contents = np.stack([center_crop_to(a, H, W) for a in arr])
         with torch.cuda.device(dev):
             c = to_dev(contents)
             s = to_dev(styles)
             if swap5:
-                if self.ss_patch_size != 3 or self.ss_stride != 1:
-                    raise NotImplementedError("style swap is built for --ss-patch-size 3 --ss-stride 1 (the reference's defaults)")
                 # one pair per call like the reference graph (ops.py:146); frames of a batch are swapped one by one
                 outs = [eng.stylize(c[i:i + 1], s[i:i + 1] if s.shape[0] > 1 else s, alpha=alpha, adain=adain, swap5=True,
-                                    ss_alpha=ss_alpha) for i in range(c.shape[0])]
+                                    ss_alpha=ss_alpha, ss_patch_size=self.ss_patch_size, ss_stride=self.ss_stride)
+                        for i in range(c.shape[0])]
                 out_f = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
             else:
                 out_f = eng.stylize(c, s, alpha=alpha, adain=adain)
