@@ -203,7 +203,7 @@ def test_jacobi_rank_deficient_null_space_stays_below_threshold():
     (64, (9, 11), (11, 9), 0.6, 8, 5, 2),        # --ss-patch-size 5 --ss-stride 2
     (128, (9, 7), (10, 8), 0.7, 9, 3, 2),        # stride 2
     (64, (8, 10), (9, 9), 0.5, 10, 4, 1),        # even patch, stride 1
-    (64, (7, 9), (8, 8), 0.6, 11, 1, 1),         # 1x1 patches
+    (64, (7, 9), (8, 8), 0.6, 12, 1, 1),         # 1x1 patches
 ], ids=lambda c: "C%d_p%ds%d" % (c[0], c[5], c[6]))
 def test_style_swap_level_matches_oracle(case):
     """wctb200_style_swap_level vs the NumPy restatement of ops.py:145-278 (itself pinned to the reference's own code by
