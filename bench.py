@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--no-prio", action="store_true", help="tuning: all streams at the same priority")
     ap.add_argument("--no-fuse-upsample", action="store_true", help="tuning: separate upsample2 kernels + 9-tap convs")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel profiling steps")
+    ap.add_argument("--jacobi-tolq", type=float, default=0.0, help="tuning: eigensolver predicted-convergence level (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -246,6 +247,8 @@ def main():
     eng = wct.engine
     if args.oversub:
         eng.lib.wctb200_debug_set_conv_oversub(args.oversub)
+    if args.jacobi_tolq > 0:
+        eng.lib.wctb200_debug_set_jacobi_tolq(args.jacobi_tolq)
     if args.no_overlap:
         eng.overlap_style = False
     eng.groups = max(1, args.groups)
