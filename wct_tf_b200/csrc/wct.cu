@@ -108,25 +108,17 @@ __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], floa
     float p0, p1, p2, p3, q0, q1, q2, q3;
     unpack2(d00, p0, p1); unpack2(d01, p2, p3);
     unpack2(d10, q0, q1); unpack2(d11, q2, q3);
-    const float g0 = (p0 + p1) + (p2 + p3);
-    const float g1 = (q0 + q1) + (q2 + q3);
-    // The two rotations are SPLIT over the half-warps: lanes 0-15 reduce and solve rotation 0, lanes 16-31 rotation 1
-    // (one exchange step, then 4 butterfly steps inside the half: 5 shuffles instead of 10), each lane runs the scalar
-    // chain of ONE rotation instead of two, and three shuffles hand (s, c-1, t*g) to the other half.  Every lane of a half
-    // holds bit-identical values, so all 32 lanes apply identical rotations.  (-17 % instructions per rotation: the
-    // kernel is issue/latency bound, 470 warp-instructions per 4 rotations of which only 160 are the packed FMAs.)
-    const bool hi = (threadIdx.x & 16) != 0;
-    float mine = (hi ? g1 : g0) + __shfl_xor_sync(0xffffffffu, hi ? g0 : g1, 16);
+    float g0 = (p0 + p1) + (p2 + p3);
+    float g1 = (q0 + q1) + (q2 + q3);
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    float t, s, cm1;
-    rot_scalars(mine, hi ? a1 : a0, hi ? b1 : b0, tol2, tolq2, null2, flag, t, s, cm1);   // `flag`: this half's rotations only
-    const float tg = t * mine;
-    const float s_o = __shfl_xor_sync(0xffffffffu, s, 16), c_o = __shfl_xor_sync(0xffffffffu, cm1, 16);
-    const float tg_o = __shfl_xor_sync(0xffffffffu, tg, 16);
-    const float s0 = hi ? s_o : s, s1 = hi ? s : s_o, c0 = hi ? c_o : cm1, c1 = hi ? cm1 : c_o;
-    const float tg0 = hi ? tg_o : tg, tg1 = hi ? tg : tg_o;
-    if (s0 != 0.f || s1 != 0.f) {          // warp-uniform: skip the FMAs only when BOTH pairs are already orthogonal
+    for (int o = 16; o >= 1; o >>= 1) {
+        g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    }
+    float t0, s0, c0, t1, s1, c1;
+    rot_scalars(g0, a0, b0, tol2, tolq2, null2, flag, t0, s0, c0);
+    rot_scalars(g1, a1, b1, tol2, tolq2, null2, flag, t1, s1, c1);
+    if (t0 != 0.f || t1 != 0.f) {          // warp-uniform: skip the FMAs only when BOTH pairs are already orthogonal
         const f32x2 s20 = pack2(s0, s0), ns20 = pack2(-s0, -s0), c20 = pack2(c0, c0);
         const f32x2 s21 = pack2(s1, s1), ns21 = pack2(-s1, -s1), c21 = pack2(c1, c1);
 #pragma unroll
@@ -137,8 +129,8 @@ __device__ __forceinline__ void rot_regs2(f32x2 (&x0)[HP], f32x2 (&y0)[HP], floa
             x1[i] = fma2(c21, xb, fma2(ns21, yb, xb));
             y1[i] = fma2(c21, yb, fma2(s21, xb, yb));
         }
-        a0 = fmaxf(a0 - tg0, 0.f); b0 = fmaxf(b0 + tg0, 0.f);   // |x'|^2 = |x|^2 - t g , |y'|^2 = |y|^2 + t g
-        a1 = fmaxf(a1 - tg1, 0.f); b1 = fmaxf(b1 + tg1, 0.f);
+        a0 = fmaxf(fmaf(-t0, g0, a0), 0.f); b0 = fmaxf(fmaf(t0, g0, b0), 0.f);   // |x'|^2 = |x|^2 - t g , |y'|^2 = |y|^2 + t g
+        a1 = fmaxf(fmaf(-t1, g1, a1), 0.f); b1 = fmaxf(fmaf(t1, g1, b1), 0.f);
     }
 }
 
@@ -350,7 +342,6 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
             }
         }
         // ---- convergence: worst pair class seen in this sweep (0 / 1 / 2), agreed across the cluster
-        flag = fmaxf(flag, __shfl_xor_sync(0xffffffffu, flag, 16));     // each half-warp tracked its own rotations (rot_regs2)
         if (lane == 0) { atomicMax(&s_max, __float_as_uint(flag)); atomicMax(&s_amax, __float_as_uint(amax)); }
         __syncthreads();
         float gmax = __uint_as_float(s_max);
