@@ -54,6 +54,7 @@ DEBUG_SIGNATURES = {
     "wctb200_debug_set_conv_fuse": (_i, [_i]),
     "wctb200_debug_set_jacobi": (_i, [_i, _i]),
     "wctb200_debug_set_jacobi_tolq": (_i, [_f]),
+    "wctb200_debug_set_conv_products": (_i, [_i]),
 }
 
 _lib = None

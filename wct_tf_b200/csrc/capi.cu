@@ -109,6 +109,7 @@ int launch_eig_post(const float*, const float*, float*, int, int, float, float, 
 extern int g_conv_bn_override;
 extern int g_conv_oversub;
 extern int g_conv_fuse;
+extern int g_conv_products;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
 extern int g_jacobi_stagger;
@@ -318,6 +319,10 @@ int wctb200_debug_set_conv_fuse(int mode) {
     return g_conv_fuse;
 }
 int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
+int wctb200_debug_set_conv_products(int n) {
+    if (n >= 1 && n <= 3) g_conv_products = n;
+    return g_conv_products;
+}
 
 int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles) {
     if (lg_groups <= 4) g_jacobi_lg = lg_groups < 0 ? -1 : lg_groups;              // negative: back to the per-size default

@@ -49,6 +49,7 @@ struct ConvParams {
     int mode;             // ConvMode
     int taps;             // 9 (3x3), 1 (apply), 4 (up2: per output parity), kw*kw (taps)
     int kw;               // CONV_TAPS: filter width (top-left anchored kw x kw correlation, style-swap patches)
+    int products;         // 3 (default): a_hi b_hi + a_hi b_lo + a_lo b_hi; 2: without a_lo b_hi; 1: a_hi b_hi only (experiment knob)
     int per_image;        // tiles never straddle images; weight/bias set = image index (APPLY with nsets > 1)
     int nsets;
     int tiles_per_image;
@@ -240,11 +241,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                             if (Cfg::FUSE) {
                                 // [b_hi | b_lo] is one 2*BN-row K-major tile: columns [0,BN) += a_hi b_hi, [BN,2BN) += a_hi b_lo
                                 umma_f16(tacc, a_hi + ko, b_hi + ko, idesc2, (first && k == 0) ? 0u : 1u);
-                                umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
+                                if (p.products >= 3) umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
                             } else {
-                                umma_f16(tacc, a_hi + ko, b_lo + ko, idesc, (first && k == 0) ? 0u : 1u);
-                                umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
-                                umma_f16(tacc, a_hi + ko, b_hi + ko, idesc, 1u);
+                                umma_f16(tacc, a_hi + ko, b_hi + ko, idesc, (first && k == 0) ? 0u : 1u);
+                                if (p.products >= 2) umma_f16(tacc, a_hi + ko, b_lo + ko, idesc, 1u);
+                                if (p.products >= 3) umma_f16(tacc, a_lo + ko, b_hi + ko, idesc, 1u);
                             }
                         }
                         umma_commit(&empty[s]);
@@ -415,6 +416,7 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
     return 0;
 }
 
+int g_conv_products = 3;     // experiment knob (wctb200_debug_set_conv_products): split-fp16 products per MAC
 int g_conv_fuse = -1;        // -1 auto, 0 never, 1 whenever the tile allows (wctb200_debug_set_conv_fuse)
 int g_conv_bn_override = 0;  // test/tuning hook: force the N tile (64/128/256)
 
@@ -450,6 +452,7 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     p.mode = mode;
     p.taps = taps;
     p.kw = kw;
+    p.products = (mode == CONV_3X3 || mode == CONV_UP2) ? g_conv_products : 3;    // the knob only touches the encoder / decoder convs
     p.nsets = nsets;
     p.per_image = nsets > 1 ? 1 : 0;
     p.tiles_per_image = cdiv((long long)gi.Hp * gi.Wp, 128);

@@ -11,7 +11,7 @@
 //
 // Centring (ops.py:44,49,106: fc = f - mean BEFORE the product).  Round 1 ran three extra passes for it (channel sums,
 // a centred SPF16 copy written to HBM, the product over the copy).  Now a tiny pre-kernel estimates a per-channel SHIFT t
-// (the mean of <= 1024 strided pixels; the exact mean when HW <= 1024), four "centring" warps subtract t from every staged
+// (the mean of <= 1024 strided pixels; the exact mean when HW <= 1024), eight worker warps subtract t from every staged
 // tile IN SHARED MEMORY (hi+lo -> fp32 -> minus t -> re-split, zero-filled out-of-range pixels stay zero) before the MMA warp
 // may read it, and accumulate s = sum_p (x_p - t) on the way.  The finalize kernel forms
 //     cov = (S - s s^T / HW) / (HW - 1),   mean = t + s / HW
@@ -34,7 +34,7 @@ struct CovParams {
     int tiles_x, tiles_y;        // 32 x 2 pixel tiles per image
     int ksplit, tiles_per_split;
     int nb;                      // 128-channel blocks (C=64: 1 block, rows duplicated)
-    int nslots;                  // partial slots per image: ksplit (C=64: 2*ksplit)
+    int nslots;                  // partial slots per image: ksplit (C=64: 4*ksplit)
     const float* shift;          // [N][C]
     float* part;                 // [N][nslots][C][C] fp32 partial products (upper block triangle)
     float* psum;                 // [N][ksplit][C] fp32 partial sums of (x - shift)
@@ -48,8 +48,8 @@ struct CovCfg {
     static constexpr int STAGES = 3;
     static constexpr int NBUF = 4;
     static constexpr int CH = 2;                            // 64-pixel tiles per TMEM accumulation chunk (24 truncating adds)
-    static constexpr int THREADS = 320;                     // producer, MMA, 4 epilogue warps, 4 centring warps
-    static constexpr int RED_BYTES = 16 * 128 * 4;          // centring warps: [16 row groups][128 channels] partial sums
+    static constexpr int THREADS = 320;                     // producer, MMA, 8 worker warps (centring + TMEM drains)
+    static constexpr int RED_BYTES = 32 * 128 * 4;          // worker warps: [32 row groups][128 channels] partial sums
     static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + RED_BYTES + 1024;
 };
 
@@ -97,8 +97,8 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     const bool dup = (p.C == 64);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
-        for (int b = 0; b < Cfg::NBUF; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 8); }
+        for (int b = 0; b < Cfg::NBUF; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
         *abort_flag = 0;
         fence_barrier_init();
         tma_prefetch_desc(&mapX);
@@ -176,59 +176,22 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ---- epilogue warps: drain TMEM chunks into registers, write this CTA's partial block to its own slot ----
-        const int g = warp & 3;
-        float acc[128];
-#pragma unroll
-        for (int i = 0; i < 128; ++i) acc[i] = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-            const int b = c % Cfg::NBUF;
-            mbar_wait(&tfull[b], (c / Cfg::NBUF) & 1, abort_flag, p.err, 0x530u + b);
-            tc_fence_after();
-            const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * 128);
-#pragma unroll
-            for (int c0 = 0; c0 < 128; c0 += 64) {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tsrc + c0, r0);
-                tmem_ld32(tsrc + c0 + 32, r1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[b]);
-        }
-        const int m = g * 32 + lane;          // accumulator row
-        if (!*abort_flag) {
-            if (dup) {
-                // accumulator rows m and m+64 both belong to channel m & 63, columns j and 64+j to channel j:
-                // the two row halves go to two slots, the finalize kernel adds them
-                float* dst = p.part + (((long long)img * p.nslots + split * 2 + (m >> 6)) * p.C + (m & 63)) * p.C;
-#pragma unroll
-                for (int j = 0; j < 64; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j] + acc[64 + j], acc[j + 1] + acc[65 + j],
-                                                                      acc[j + 2] + acc[66 + j], acc[j + 3] + acc[67 + j]);
-            } else {
-                float* dst = p.part + (((long long)img * p.nslots + split) * p.C + bi * 128 + m) * p.C + bj * 128;
-#pragma unroll
-                for (int j = 0; j < 128; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            }
-        }
     } else {
-        // ---- centring warps: x -> x - shift in place on the staged tile, sums of the shifted values ----
-        const int ct = threadIdx.x - 192;     // 0..127
+        // ---- 8 worker warps (2..9).  All of them centre the staged tiles (x -> x - shift in place, sums of the shifted
+        // values); in between they drain the finished TMEM chunks into registers: warps 2-5 own accumulator columns 0..63,
+        // warps 6-9 columns 64..127 (a warp may only read the TMEM lanes of its quadrant, warp & 3).  One warp per
+        // scheduler for the centring (the first version: warps 6-9 only) ran at the latency of its own instruction chain
+        // and capped the kernel at 0.34 of the HBM rate.
+        const int ct = threadIdx.x - 64;      // 0..255
         const int chunk = ct & 7;             // logical 16-byte chunk of a 128-byte row = channels chunk*8 .. +7 of the slice
-        const int rg = ct >> 3;               // rows rg, rg+16, rg+32, rg+48 of every 64-pixel slice
+        const int rg = ct >> 3;               // rows rg and rg+32 of every 64-pixel slice
         const int pchunk = (chunk ^ (rg & 7)) << 4;      // SWIZZLE_128B: physical chunk = logical ^ (row & 7); row & 7 == rg & 7
         const int nops = dup ? 1 : (diag ? 1 : 2);
         const int nsl = dup ? 1 : 2;
         const bool want_sums = dup || diag;   // every channel block has exactly one diagonal pair
-        float sh[2][2][8], sums[2][8];
+        const int g = warp & 3;               // TMEM lane quadrant
+        const int chalf = warp >= 6 ? 1 : 0;  // accumulator column half drained by this warp
+        float sh[2][2][8], sums[2][8], acc[64];
 #pragma unroll
         for (int op = 0; op < 2; ++op)
 #pragma unroll
@@ -242,6 +205,26 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
         for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
             for (int j = 0; j < 8; ++j) sums[sl][j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        int drained = 0;
+        auto drain = [&](int c) {
+            const int b = c % Cfg::NBUF;
+            mbar_wait(&tfull[b], (c / Cfg::NBUF) & 1, abort_flag, p.err, 0x530u + b);
+            tc_fence_after();
+            const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(b * 128 + chalf * 64);
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tsrc, r0);
+            tmem_ld32(tsrc + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r1[j]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[b]);
+        };
         for (int it = 0; it < ntiles; ++it) {
             const int s = it % Cfg::STAGES;
             mbar_wait(&full[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x550u + s);
@@ -257,8 +240,8 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
                     uint8_t* hi_base = dup ? st : st + op * Cfg::OPER + sl * Cfg::SLICE;
                     uint8_t* lo_base = dup ? st + Cfg::SLICE : st + op * Cfg::OPER + (2 + sl) * Cfg::SLICE;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int r = rg + 16 * k;
+                    for (int k = 0; k < 2; ++k) {
+                        const int r = rg + 32 * k;
                         const int x = tx * 32 + (r & 31), y = ty * 2 + (r >> 5);
                         if (x < p.W && y < p.H) {           // out-of-range pixels were zero-filled by TMA and must stay zero
                             const int off = r * 128 + pchunk;
@@ -283,19 +266,44 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[s]);
+            // the tiles of chunk it / CH are all centred now: drain the chunks BEFORE it (their MMAs were issued a chunk ago)
+            if ((it % Cfg::CH) == Cfg::CH - 1 || it == ntiles - 1) {
+                const int cdone = it / Cfg::CH;
+                while (drained < cdone) drain(drained++);
+            }
+        }
+        while (drained < nchunks) drain(drained++);
+        // ---- this CTA's partial block -> its own slot ----
+        const int m = g * 32 + lane;          // accumulator row
+        if (!*abort_flag) {
+            if (dup) {
+                // accumulator rows m and m+64 both belong to channel m & 63, columns j and 64+j to channel j: the four
+                // (row half, column half) quadrants go to four slots, the finalize kernel adds them
+                float* dst = p.part + (((long long)img * p.nslots + split * 4 + (m >> 6) * 2 + chalf) * p.C + (m & 63)) * p.C;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            } else {
+                float* dst = p.part + (((long long)img * p.nslots + split) * p.C + bi * 128 + m) * p.C + bj * 128 + chalf * 64;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            }
         }
         if (want_sums) {
-            // fixed-order reduction over the 16 row groups, then one partial per (image, split, channel)
+            // fixed-order reduction over the 32 row groups, then one partial per (image, split, channel)
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) red[rg * 128 + sl * 64 + chunk * 8 + j] = sums[sl][j];
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (want_sums) {
             const int nch = dup ? 64 : 128;
             if (ct < nch && !*abort_flag) {
                 float a = 0.f;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) a += red[r * 128 + ct];
+                for (int r = 0; r < 32; ++r) a += red[r * 128 + ct];
                 p.psum[((long long)img * p.ksplit + split) * p.C + (dup ? 0 : bi * 128) + ct] = a;
             }
         }
@@ -408,7 +416,7 @@ int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, fl
     if (tps < 8) tps = 8;
     p.tiles_per_split = tps;
     p.ksplit = (tiles_img + tps - 1) / tps;
-    p.nslots = g.C == 64 ? 2 * p.ksplit : p.ksplit;
+    p.nslots = g.C == 64 ? 4 * p.ksplit : p.ksplit;
     // scratch: shift [N][C] | psum [N][ksplit][C] | part [N][nslots][C][C]
     const size_t n_shift = (size_t)g.N * g.C, n_psum = (size_t)g.N * p.ksplit * g.C;
     const size_t n_part = (size_t)g.N * p.nslots * g.C * g.C;
