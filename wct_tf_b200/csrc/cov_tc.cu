@@ -44,13 +44,14 @@ struct CovParams {
 struct CovCfg {
     static constexpr int SLICE = 64 * 128;                  // 64 pixels x 64 channels fp16 = 8 KB
     static constexpr int OPER = 4 * SLICE;                  // 2 channel slices x 2 planes
-    static constexpr int STAGE = 2 * OPER;                  // A + B
-    static constexpr int STAGES = 3;
+    static constexpr int STAGE = 2 * OPER;                  // A + B (off-diagonal block pair); a diagonal pair uses OPER, C = 64 two SLICEs
+    static constexpr int RING_BYTES = 3 * STAGE;            // 192 KB of tiles in flight whatever the stage size: 3 / 6 / 12 stages
+    static constexpr int STAGES = 12;                       // barrier slots (the deepest ring)
     static constexpr int NBUF = 4;
     static constexpr int CH = 2;                            // 64-pixel tiles per TMEM accumulation chunk (24 truncating adds)
     static constexpr int THREADS = 320;                     // producer, MMA, 8 worker warps (centring + TMEM drains)
     static constexpr int RED_BYTES = 32 * 128 * 4;          // worker warps: [32 row groups][128 channels] partial sums
-    static constexpr int SMEM_BYTES = STAGES * STAGE + 512 + RED_BYTES + 1024;
+    static constexpr int SMEM_BYTES = RING_BYTES + 512 + RED_BYTES + 1024;
 };
 
 __device__ __forceinline__ void tma_load_5d_cov(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2,
@@ -67,7 +68,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     using Cfg = CovCfg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE;
+    uint8_t* aux = smem + Cfg::RING_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* ready = empty + Cfg::STAGES;
@@ -109,16 +110,20 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nchunks = (ntiles + Cfg::CH - 1) / Cfg::CH;
+    // One stage holds exactly what one tile needs, so the ring is 3 (off-diagonal pair), 6 (diagonal pair) or 12 (C = 64)
+    // stages deep: the C <= 128 levels are HBM-latency bound, with 3 stages of 16 KB in flight a CTA could not pull more than
+    // ~27 GB/s (measured 0.34 of the HBM rate)
     const uint32_t stage_bytes = dup ? 2 * Cfg::SLICE : (diag ? Cfg::OPER : Cfg::STAGE);
+    const int nst = Cfg::RING_BYTES / (int)stage_bytes;
 
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < ntiles; ++it) {
-                const int s = it % Cfg::STAGES;
-                mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1u, abort_flag, p.err, 0x510u + s);
+                const int s = it % nst;
+                mbar_wait(&empty[s], ((it / nst) & 1) ^ 1u, abort_flag, p.err, 0x510u + s);
                 const int t = t0 + it;
                 const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-                uint8_t* st = smem + s * Cfg::STAGE;
+                uint8_t* st = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 if (dup) {
                     tma_load_5d_cov(st, &mapX, &full[s], 0, tx * 32, ty * 2, img, 0);                  // rows 0..63   : hi
@@ -148,10 +153,10 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
                 const uint32_t tacc = tmem_base + (uint32_t)(b * 128);
                 const int it_end = min(ntiles, (c + 1) * Cfg::CH);
                 for (; it < it_end; ++it) {
-                    const int s = it % Cfg::STAGES;
-                    mbar_wait(&ready[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x520u + s);   // tile landed AND centred
+                    const int s = it % nst;
+                    mbar_wait(&ready[s], (it / nst) & 1, abort_flag, p.err, 0x520u + s);   // tile landed AND centred
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(smem + s * Cfg::STAGE);
+                    const uint32_t a0 = smem_u32(smem + s * stage_bytes);
                     const uint32_t b0 = diag ? a0 : a0 + Cfg::OPER;
                     const bool first = (it == c * Cfg::CH);
 #pragma unroll
@@ -226,11 +231,11 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             if (lane == 0) mbar_arrive(&tempty[b]);
         };
         for (int it = 0; it < ntiles; ++it) {
-            const int s = it % Cfg::STAGES;
-            mbar_wait(&full[s], (it / Cfg::STAGES) & 1, abort_flag, p.err, 0x550u + s);
+            const int s = it % nst;
+            mbar_wait(&full[s], (it / nst) & 1, abort_flag, p.err, 0x550u + s);
             const int t = t0 + it;
             const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-            uint8_t* st = smem + s * Cfg::STAGE;
+            uint8_t* st = smem + s * stage_bytes;
 #pragma unroll
             for (int op = 0; op < 2; ++op) {
                 if (op >= nops) break;
