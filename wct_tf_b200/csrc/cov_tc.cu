@@ -35,6 +35,7 @@ struct CovParams {
     int ksplit, tiles_per_split;
     int nb;                      // 128-channel blocks (C=64: 1 block, rows duplicated)
     int nslots;                  // partial slots per image: ksplit (C=64: 4*ksplit)
+    int max_stages;              // cap on the ring depth (probe knob; 12 = no cap)
     const float* shift;          // [N][C]
     float* part;                 // [N][nslots][C][C] fp32 partial products (upper block triangle)
     float* psum;                 // [N][ksplit][C] fp32 partial sums of (x - shift)
@@ -114,7 +115,7 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     // stages deep: the C <= 128 levels are HBM-latency bound, with 3 stages of 16 KB in flight a CTA could not pull more than
     // ~27 GB/s (measured 0.34 of the HBM rate)
     const uint32_t stage_bytes = dup ? 2 * Cfg::SLICE : (diag ? Cfg::OPER : Cfg::STAGE);
-    const int nst = Cfg::RING_BYTES / (int)stage_bytes;
+    const int nst = min(Cfg::RING_BYTES / (int)stage_bytes, p.max_stages);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -390,6 +391,8 @@ typedef CUresult (*PFN_encodeTiledC)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+int g_cov_max_stages = 12;   // probe knob (wctb200_debug_set_cov_stages)
+
 // Means and covariance (+ eps_cov I) of a feature batch: mean [N][C], G [N][C][C] (and a copy A0 if not null), fp32.
 // dsum: [N][C] fp64 scratch (caller's workspace); partial products live in the per-stream scratch cache.
 int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, float* G, float* A0, double* dsum, cudaStream_t st) {
@@ -432,6 +435,7 @@ int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, fl
     float* part = psum + ((n_psum + 3) & ~(size_t)3);
     p.shift = shift; p.psum = psum; p.part = part;
     p.err = device_error_word();
+    p.max_stages = g_cov_max_stages;
     // (blocks below the diagonal are never written -- and never read: k_cov_finalize only touches (min,max) entries)
 
     const int stride = HW <= 1024 ? 1 : (int)(HW / 1024);

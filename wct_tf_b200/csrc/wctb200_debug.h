@@ -16,6 +16,8 @@ WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
 WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
 /* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4) */
 WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
+/* covariance kernel: cap on the depth of the tile ring (default 12 = 192 KB in flight at every stage size) */
+WCTB200_API int wctb200_debug_set_cov_stages(int n);
 /* EXPERIMENT: split-fp16 products per MAC in the encoder / decoder convs: 3 = a_hi b_hi + a_hi b_lo +
  * a_lo b_hi (default, fp32-class), 2 = without a_lo b_hi (activations effectively fp16), 1 = a_hi b_hi only.  Returns the
  * value now selected.  With the fused MMA (N = 2*tile) 2 and 1 cost the same: a_hi [b_hi|b_lo] is one instruction. */
