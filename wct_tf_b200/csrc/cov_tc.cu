@@ -231,50 +231,58 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
         };
-        for (int it = 0; it < ntiles; ++it) {
-            const int s = it % nst;
-            mbar_wait(&full[s], (it / nst) & 1, abort_flag, p.err, 0x550u + s);
-            const int t = t0 + it;
-            const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-            uint8_t* st = smem + s * stage_bytes;
+        // fence.proxy.async (generic-proxy writes -> visible to the tensor core) is expensive: measured ~2100 cycles per tile
+        // whatever the number of centring warps or the ring depth (ncu: tensor pipe 13 % active, 2.2 TB/s).  The workers
+        // therefore centre a GROUP of tiles per fence: 4 when the ring is 12 deep, 2 when 6, 1 when 3.
+        const int T = nst >= 12 ? 4 : (nst >= 6 ? 2 : 1);
+        for (int it0 = 0; it0 < ntiles; it0 += T) {
+            const int it1 = min(it0 + T, ntiles);
+            for (int it = it0; it < it1; ++it) {
+                const int s = it % nst;
+                mbar_wait(&full[s], (it / nst) & 1, abort_flag, p.err, 0x550u + s);
+                const int t = t0 + it;
+                const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+                uint8_t* st = smem + s * stage_bytes;
 #pragma unroll
-            for (int op = 0; op < 2; ++op) {
-                if (op >= nops) break;
+                for (int op = 0; op < 2; ++op) {
+                    if (op >= nops) break;
 #pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    if (sl >= nsl) break;
-                    uint8_t* hi_base = dup ? st : st + op * Cfg::OPER + sl * Cfg::SLICE;
-                    uint8_t* lo_base = dup ? st + Cfg::SLICE : st + op * Cfg::OPER + (2 + sl) * Cfg::SLICE;
+                    for (int sl = 0; sl < 2; ++sl) {
+                        if (sl >= nsl) break;
+                        uint8_t* hi_base = dup ? st : st + op * Cfg::OPER + sl * Cfg::SLICE;
+                        uint8_t* lo_base = dup ? st + Cfg::SLICE : st + op * Cfg::OPER + (2 + sl) * Cfg::SLICE;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int r = rg + 32 * k;
-                        const int x = tx * 32 + (r & 31), y = ty * 2 + (r >> 5);
-                        if (x < p.W && y < p.H) {           // out-of-range pixels were zero-filled by TMA and must stay zero
-                            const int off = r * 128 + pchunk;
-                            const Half8 h = *reinterpret_cast<const Half8*>(hi_base + off);
-                            const Half8 l = *reinterpret_cast<const Half8*>(lo_base + off);
-                            float v[8];
-                            merge8(h, l, v);
+                        for (int k = 0; k < 2; ++k) {
+                            const int r = rg + 32 * k;
+                            const int x = tx * 32 + (r & 31), y = ty * 2 + (r >> 5);
+                            if (x < p.W && y < p.H) {           // out-of-range pixels were zero-filled by TMA and must stay zero
+                                const int off = r * 128 + pchunk;
+                                const Half8 h = *reinterpret_cast<const Half8*>(hi_base + off);
+                                const Half8 l = *reinterpret_cast<const Half8*>(lo_base + off);
+                                float v[8];
+                                merge8(h, l, v);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] -= sh[op][sl][j];
-                            if (op == 0) {
+                                for (int j = 0; j < 8; ++j) v[j] -= sh[op][sl][j];
+                                if (op == 0) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) sums[sl][j] += v[j];
+                                    for (int j = 0; j < 8; ++j) sums[sl][j] += v[j];
+                                }
+                                Half8 nh, nl;
+                                split8(v, nh, nl);
+                                *reinterpret_cast<Half8*>(hi_base + off) = nh;
+                                *reinterpret_cast<Half8*>(lo_base + off) = nl;
                             }
-                            Half8 nh, nl;
-                            split8(v, nh, nl);
-                            *reinterpret_cast<Half8*>(hi_base + off) = nh;
-                            *reinterpret_cast<Half8*>(lo_base + off) = nl;
                         }
                     }
                 }
             }
-            fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[s]);
-            // the tiles of chunk it / CH are all centred now: drain the chunks BEFORE it (their MMAs were issued a chunk ago)
-            if ((it % Cfg::CH) == Cfg::CH - 1 || it == ntiles - 1) {
-                const int cdone = it / Cfg::CH;
+            if (lane == 0)
+                for (int it = it0; it < it1; ++it) mbar_arrive(&ready[it % nst]);
+            // every tile of the chunks up to (it1-1) / CH is centred now: drain the chunks BEFORE that one
+            {
+                const int cdone = (it1 - 1) / Cfg::CH;
                 while (drained < cdone) drain(drained++);
             }
         }
@@ -319,37 +327,37 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// shift[n][c] = mean of <= ~1024 strided interior pixels (all pixels when HW <= 1024): fixed-order reduction
+// shift[n][c] = mean of <= ~1024 strided interior pixels (all pixels when HW <= 1024): fixed-order reduction.
+// grid (C/64, N): one CTA per 64 channels of an image (a single CTA per image took 180 us at C = 512);
+// 256 threads = 8 channel groups x 32 pixel lanes
 __global__ void __launch_bounds__(256)
 k_sample_shift(const __half* __restrict__ act, ActGeom g, int stride, float* __restrict__ shift) {
-    __shared__ float red[256 * 8];
-    const int cgs = g.C / 8;                    // 8..64 channel groups
-    const int rows = 256 / cgs;
-    const int grp = threadIdx.x % cgs, rl = threadIdx.x / cgs;
-    const int n = blockIdx.x;
+    __shared__ float red[32][64];
+    const int grp = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c0 = blockIdx.x * 64 + grp * 8;
+    const int n = blockIdx.y;
     const long long HW = (long long)g.H * g.W;
     const long long ns = (HW + stride - 1) / stride;
     float s[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = 0.f;
-    if (rl < rows) {
-        for (long long k = rl; k < ns; k += rows) {
-            const long long q = k * stride;
-            const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
-            float v[8];
-            load8(act, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, grp * 8, v);
+#pragma unroll 4
+    for (long long k = rl; k < ns; k += 32) {
+        const long long q = k * stride;
+        const int y = (int)(q / g.W), x = (int)(q - (long long)y * g.W);
+        float v[8];
+        load8(act, g, ((long long)n * g.Hp + y + 1) * g.Wp + x + 1, c0, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] += v[j];
-        }
+        for (int j = 0; j < 8; ++j) s[j] += v[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = s[j];
+    for (int j = 0; j < 8; ++j) red[rl][grp * 8 + j] = s[j];
     __syncthreads();
-    for (int c = threadIdx.x; c < g.C; c += 256) {
-        const int gq = c / 8, j = c % 8;
+    if (threadIdx.x < 64) {
         float a = 0.f;
-        for (int r = 0; r < rows; ++r) a += red[(r * cgs + gq) * 8 + j];
-        shift[(long long)n * g.C + c] = a / (float)ns;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) a += red[r][threadIdx.x];
+        shift[(long long)n * g.C + blockIdx.x * 64 + threadIdx.x] = a / (float)ns;
     }
 }
 
@@ -376,8 +384,18 @@ __global__ void k_cov_finalize(const float* __restrict__ part, const double* __r
         // every (min,max) entry lies in a stored upper block: reading it for both (i,j) and (j,i) makes G exactly symmetric
         const long long e = (i <= j) ? (long long)i * C + j : (long long)j * C + i;
         const float* pp = part + n * nslots * (long long)C * C + e;
-        double v = 0.0;
-        for (int s = 0; s < nslots; ++s) v += (double)pp[(long long)s * C * C];
+        // four interleaved partial sums (a fixed order all the same): the serial fp64 chain over up to 256 slots took 73-85 us
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        const long long cc = (long long)C * C;
+        int s = 0;
+        for (; s + 4 <= nslots; s += 4) {
+            v0 += (double)pp[(long long)s * cc];
+            v1 += (double)pp[(long long)(s + 1) * cc];
+            v2 += (double)pp[(long long)(s + 2) * cc];
+            v3 += (double)pp[(long long)(s + 3) * cc];
+        }
+        for (; s < nslots; ++s) v0 += (double)pp[(long long)s * cc];
+        double v = (v0 + v1) + (v2 + v3);
         v -= dsum[n * C + i] * dsum[n * C + j] / (double)HW;
         float r = (float)(v / (double)(HW - 1));
         if (i == j) r += eps_cov;
@@ -439,7 +457,7 @@ int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, fl
     // (blocks below the diagonal are never written -- and never read: k_cov_finalize only touches (min,max) entries)
 
     const int stride = HW <= 1024 ? 1 : (int)(HW / 1024);
-    k_sample_shift<<<(unsigned)g.N, 256, 0, st>>>(act, g, stride, shift);
+    k_sample_shift<<<dim3((unsigned)(g.C / 64), (unsigned)g.N), 256, 0, st>>>(act, g, stride, shift);
     WCTB_CHECK_LAUNCH("k_sample_shift");
 
     // tensor map over the interior pixels only (see header comment)
