@@ -119,11 +119,13 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < ntiles; ++it) {
-                const int s = it % nst;
-                mbar_wait(&empty[s], ((it / nst) & 1) ^ 1u, abort_flag, p.err, 0x510u + s);
-                const int t = t0 + it;
-                const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            // (stage index, barrier phase and tile coordinates advance incrementally: runtime div/mod cost ~40 instructions each)
+            int s = 0, ty = t0 / p.tiles_x, tx = t0 - ty * p.tiles_x;
+            uint32_t ph = 0;
+            for (int it = 0; it < ntiles; ++it, ++s, ++tx) {
+                if (s == nst) { s = 0; ph ^= 1u; }
+                if (tx == p.tiles_x) { tx = 0; ++ty; }
+                mbar_wait(&empty[s], ph ^ 1u, abort_flag, p.err, 0x510u + s);
                 uint8_t* st = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&full[s], stage_bytes);
                 if (dup) {
@@ -146,16 +148,17 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
-            int it = 0;
+            int it = 0, s = 0;
+            uint32_t ph = 0;
             for (int c = 0; c < nchunks; ++c) {
                 const int b = c % Cfg::NBUF;
                 mbar_wait(&tempty[b], ((c / Cfg::NBUF) & 1) ^ 1u, abort_flag, p.err, 0x540u + b);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(b * 128);
                 const int it_end = min(ntiles, (c + 1) * Cfg::CH);
-                for (; it < it_end; ++it) {
-                    const int s = it % nst;
-                    mbar_wait(&ready[s], (it / nst) & 1, abort_flag, p.err, 0x520u + s);   // tile landed AND centred
+                for (; it < it_end; ++it, ++s) {
+                    if (s == nst) { s = 0; ph ^= 1u; }
+                    mbar_wait(&ready[s], ph, abort_flag, p.err, 0x520u + s);   // tile landed AND centred
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(smem + s * stage_bytes);
                     const uint32_t b0 = diag ? a0 : a0 + Cfg::OPER;
@@ -235,13 +238,15 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
         // whatever the number of centring warps or the ring depth (ncu: tensor pipe 13 % active, 2.2 TB/s).  The workers
         // therefore centre a GROUP of tiles per fence: 4 when the ring is 12 deep, 2 when 6, 1 when 3.
         const int T = nst >= 12 ? 4 : (nst >= 6 ? 2 : 1);
+        int s = 0, ty = t0 / p.tiles_x, tx = t0 - ty * p.tiles_x;
+        uint32_t ph = 0;
         for (int it0 = 0; it0 < ntiles; it0 += T) {
             const int it1 = min(it0 + T, ntiles);
-            for (int it = it0; it < it1; ++it) {
-                const int s = it % nst;
-                mbar_wait(&full[s], (it / nst) & 1, abort_flag, p.err, 0x550u + s);
-                const int t = t0 + it;
-                const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+            const int s_first = s;
+            for (int it = it0; it < it1; ++it, ++s, ++tx) {
+                if (s == nst) { s = 0; ph ^= 1u; }
+                if (tx == p.tiles_x) { tx = 0; ++ty; }
+                mbar_wait(&full[s], ph, abort_flag, p.err, 0x550u + s);
                 uint8_t* st = smem + s * stage_bytes;
 #pragma unroll
                 for (int op = 0; op < 2; ++op) {
@@ -278,8 +283,13 @@ cov_tc_kernel(const __grid_constant__ CUtensorMap mapX, const CovParams p) {
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0)
-                for (int it = it0; it < it1; ++it) mbar_arrive(&ready[it % nst]);
+            if (lane == 0) {
+                int sa = s_first == nst ? 0 : s_first;
+                for (int it = it0; it < it1; ++it) {
+                    mbar_arrive(&ready[sa]);
+                    if (++sa == nst) sa = 0;
+                }
+            }
             // every tile of the chunks up to (it1-1) / CH is centred now: drain the chunks BEFORE that one
             {
                 const int cdone = (it1 - 1) / Cfg::CH;
