@@ -1,4 +1,5 @@
-"""One conv launch per shape for `ncu --set full` (profile-from-start off): 3x3 64->64 @512, UP2 64->64 @512, apply C=64."""
+"""One conv launch per shape for `ncu --set full` (profile-from-start off): 3x3 64->64 @512, UP2 64->64 @512, 3x3 512->512 @64,
+3x3 256->256 @128 (the layer shape with the largest share of the step).  usage: python tools/ncu_conv.py [frames]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,7 +20,7 @@ def mk(hw, cin, cout, up2):
     out = torch.empty(lib.wctb200_act_bytes(B, hw, hw, cout), dtype=torch.uint8, device="cuda")
     fn = lib.wctb200_conv3x3_up2 if up2 else lib.wctb200_conv3x3
     return lambda: _capi.check(fn(xin.data_ptr(), B, hin, hin, cin, ws.data_ptr(), bias.data_ptr(), cout, 1, out.data_ptr(), U.stream())), (xin, ws, bias, out, k)
-runs = [mk(512, 64, 64, 0), mk(512, 64, 64, 1), mk(64, 512, 512, 0)]
+runs = [mk(512, 64, 64, 0), mk(512, 64, 64, 1), mk(64, 512, 512, 0), mk(128, 256, 256, 0)]
 for r, _ in runs: r()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
