@@ -174,8 +174,9 @@ WCTB200_API int wctb200_covariance(const void* act, int N, int H, int W, int C, 
                        void* stream);
 /*
  * symmetric eigen-decomposition of `count` CxC fp32 matrices by one-sided Jacobi.
- * a: [count][C][C] symmetric (overwritten: column i becomes sigma_i * u_i),
- * sigma: [count][C] = |lambda_i|, sweeps: [count] (may be NULL). */
+ * a: [count][C][C] symmetric (overwritten: column i becomes s_i * u_i, u_i the unit eigenvector, s_i within 2e-4 relative of
+ * sigma_i -- only the direction of a column is significant),
+ * sigma: [count][C] = |lambda_i| (Rayleigh quotients against the input), sweeps: [count] (may be NULL). */
 WCTB200_API int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweeps, void* stream);
 
 #ifdef __cplusplus

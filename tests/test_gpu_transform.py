@@ -40,13 +40,17 @@ def test_jacobi_eigh_matches_lapack(n):
         w = np.linalg.eigvalsh(a[i].astype(np.float64))[::-1]
         got = np.sort(sg[i])[::-1]
         assert np.abs(got - np.abs(w)).max() <= 4e-5 * np.abs(w).max(), (i, np.abs(got - np.abs(w)).max())
-        # reconstruct A = sum_i u_i u_i^T sigma_i = G diag(1/sigma) G^T over the non-null columns
+        # reconstruct A = sum_i sigma_i u_i u_i^T over the non-null columns, u_i = the NORMALISED column i (the transform uses
+        # exactly this: d_i = f(sigma_i) / |g_i|^2, k_eig_post; sigma_i is the Rayleigh quotient, and the column norms of the
+        # tensor-core solver drift from sigma_i by a few 1e-5 relative -- a pure scaling of the columns)
         keep = sg[i] > 1e-6 * sg[i].max()
         gi = g[i][keep]                       # rows = columns of G
-        rec = (gi.T / sg[i][keep]) @ gi
+        nrm = np.linalg.norm(gi, axis=1)
+        assert np.abs(nrm / sg[i][keep] - 1).max() <= 2e-4
+        u = gi / nrm[:, None]
+        rec = (u.T * sg[i][keep]) @ u
         assert np.abs(rec - a[i]).max() <= 5e-5 * np.abs(a[i]).max()
-        u = gi / sg[i][keep][:, None]
-        assert np.abs(u @ u.T - np.eye(u.shape[0])).max() <= 5e-5
+        assert np.abs(u @ u.T - np.eye(u.shape[0])).max() <= 2e-5
 
 
 def _run_wct(content, style, alpha, sem):

@@ -38,7 +38,7 @@ struct JtCfg {
     static constexpr int SV_BYTES = 64 * SLD * 4;   // 16640
     static constexpr int SV_REGION = (2 * SV_BYTES + 1023) / 1024 * 1024;   // S and V; the B operand behind them must stay 1024-aligned
     static constexpr int B_BYTES = 2 * 64 * 128;    // V as split-fp16 B operand: hi 8 KB | lo 8 KB
-    static constexpr int AUX_BYTES = 3072;
+    static constexpr int AUX_BYTES = 3072 + 4096;
     static constexpr int SMEM_BYTES = TILE_BYTES + SV_REGION + B_BYTES + AUX_BYTES + 1024;
 };
 
@@ -58,10 +58,9 @@ __device__ __forceinline__ uint64_t jt_desc_mn(uint32_t smem_addr) {
 struct JtShared {
     float* S;          // [64][SLD] Gram matrix of the block pair (true scale)
     float* V;          // [64][SLD] accumulated rotation of the round
-    float2* rotcs;     // [2][32] (c, s) of column pair p, double buffered
-    int* pi;           // [2][32] column i of pair p
-    int* pj;           // [2][32]
-    int* slotcol;      // [32][2] schedule table: the column in slot k, half e (warp 0 only)
+    float4* rec;       // [2][32] (c, s, bits(i | j << 8), -) of column pair p of the current / previous step
+    unsigned short* sched;   // [63][32] i | j << 8: the pairs of every step of a round (built once per kernel)
+    int* slotcol;      // [32][2] scratch of the schedule builder (warp 0 only)
 };
 
 // ---- pair schedule (warp 0 only).  32 slots of two columns; at level H the slots [base, base+H) meet the slots
@@ -117,10 +116,9 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
     sh.V = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + Cfg::SV_BYTES);
     uint8_t* Bop = smem + Cfg::TILE_BYTES + Cfg::SV_REGION;         // 1024-aligned (SWIZZLE_128B operands)
     uint8_t* aux = Bop + Cfg::B_BYTES;
-    sh.rotcs = reinterpret_cast<float2*>(aux);                      // 512 B
-    sh.pi = reinterpret_cast<int*>(aux + 512);                      // 256 B
-    sh.pj = reinterpret_cast<int*>(aux + 768);                      // 256 B
+    sh.rec = reinterpret_cast<float4*>(aux);                        // 1024 B
     sh.slotcol = reinterpret_cast<int*>(aux + 1024);                // 256 B
+    sh.sched = reinterpret_cast<unsigned short*>(aux + 3072);       // 4032 B
     float* scl = reinterpret_cast<float*>(aux + 1280);              // [64] power-of-two scale of the Gram / apply operand
     float* iscl = reinterpret_cast<float*>(aux + 1536);             // [64] its inverse
     float* scl2 = reinterpret_cast<float*>(aux + 1792);             // [64] scale of the NEW columns (apply output)
@@ -149,6 +147,28 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // ---- the pair schedule of a round, once: 63 steps x 32 disjoint pairs (the first 32 steps are the cross pairs) ----
+    if (warp == 0) {
+        sh.slotcol[lane] = lane;
+        sh.slotcol[32 + lane] = 32 + lane;                              // slot k holds columns 2k, 2k+1
+        __syncwarp();
+        int H = 16, sg = 0, sub = 0;
+        for (int n = 0; n < 63; ++n) {
+            if (n > 0) {
+                if (H > 0 && sub == 0) { jt_swap_upper(sh.slotcol, H, lane); sub = 1; }
+                else {
+                    if (H > 1) jt_rotate_upper(sh.slotcol, H, lane);
+                    sub = 0;
+                    if (++sg >= H) { sg = 0; H = H > 1 ? H / 2 : 0; }       // 16 -> 8 -> 4 -> 2 -> 1 -> 0 (in-slot pairs)
+                }
+            }
+            int i, j;
+            jt_pair(sh.slotcol, H, lane, i, j);
+            sh.sched[n * 32 + lane] = (unsigned short)(i | (j << 8));
+        }
+    }
+    __syncthreads();
+
     const float tol2 = tol * tol;
     const float tolq2 = g_jacobi_tc_tolq * g_jacobi_tc_tolq;
     float null2 = 0.f;
@@ -175,7 +195,6 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
                 }
                 scl[t] = sc;
                 iscl[t] = 1.f / sc;
-                sh.slotcol[t] = t;                                      // slot k holds columns 2k, 2k+1
             }
             for (int e = t; e < 4096; e += 512) sh.V[(e >> 6) * SLD + (e & 63)] = ((e >> 6) == (e & 63)) ? 1.f : 0.f;
             __syncthreads();
@@ -252,52 +271,41 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
             // sub-step n: phase A  warp 0: schedule + parameters of step n  ||  warps 1-15: V update of step n-1
             //             phase B  all warps: S update of step n
             const int nsub = (r == 0) ? 63 : 32;
-            int H = 16, sg = 0, sub = 0;                               // schedule state (meaningful in warp 0)
             for (int n = 0; n <= nsub; ++n) {
                 const int cur = n & 1, prv = cur ^ 1;
                 if (warp == 0) {
                     if (n < nsub) {
-                        if (n > 0) {                                   // advance the schedule past step n-1
-                            if (H > 0 && sub == 0) { jt_swap_upper(sh.slotcol, H, lane); sub = 1; }
-                            else {
-                                if (H > 1) jt_rotate_upper(sh.slotcol, H, lane);
-                                sub = 0;
-                                if (++sg >= H) { sg = 0; H = H > 1 ? H / 2 : 0; }   // 16 -> 8 -> 4 -> 2 -> 1 -> 0 (in-slot pairs)
-                            }
-                        }
-                        int i, j;
-                        jt_pair(sh.slotcol, H, lane, i, j);
+                        const unsigned int ij = sh.sched[n * 32 + lane];
+                        const int i = ij & 255, j = ij >> 8;
                         const float a = sh.S[i * SLD + i], b = sh.S[j * SLD + j], g = sh.S[i * SLD + j];
                         float tt, s, cm1;
                         rot_scalars(g, a, b, tol2, tolq2, null2, flag, tt, s, cm1);
-                        sh.pi[cur * 32 + lane] = i;
-                        sh.pj[cur * 32 + lane] = j;
-                        sh.rotcs[cur * 32 + lane] = make_float2(1.f + cm1, s);
+                        sh.rec[cur * 32 + lane] = make_float4(1.f + cm1, s, __uint_as_float(ij), 0.f);
                     }
                 } else if (n > 0) {
                     // V <- V J for step n-1: 32 pairs x 64 rows, 480 threads
                     for (int it = t - 32; it < 2048; it += 480) {
                         const int row = it & 63, p = it >> 6;
-                        const int i = sh.pi[prv * 32 + p], j = sh.pj[prv * 32 + p];
-                        const float2 cs = sh.rotcs[prv * 32 + p];
+                        const float4 rc = sh.rec[prv * 32 + p];
+                        const unsigned int ij = __float_as_uint(rc.z);
                         float* vr = sh.V + row * SLD;
-                        const float x = vr[i], y = vr[j];
-                        vr[i] = cs.x * x - cs.y * y;
-                        vr[j] = cs.y * x + cs.x * y;
+                        const float x = vr[ij & 255], y = vr[ij >> 8];
+                        vr[ij & 255] = rc.x * x - rc.y * y;
+                        vr[ij >> 8] = rc.y * x + rc.x * y;
                     }
                 }
                 __syncthreads();
                 if (n < nsub) {
                     // S <- J^T S J : thread (warp w, lane l) owns the 2 x 2 blocks (pair 2w, pair l) and (pair 2w+1, pair l)
-                    const int iq = sh.pi[cur * 32 + lane], jq = sh.pj[cur * 32 + lane];
-                    const float2 rq = sh.rotcs[cur * 32 + lane];
+                    const float4 rq = sh.rec[cur * 32 + lane];
+                    const unsigned int ijq = __float_as_uint(rq.z);
+                    const int iq = ijq & 255, jq = ijq >> 8;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int p = 2 * warp + h;
-                        const int ip = sh.pi[cur * 32 + p], jp = sh.pj[cur * 32 + p];
-                        const float2 rp = sh.rotcs[cur * 32 + p];
-                        float* r0 = sh.S + ip * SLD;
-                        float* r1 = sh.S + jp * SLD;
+                        const float4 rp = sh.rec[cur * 32 + 2 * warp + h];
+                        const unsigned int ijp = __float_as_uint(rp.z);
+                        float* r0 = sh.S + (ijp & 255) * SLD;
+                        float* r1 = sh.S + (ijp >> 8) * SLD;
                         const float a = r0[iq], b = r0[jq], c = r1[iq], d = r1[jq];
                         const float a1 = a * rq.x - b * rq.y, b1 = a * rq.y + b * rq.x;     // columns
                         const float c1 = c * rq.x - d * rq.y, d1 = c * rq.y + d * rq.x;
