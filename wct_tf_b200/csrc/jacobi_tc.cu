@@ -103,6 +103,80 @@ __device__ __forceinline__ void jt_pair(const int* slotcol, int H, int lane, int
     }
 }
 
+// ---- V <- V J with the rows of V in REGISTERS (warps 1-2: thread = one row, 32 slots of two columns = 32 packed pairs).
+// Slot pair q = (u, v) of level H carries the column pairs p = 2q (lower halves) and p = 2q+1 (upper halves) of the schedule;
+// the swap / rotate transitions are the ones the schedule builder applied to its table, so register indices stay static.
+__device__ __forceinline__ f32x2 jt_swap2(f32x2 v) {
+    float a, b;
+    unpack2(v, a, b);
+    return pack2(b, a);
+}
+template <int H>
+__device__ __forceinline__ void jt_v_apply(f32x2 (&slot)[32], const float4* __restrict__ rec) {
+    const f32x2 zero = 0ull;
+    if constexpr (H == 0) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const float4 r = rec[k];
+            float x, y;
+            unpack2(slot[k], x, y);
+            slot[k] = pack2(r.x * x - r.y * y, r.y * x + r.x * y);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int grp = q / H, k = q - grp * H;
+            const int u = grp * 2 * H + k, v = u + H;
+            const float4 ra = rec[2 * q], rb = rec[2 * q + 1];
+            const f32x2 c2 = pack2(ra.x, rb.x), s2 = pack2(ra.y, rb.y), ns2 = pack2(-ra.y, -rb.y);
+            const f32x2 x = slot[u], y = slot[v];
+            slot[u] = fma2(ns2, y, fma2(c2, x, zero));      // x' = c x - s y
+            slot[v] = fma2(s2, x, fma2(c2, y, zero));       // y' = s x + c y
+        }
+    }
+}
+template <int H>
+__device__ __forceinline__ void jt_v_swap(f32x2 (&slot)[32]) {
+    if constexpr (H > 0) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int grp = q / H, k = q - grp * H;
+            const int v = grp * 2 * H + H + k;
+            slot[v] = jt_swap2(slot[v]);
+        }
+    }
+}
+template <int H>
+__device__ __forceinline__ void jt_v_rotate(f32x2 (&slot)[32]) {
+    if constexpr (H > 1) {
+#pragma unroll
+        for (int grp = 0; grp < 16 / H; ++grp) {
+            const int b0 = grp * 2 * H + H;
+            const f32x2 first = slot[b0];
+#pragma unroll
+            for (int k = 0; k < H - 1; ++k) slot[b0 + k] = slot[b0 + k + 1];
+            slot[b0 + H - 1] = first;
+        }
+    }
+}
+// apply step `n` of the schedule to the register rows: first the transition the builder made before that step, then the rotations
+__device__ __forceinline__ void jt_v_step(f32x2 (&slot)[32], const float4* __restrict__ rec, int n, int& H, int& sg, int& sub) {
+    if (n > 0) {
+        if (H > 0 && sub == 0) {
+            switch (H) { case 16: jt_v_swap<16>(slot); break; case 8: jt_v_swap<8>(slot); break; case 4: jt_v_swap<4>(slot); break;
+                         case 2: jt_v_swap<2>(slot); break; default: jt_v_swap<1>(slot); break; }
+            sub = 1;
+        } else {
+            switch (H) { case 16: jt_v_rotate<16>(slot); break; case 8: jt_v_rotate<8>(slot); break; case 4: jt_v_rotate<4>(slot); break;
+                         case 2: jt_v_rotate<2>(slot); break; default: break; }
+            sub = 0;
+            if (++sg >= H) { sg = 0; H = H > 1 ? H / 2 : 0; }
+        }
+    }
+    switch (H) { case 16: jt_v_apply<16>(slot, rec); break; case 8: jt_v_apply<8>(slot, rec); break; case 4: jt_v_apply<4>(slot, rec); break;
+                 case 2: jt_v_apply<2>(slot, rec); break; case 1: jt_v_apply<1>(slot, rec); break; default: jt_v_apply<0>(slot, rec); break; }
+}
+
 __global__ void __launch_bounds__(512, 1)
 k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __restrict__ conv_ws, int* __restrict__ sweeps_out,
             int max_sweeps, float tol, unsigned int* err) {
@@ -119,6 +193,7 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
     sh.rec = reinterpret_cast<float4*>(aux);                        // 1024 B
     sh.slotcol = reinterpret_cast<int*>(aux + 1024);                // 256 B
     sh.sched = reinterpret_cast<unsigned short*>(aux + 3072);       // 4032 B
+    unsigned char* fin = reinterpret_cast<unsigned char*>(aux + 2560);   // [2][64] slot half -> column at the end of a round
     float* scl = reinterpret_cast<float*>(aux + 1280);              // [64] power-of-two scale of the Gram / apply operand
     float* iscl = reinterpret_cast<float*>(aux + 1536);             // [64] its inverse
     float* scl2 = reinterpret_cast<float*>(aux + 1792);             // [64] scale of the NEW columns (apply output)
@@ -165,6 +240,10 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
             int i, j;
             jt_pair(sh.slotcol, H, lane, i, j);
             sh.sched[n * 32 + lane] = (unsigned short)(i | (j << 8));
+            // the column held by every slot half when a round ends after this step (cross-only rounds: 32 steps; round 0: 63)
+            if (n == 31) { fin[lane] = (unsigned char)sh.slotcol[lane]; fin[32 + lane] = (unsigned char)sh.slotcol[32 + lane]; }
+            if (n == 62) { fin[64 + lane] = (unsigned char)sh.slotcol[lane]; fin[96 + lane] = (unsigned char)sh.slotcol[32 + lane]; }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -196,7 +275,6 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
                 scl[t] = sc;
                 iscl[t] = 1.f / sc;
             }
-            for (int e = t; e < 4096; e += 512) sh.V[(e >> 6) * SLD + (e & 63)] = ((e >> 6) == (e & 63)) ? 1.f : 0.f;
             __syncthreads();
             // ---- load row t of the 64 columns (coalesced: a warp reads 128 contiguous bytes per column), scale, split,
             //      store as the shared-memory tile: row t at t*128 in both planes, 16-byte chunk c at c ^ (t & 7) ----
@@ -271,6 +349,13 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
             // sub-step n: phase A  warp 0: schedule + parameters of step n  ||  warps 1-15: V update of step n-1
             //             phase B  all warps: S update of step n
             const int nsub = (r == 0) ? 63 : 32;
+            f32x2 vrow[32];                                             // warps 1-2: row (t - 32) of V, slot k = columns 2k, 2k+1
+            int vH = 16, vsg = 0, vsub = 0;
+            if (warp == 1 || warp == 2) {
+                const int row = t - 32;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) vrow[k] = pack2(row == 2 * k ? 1.f : 0.f, row == 2 * k + 1 ? 1.f : 0.f);
+            }
             for (int n = 0; n <= nsub; ++n) {
                 const int cur = n & 1, prv = cur ^ 1;
                 if (warp == 0) {
@@ -282,17 +367,8 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
                         rot_scalars(g, a, b, tol2, tolq2, null2, flag, tt, s, cm1);
                         sh.rec[cur * 32 + lane] = make_float4(1.f + cm1, s, __uint_as_float(ij), 0.f);
                     }
-                } else if (n > 0) {
-                    // V <- V J for step n-1: 32 pairs x 64 rows, 480 threads
-                    for (int it = t - 32; it < 2048; it += 480) {
-                        const int row = it & 63, p = it >> 6;
-                        const float4 rc = sh.rec[prv * 32 + p];
-                        const unsigned int ij = __float_as_uint(rc.z);
-                        float* vr = sh.V + row * SLD;
-                        const float x = vr[ij & 255], y = vr[ij >> 8];
-                        vr[ij & 255] = rc.x * x - rc.y * y;
-                        vr[ij >> 8] = rc.y * x + rc.x * y;
-                    }
+                } else if ((warp == 1 || warp == 2) && n > 0) {
+                    jt_v_step(vrow, sh.rec + prv * 32, n - 1, vH, vsg, vsub);       // V <- V J for step n-1, thread-local
                 }
                 __syncthreads();
                 if (n < nsub) {
@@ -315,6 +391,17 @@ k_jacobi_tc(float* __restrict__ Gall, float* __restrict__ nrm_all, float* __rest
                         r1[jq] = b1 * rp.y + d1 * rp.x;
                     }
                     __syncthreads();
+                }
+            }
+            if (warp == 1 || warp == 2) {
+                const unsigned char* fc = fin + (r == 0 ? 64 : 0);
+                float* vr = sh.V + (t - 32) * SLD;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    float a, b;
+                    unpack2(vrow[k], a, b);
+                    vr[fc[2 * k]] = a;
+                    vr[fc[2 * k + 1]] = b;
                 }
             }
             // ---- scales of the NEW columns (their norms are the diagonal of the updated S), carried norms ----
