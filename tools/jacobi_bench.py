@@ -6,8 +6,6 @@ import torch
 from wct_tf_b200 import _capi
 
 lib = _capi.load()
-if os.environ.get("JAC_IMPL"):
-    print("C=512 eigensolver impl", lib.wctb200_debug_set_jacobi_impl(int(os.environ["JAC_IMPL"])))
 st = torch.cuda.current_stream().cuda_stream
 rng = np.random.default_rng(0)
 SCHED = [(int(a), int(b)) for a, b in (x.split(":") for x in os.environ.get("JAC_SCHED", "-1:-1").split(","))]

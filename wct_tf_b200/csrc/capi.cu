@@ -110,7 +110,6 @@ extern int g_conv_bn_override;
 extern int g_conv_oversub;
 extern int g_conv_fuse;
 extern int g_conv_products;
-extern int g_jacobi_impl;
 extern int g_cov_max_stages;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
@@ -321,10 +320,6 @@ int wctb200_debug_set_conv_fuse(int mode) {
     return g_conv_fuse;
 }
 int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
-int wctb200_debug_set_jacobi_impl(int impl) {
-    if (impl == 1 || impl == 2) g_jacobi_impl = impl;
-    return g_jacobi_impl;
-}
 int wctb200_debug_set_cov_stages(int n) {
     if (n >= 1 && n <= 12) g_cov_max_stages = n;
     return g_cov_max_stages;

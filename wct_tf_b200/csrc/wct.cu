@@ -640,11 +640,7 @@ int set_jacobi_tolq(float v) {
     return cudaMemcpyToSymbol(g_jacobi_tolq, &v, sizeof(float)) == cudaSuccess ? 0 : -1;
 }
 
-extern int g_jacobi_impl;
-int launch_jacobi_tc(float* G, int count, float* conv_ws, int* sweeps, cudaStream_t st);
-
 int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
-    if (C == 512 && g_jacobi_impl == 2) return launch_jacobi_tc(G, count, conv_ws, sweeps, st);
     const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
     const int max_sweeps = 40;
     const int lg = g_jacobi_lg >= 0 ? g_jacobi_lg : (C >= 512 ? 2 : 1);

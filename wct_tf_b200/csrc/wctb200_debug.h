@@ -16,9 +16,6 @@ WCTB200_API int wctb200_debug_set_conv_fuse(int mode);
 WCTB200_API int wctb200_debug_set_jacobi(int lg_groups, int stagger_cycles);
 /* Jacobi: largest pair cosine of a sweep below which no verification sweep follows (default 1e-4) */
 WCTB200_API int wctb200_debug_set_jacobi_tolq(float tolq);
-/* C = 512 eigensolver: 1 = k_jacobi<512> (FFMA rotations, columns in shared memory), 2 = k_jacobi_tc (Gram matrix and column
- * update on tcgen05); returns the implementation now selected */
-WCTB200_API int wctb200_debug_set_jacobi_impl(int impl);
 /* covariance kernel: cap on the depth of the tile ring (default 12 = 192 KB in flight at every stage size) */
 WCTB200_API int wctb200_debug_set_cov_stages(int n);
 /* EXPERIMENT: split-fp16 products per MAC in the encoder / decoder convs: 3 = a_hi b_hi + a_hi b_lo +
