@@ -74,6 +74,26 @@ WCTB200_API int wctb200_image_u8_to_f32(const uint8_t* img, size_t count, float*
 /* out[i] = (uint8) (clip(img[i],0,1) * 255)   -- truncation, like np.uint8 */
 WCTB200_API int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t* out, void* stream);
 
+/* ---- CLI image steps on the device (scope row 8f-3) ------------------------- */
+/* utils.resize_to / center_crop / center_crop_to (utils.py:29-67) -> scipy.misc.imresize(interp='bilinear'), i.e. Pillow's
+ * 8-bit ImagingResample: bit-exact restatement (separable triangle filter with support max(1, in/out), 22-bit fixed-point
+ * coefficients, horizontal pass first, uint8 rounding between the passes).  src [N][Hs][Ws][C] uint8 is resampled to
+ * Hd x Wd and the window rows [y0, y0+Hout) x columns [x0, x0+Wout) of the result is written to dst [N][Hout][Wout][C]
+ * (the centre crop of utils.py:29-53 folded in; y0 = x0 = 0, Hout = Hd, Wout = Wd for a plain resize; Hd = Hs, Wd = Ws
+ * for a plain crop).  ws: wctb200_resize_workspace_bytes(N, Hs, Ws, C, Hd, Wd, Wout) bytes of device scratch. */
+WCTB200_API size_t wctb200_resize_workspace_bytes(int N, int Hs, int Ws, int C, int Hd, int Wd, int Wout);
+WCTB200_API int wctb200_resize_bilinear_u8(const uint8_t* src, int N, int Hs, int Ws, int C, int Hd, int Wd, int y0, int x0,
+                                           int Hout, int Wout, uint8_t* dst, void* ws, size_t ws_bytes, void* stream);
+/* --keep-colors, the pixel-sized parts of coral.coral_numpy (coral.py:13-39; utils.preserve_colors_np utils.py:87-90).
+ * rgb_moments: sums[0..2] = sum x_c, sums[3..8] = sum x0x0, x0x1, x0x2, x1x1, x1x2, x2x2 over the npix RGB pixels, exact
+ * uint64 on the DEVICE (9 words).  coral_apply: dst = uint8(clip((A ((x/255 - src_mean)/src_std)) * tgt_std + tgt_mean, 0, 1)
+ * * 255) in double precision; A (3x3 row-major), the means and the stds are HOST arrays (the 3x3 algebra that produces them
+ * from the moments -- numpy's SVD inside the reference's matSqrt, coral.py:8-11 -- is host work). */
+WCTB200_API int wctb200_rgb_moments_u8(const uint8_t* img, long long npix, unsigned long long* sums, void* stream);
+WCTB200_API int wctb200_coral_apply_u8(const uint8_t* src, long long npix, const double* A, const double* src_mean,
+                                       const double* src_std, const double* tgt_mean, const double* tgt_std, uint8_t* dst,
+                                       void* stream);
+
 /* ---- encoder / decoder layers ---------------------------------------------- */
 /* Weight preparation (one-time, device side):
  * w_hwio fp32 [3][3][Cin][Cout] (Keras kernel layout, vgg_normalised.py:33 /

@@ -57,22 +57,25 @@ def _listing(path, io):
     return io.get_files(path) if os.path.isdir(path) else [path]
 
 
-def _prepare_style(path, args, io, content_img):
-    img = io.get_img(path)
+def _prepare_style(path, args, io, dimg, content_dev, device):
+    """stylize.py:86-95 on the device: decode on the host, then resize / crop / CORAL without leaving the GPU."""
+    img = dimg.to_device(io.get_img(path), device)
     if args.style_size > 0:
-        img = io.resize_to(img, args.style_size)
+        img = dimg.resize_to(img, args.style_size)
     if args.crop_size > 0:
-        img = io.center_crop(img, args.crop_size)
+        img = dimg.center_crop(img, args.crop_size)
     if args.keep_colors:
-        img = io.preserve_colors_np(img, content_img)
+        img = dimg.preserve_colors_np(img, content_dev)
     return img
 
 
-def _stylize_pair(model, content_img, style_img, args):
-    result = model.predict(content_img, style_img, args.alpha, args.swap5, args.ss_alpha, args.adain)
+def _stylize_pair(model, content_dev, style_dev, args):
+    """stylize.py:100-104; every pass takes and returns uint8 frames on the device (no host round trip between passes)."""
+    kw = dict(alpha=args.alpha, swap5=args.swap5, ss_alpha=args.ss_alpha, adain=args.adain, return_device=True)
+    result = model.predict_batch(content_dev, style_dev, **kw)
     for _ in range(args.passes - 1):
-        result = model.predict(result, style_img, args.alpha, args.swap5, args.ss_alpha, args.adain)
-    return result
+        result = model.predict_batch(result, style_dev, **kw)
+    return result[0]
 
 
 def make_model(args):
@@ -89,6 +92,7 @@ def make_model(args):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    from wct_tf_b200 import device_image as dimg
     from wct_tf_b200 import imageio as io
     t_start = time.time()
     model = make_model(args)
@@ -97,20 +101,20 @@ def main(argv=None):
         styles = list(np.random.choice(styles, args.random))
     os.makedirs(args.out_path, exist_ok=True)
 
+    device = model.engine.device
     written = 0
     for content_path in _listing(args.content_path, io):
         stem, ext = os.path.splitext(os.path.basename(content_path))
-        content_img = io.get_img(content_path)
+        content_dev = dimg.to_device(io.get_img(content_path), device)
         if args.content_size > 0:
-            content_img = io.resize_to(content_img, args.content_size)
+            content_dev = dimg.resize_to(content_dev, args.content_size)
         for style_path in styles:
-            style_img = _prepare_style(style_path, args, io, content_img)
-            result = _stylize_pair(model, content_img, style_img, args)
+            style_dev = _prepare_style(style_path, args, io, dimg, content_dev, device)
+            result = _stylize_pair(model, content_dev, style_dev, args)
             if args.concat:
-                edge = result.shape[0]
-                result = np.hstack([io._imresize(style_img, (edge, edge)), result])
+                result = dimg.concat_with_style(style_dev, result)
             target = os.path.join(args.out_path, "{}_{}{}".format(stem, os.path.splitext(os.path.basename(style_path))[0], ext))
-            io.save_img(target, result)
+            io.save_img(target, result.cpu().numpy())
             written += 1
             print("{}: Wrote stylized output image to {}".format(written, target))
     print("Finished stylizing {} outputs in {}s".format(written, time.time() - t_start))

@@ -59,41 +59,44 @@ def batches(seq, n):
         yield seq[i:i + n]
 
 
-def stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool):
-    """All frames of one clip with one style.  Frames of equal size are batched; decode of batch i+1 and the PNG writes
-    of batch i-1 overlap the GPU work of batch i."""
-    def load(f):
-        img = io.get_img(f)
-        return io.resize_to(img, args.content_size) if args.content_size > 0 else img
+def stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool, dimg, device):
+    """All frames of one clip with one style (a uint8 CUDA tensor, already resized / cropped).  Frames of equal size are
+    batched; the decode of batch i+1 and the PNG writes of batch i-1 overlap the GPU work of batch i.  Resize
+    (``--content-size``), CORAL (``--keep-colors``), every pass and the ``--concat`` thumbnail run on the device
+    (wct_tf_b200.device_image); a frame crosses PCIe once in each direction."""
+    def finish(out_f, frame_u8):
+        io.save_img(out_f, frame_u8)
 
-    def finish(out_f, stylized, style_rgb):
-        if args.concat:                                        # stylize_video.py:125-128
-            side = stylized.shape[0]
-            stylized = np.hstack([io._imresize(style_rgb, (side, side)), stylized])
-        io.save_img(out_f, stylized)
+    def prep(frames_dev):
+        return dimg.resize_to(frames_dev, args.content_size) if args.content_size > 0 else frames_dev
 
     todo = list(batches(list(zip(in_files, out_files)), max(1, args.batch)))
-    pending_loads = [pool.submit(load, f) for f, _ in todo[0]] if todo else []
+    pending_loads = [pool.submit(io.get_img, f) for f, _ in todo[0]] if todo else []
     writes, count = [], 0
     for bi, group in enumerate(todo):
         frames = [f.result() for f in pending_loads]
-        pending_loads = [pool.submit(load, f) for f, _ in todo[bi + 1]] if bi + 1 < len(todo) else []
+        pending_loads = [pool.submit(io.get_img, f) for f, _ in todo[bi + 1]] if bi + 1 < len(todo) else []
         same = all(fr.shape == frames[0].shape for fr in frames) and not args.keep_colors and not args.swap5
         if same and len(frames) > 1:
-            x = np.stack(frames)
+            x = prep(dimg.to_device(np.stack(frames), device))
             # --passes (stylize_video.py:119-121) run back to back on the device
-            out = wct_model.predict_batch(x, style_img[None], alpha=args.alpha, adain=args.adain, passes=args.passes)
+            out = wct_model.predict_batch(x, style_img[None], alpha=args.alpha, adain=args.adain, passes=args.passes,
+                                          return_device=True)
             results = [(out[i], style_img) for i in range(len(frames))]
         else:                                                  # per-frame styles (CORAL), style swap or ragged sizes
             results = []
             for fr in frames:
-                style_rgb = io.preserve_colors_np(style_img, fr) if args.keep_colors else style_img
-                o = wct_model.predict(fr, style_rgb, args.alpha, args.swap5, args.ss_alpha, args.adain)
+                fr = prep(dimg.to_device(fr, device))
+                style_rgb = dimg.preserve_colors_np(style_img, fr) if args.keep_colors else style_img
+                kw = dict(alpha=args.alpha, ss_alpha=args.ss_alpha, adain=args.adain, return_device=True)
+                o = wct_model.predict_batch(fr, style_rgb, swap5=args.swap5, **kw)
                 for _ in range(args.passes - 1):
-                    o = wct_model.predict(o, style_rgb, args.alpha, False, args.ss_alpha, args.adain)
-                results.append((o, style_rgb))
+                    o = wct_model.predict_batch(o, style_rgb, swap5=False, **kw)
+                results.append((o[0], style_rgb))
         for (_, out_f), (o, srgb) in zip(group, results):
-            writes.append(pool.submit(finish, out_f, np.array(o, copy=True), srgb))
+            if args.concat:                                    # stylize_video.py:125-128
+                o = dimg.concat_with_style(srgb, o)
+            writes.append(pool.submit(finish, out_f, dimg.to_host(o)))
             count += 1
     for w in writes:
         w.result()
@@ -104,9 +107,14 @@ def have_ffmpeg():
     return shutil.which('ffmpeg') is not None
 
 
-def main(argv=None, wct_factory=None):
+def main(argv=None, wct_factory=None, image_ops=None):
+    """``wct_factory`` / ``image_ops`` let the tests drive the frame logic with stand-ins for the engine and for
+    wct_tf_b200.device_image; the CLI always uses the real ones."""
     args = build_parser().parse_args(argv)
     from wct_tf_b200 import imageio as io
+    if image_ops is None:
+        from wct_tf_b200 import device_image as image_ops
+    dimg = image_ops
     start = time.time()
     if wct_factory is None:
         from wct_tf_b200.wct import WCT
@@ -140,11 +148,12 @@ def main(argv=None, wct_factory=None):
     total = 0
     with ThreadPoolExecutor(max_workers=8) as pool:
         for style_fullpath in style_files:                     # stylize_video.py:97
-            style_img = io.get_img(style_fullpath)
+            device = wct_model.engine.device if hasattr(wct_model, "engine") else None
+            style_img = dimg.to_device(io.get_img(style_fullpath), device)
             if args.style_size > 0:
-                style_img = io.resize_to(style_img, args.style_size)
+                style_img = dimg.resize_to(style_img, args.style_size)
             if args.crop_size > 0:
-                style_img = io.center_crop(style_img, args.crop_size)
+                style_img = dimg.center_crop(style_img, args.crop_size)
             style_prefix = os.path.basename(os.path.splitext(style_fullpath)[0])
             out_v = os.path.join(args.out_path, '{}_{}{}'.format(clip, style_prefix, ext))
             frames_dir = os.path.join(args.out_path if from_dir else tmp_dir, '{}_{}_frames'.format(clip, style_prefix))
@@ -153,7 +162,7 @@ def main(argv=None, wct_factory=None):
                 continue
             os.makedirs(frames_dir, exist_ok=True)
             out_files = [os.path.join(frames_dir, os.path.splitext(os.path.basename(f))[0] + '.png') for f in in_files]
-            n = stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool)
+            n = stylize_frames(wct_model, in_files, out_files, style_img, args, io, pool, dimg, device)
             total += n
             print("Stylized {} frames with {} -> {}".format(n, style_prefix, frames_dir))
             # stylize_video.py:137-149 re-encodes "frame_%d.png".  Frames extracted by ffmpeg carry that name; a user-supplied

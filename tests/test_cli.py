@@ -57,17 +57,30 @@ def test_video_driver_batches_frames_in_order(tmp_path):
     calls = []
 
     class FakeWCT(object):
-        def predict_batch(self, contents, styles, alpha=1, adain=False, passes=1, **kw):
+        def predict_batch(self, contents, styles, alpha=1, adain=False, passes=None, swap5=False, **kw):
+            contents = np.asarray(contents)
+            if passes is None:                                      # the per-frame path: one pass per call
+                contents = contents[None] if contents.ndim == 3 else contents
+                calls.append(("single", int(contents[0, 0, 0, 0])))
+                return contents + 1
             calls.append(("batch", [int(c[0, 0, 0]) for c in contents], styles.shape[0], passes))
-            return np.asarray(contents) + passes
+            return contents + passes
 
-        def predict(self, content, style, alpha=1, swap5=False, ss_alpha=1, adain=False):
-            calls.append(("single", int(content[0, 0, 0])))
-            return np.asarray(content) + 1
+    class HostImageOps(object):
+        """stand-in for wct_tf_b200.device_image (which needs a GPU): the frame logic only moves arrays around"""
+        to_device = staticmethod(lambda img, device=None: np.asarray(img))
+        to_host = staticmethod(lambda img: np.asarray(img))
+        resize_to = staticmethod(lambda img, size: img)
+
+        @staticmethod
+        def concat_with_style(style, result):
+            from wct_tf_b200 import imageio
+            side = result.shape[0]
+            return np.hstack([imageio._imresize(style, (side, side)), result])
 
     out = tmp_path / "out"
     n = V.main(["--relu-targets", "relu1_1", "--in-path", str(frames), "--style-path", str(style), "--out-path", str(out),
-                "--batch", "2", "--passes", "2", "--concat"], wct_factory=lambda a: FakeWCT())
+                "--batch", "2", "--passes", "2", "--concat"], wct_factory=lambda a: FakeWCT(), image_ops=HostImageOps)
     assert n == 6
     assert calls[0] == ("batch", [1, 2], 1, 2)                                # first batch: one shared style, both passes in one call
     assert [c[1] for c in calls if c[0] == "batch"] == [[1, 2], [10, 11]]     # frames 3|4 differ in size -> per-frame

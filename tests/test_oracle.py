@@ -146,3 +146,35 @@ def test_reference_code_live_reproduces_fixture_if_present(tmp_path):
                                            ss_alpha=float(g["ss_alpha"]))
     assert np.abs(out - g["out_ref_fp64"]).max() <= 1e-12
     assert "tensorflow" not in __import__("sys").modules or not hasattr(__import__("sys").modules["tensorflow"], "placeholder_with_default")
+
+
+# ---------------------------------------------------------------------------
+# scope row 8f-3: the image steps of the CLI
+# ---------------------------------------------------------------------------
+RESIZE_CASES = [(37, 53, 20, 29), (37, 53, 74, 91), (64, 64, 64, 64), (100, 40, 512, 205), (513, 301, 256, 150), (5, 7, 1, 1),
+                (1, 1, 9, 4), (360, 640, 256, 455), (33, 70, 33, 35), (33, 70, 66, 70), (300, 400, 299, 401), (2, 3, 64, 64)]
+
+
+@pytest.mark.parametrize("h,w,oh,ow", RESIZE_CASES)
+def test_resample_oracle_is_pillow_bit_for_bit(h, w, oh, ow):
+    """The restatement of Pillow's 8-bit bilinear ImagingResample (what scipy.misc.imresize(interp='bilinear') ran,
+    utils.py:48,67) against the Pillow installed in this image: identical bytes for down-, up-scaling, identity and
+    degenerate sizes."""
+    from PIL import Image
+    from oracle import image_ops
+    img = np.random.default_rng(h * 1000 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+    assert np.array_equal(image_ops.resample_bilinear_u8(img, oh, ow), want)
+
+
+def test_image_oracle_helpers_follow_the_reference_rules():
+    from oracle import image_ops
+    img = np.random.default_rng(3).integers(0, 256, (40, 64, 3), dtype=np.uint8)
+    assert image_ops.resize_to(img, 20).shape == (20, 32, 3)                     # short side, aspect kept (utils.py:55-67)
+    assert image_ops.resize_to(img.transpose(1, 0, 2), 20).shape == (32, 20, 3)
+    assert np.array_equal(image_ops.center_crop(img, 32), img[4:36, 16:48])       # utils.py:29-38
+    assert image_ops.center_crop(img[:10, :10], 16).shape == (16, 16, 3)          # too small -> upscale first
+    assert image_ops.center_crop_to(img, 48, 64).shape == (48, 64, 3)             # utils.py:40-53 (upscale by the larger ratio)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coral_keep_colors.npz"))
+    assert np.abs(image_ops.coral(g["style"] / 255., g["content"] / 255.) - g["coraled"]).max() < 1e-9   # reference's coral.py output
+    assert np.array_equal(image_ops.preserve_colors(g["style"], g["content"]), g["out"])

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libwctb200.so")
 RELU = 1
 CLIP01 = 2
 HALO_EDGE = 4
+EINVAL, ECUDA, EWS, EDEVICE = -1, -2, -3, -4       # include/wctb200.h
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -25,6 +26,10 @@ SIGNATURES = {
     "wctb200_act_to_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "wctb200_image_u8_to_f32": (_i, [_vp, _sz, _vp, _vp]),
     "wctb200_image_f32_to_u8": (_i, [_vp, _sz, _vp, _vp]),
+    "wctb200_resize_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "wctb200_resize_bilinear_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "wctb200_rgb_moments_u8": (_i, [_vp, C.c_longlong, _vp, _vp]),
+    "wctb200_coral_apply_u8": (_i, [_vp, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wctb200_conv_weight_bytes": (_sz, [_i, _i, _i]),
     "wctb200_prep_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "wctb200_prep_conv_weights_up2": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -81,6 +81,12 @@ int device_sm_count() {
 // launchers (layers.cu / wct.cu)
 int launch_u8_to_f32(const uint8_t*, size_t, float*, cudaStream_t);
 int launch_f32_to_u8(const float*, size_t, uint8_t*, cudaStream_t);
+size_t resize_workspace_bytes(int N, int Hs, int Ws, int C, int Hd, int Wd, int Wout);
+int launch_resize_u8(const uint8_t* src, int N, int Hs, int Ws, int C, int Hd, int Wd, int y0, int x0, int Hout, int Wout,
+                     uint8_t* dst, void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_rgb_moments(const uint8_t* img, long long npix, unsigned long long* sums, cudaStream_t st);
+int launch_coral_apply(const uint8_t* src, long long npix, const double* A, const double* sm, const double* ss, const double* tm,
+                       const double* ts, uint8_t* dst, cudaStream_t st);
 int launch_act_from_f32(const float*, ActGeom, __half*, cudaStream_t);
 int launch_act_to_f32(const __half*, ActGeom, float*, cudaStream_t);
 int launch_prep_weights(const float*, int, int, int, __half*, cudaStream_t);
@@ -176,6 +182,32 @@ int wctb200_image_f32_to_u8(const float* img, size_t count, uint8_t* out, void* 
     WCTB_REQUIRE(img && out, "image_f32_to_u8: null pointer");
     if (count == 0) return 0;
     return launch_f32_to_u8(img, count, out, ST(stream));
+}
+
+static bool resize_args_ok(int N, int Hs, int Ws, int C, int Hd, int Wd) {
+    return N >= 1 && Hs >= 1 && Ws >= 1 && C >= 1 && C <= 4 && Hd >= 1 && Wd >= 1 && Hs <= (1 << 15) && Ws <= (1 << 15) &&
+           Hd <= (1 << 15) && Wd <= (1 << 15);
+}
+size_t wctb200_resize_workspace_bytes(int N, int Hs, int Ws, int C, int Hd, int Wd, int Wout) {
+    if (!resize_args_ok(N, Hs, Ws, C, Hd, Wd) || Wout < 1 || Wout > Wd) return 0;
+    return resize_workspace_bytes(N, Hs, Ws, C, Hd, Wd, Wout);
+}
+int wctb200_resize_bilinear_u8(const uint8_t* src, int N, int Hs, int Ws, int C, int Hd, int Wd, int y0, int x0, int Hout,
+                               int Wout, uint8_t* dst, void* ws, size_t ws_bytes, void* stream) {
+    WCTB_REQUIRE(src && dst && ws, "resize_bilinear_u8: null pointer");
+    WCTB_REQUIRE(resize_args_ok(N, Hs, Ws, C, Hd, Wd), "resize_bilinear_u8: bad geometry N=%d %dx%dx%d -> %dx%d", N, Hs, Ws, C, Hd, Wd);
+    WCTB_REQUIRE(y0 >= 0 && x0 >= 0 && Hout >= 1 && Wout >= 1 && y0 + Hout <= Hd && x0 + Wout <= Wd,
+                 "resize_bilinear_u8: window [%d,%d)x[%d,%d) outside %dx%d", y0, y0 + Hout, x0, x0 + Wout, Hd, Wd);
+    return launch_resize_u8(src, N, Hs, Ws, C, Hd, Wd, y0, x0, Hout, Wout, dst, ws, ws_bytes, ST(stream));
+}
+int wctb200_rgb_moments_u8(const uint8_t* img, long long npix, unsigned long long* sums, void* stream) {
+    WCTB_REQUIRE(img && sums && npix >= 1 && npix < (1ll << 40), "rgb_moments_u8: bad arguments");
+    return launch_rgb_moments(img, npix, sums, ST(stream));
+}
+int wctb200_coral_apply_u8(const uint8_t* src, long long npix, const double* A, const double* src_mean, const double* src_std,
+                           const double* tgt_mean, const double* tgt_std, uint8_t* dst, void* stream) {
+    WCTB_REQUIRE(src && dst && A && src_mean && src_std && tgt_mean && tgt_std && npix >= 1, "coral_apply_u8: bad arguments");
+    return launch_coral_apply(src, npix, A, src_mean, src_std, tgt_mean, tgt_std, dst, ST(stream));
 }
 
 size_t wctb200_conv_weight_bytes(int taps, int Cin, int Cout) {

@@ -90,13 +90,14 @@ class WCT(object):
             return a.to(dev, non_blocking=True).contiguous()
 
         if swap5 and self.ss_stride != 1:
-            # wct.py:84-90: with a stride the filter may not fit; centre-crop the content to a size it tiles
-            from .imageio import center_crop_to, swap_filter_fit
-            arr = contents.cpu().numpy() if isinstance(contents, torch.Tensor) else np.asarray(contents)
-            arr = arr[None] if arr.ndim == 3 else arr
-            refit, H, W = swap_filter_fit(arr.shape[1], arr.shape[2], self.ss_patch_size, self.ss_stride)
-            if refit:
-                contents = np.stack([center_crop_to(a, H, W) for a in arr])
+            # wct.py:84-90: with a stride the filter may not fit; centre-crop the content (on the device) to a size it tiles
+            from .device_image import center_crop_to
+            from .imageio import swap_filter_fit
+            with torch.cuda.device(dev):
+                contents = to_dev(contents)
+                refit, H, W = swap_filter_fit(contents.shape[1], contents.shape[2], self.ss_patch_size, self.ss_stride)
+                if refit:
+                    contents = center_crop_to(contents, H, W)
         with torch.cuda.device(dev):
             c = to_dev(contents)
             s = to_dev(styles)
