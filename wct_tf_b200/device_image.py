@@ -27,7 +27,7 @@ def to_device(img, device="cuda:0"):
     """numpy / torch uint8 HxWxC -> contiguous CUDA tensor (one H2D copy)."""
     if not torch.cuda.is_available():
         raise _capi.WctB200Error("no CUDA device: the image steps have no CPU fallback")
-    t = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img, dtype=np.uint8))
+    t = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.array(img, dtype=np.uint8, order="C"))   # own, writable copy (PIL arrays are read-only)
     if t.dtype != torch.uint8:
         raise TypeError("expected a uint8 image, got %s" % t.dtype)
     return t.to(device, non_blocking=True).contiguous()
