@@ -256,11 +256,25 @@ def test_maxpool_same_and_upsample(shape):
     assert np.array_equal(padded, np.pad(ref, ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
 
 
+@pytest.mark.parametrize("impl", ["tensor-core", "simt"])
 @pytest.mark.parametrize("clip", [False, True])
 @pytest.mark.parametrize("shape", [(1, 8, 8, 64), (2, 5, 7, 64), (1, 33, 3, 64),
-                                   (1, 32, 32, 64), (2, 37, 45, 64), (1, 64, 96, 64), (1, 40, 33, 128)])   # >= 32x32: tiled kernel
-def test_conv_tail(shape, clip):
+                                   (1, 32, 32, 64), (2, 37, 45, 64), (1, 64, 96, 64), (1, 40, 33, 128),   # >= 32x32: tiled SIMT kernel
+                                   (1, 70, 300, 64), (2, 65, 127, 64), (1, 31, 253, 64)])                 # several strips / row chunks
+def test_conv_tail(shape, clip, impl):
+    """64-channel tails run as the transposed tensor-core product (conv_tail_tc.cu); the SIMT kernels serve other widths and
+    stay covered through the debug knob."""
     n, h, w, c = shape
+    if impl == "simt":
+        U.lib().wctb200_debug_set_conv_tail_tc(0)
+    try:
+        _conv_tail_case(n, h, w, c, clip)
+    finally:
+        U.lib().wctb200_debug_set_conv_tail_tc(1)
+
+
+def _conv_tail_case(n, h, w, c, clip):
+    shape = (n, h, w, c)
     rng = np.random.default_rng(11)
     x = np.maximum(rng.normal(0.3, 1.0, shape), 0).astype(np.float32)
     k = (rng.normal(0, 1, (3, 3, c, 3)) * 0.05).astype(np.float32)

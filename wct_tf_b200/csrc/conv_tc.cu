@@ -375,7 +375,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 3-D fp16 tensor map [d2][d1][d0] (d0 contiguous), box {64, box1, 1}, 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+int make_tensor_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                     uint64_t stride2_bytes, uint32_t box1) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -441,10 +441,10 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     if (g_conv_bn_override && Cout % g_conv_bn_override == 0) BN = g_conv_bn_override;
 
     CUtensorMap mA, mB;
-    int rc = make_map(&mA, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
+    int rc = make_tensor_map_3d(&mA, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
     if (rc) return rc;
     const uint64_t K = (uint64_t)taps * Cin;
-    rc = make_map(&mB, w_split, K, (uint64_t)Cout, (uint64_t)2 * wsets, K * 2, K * Cout * 2, (uint32_t)BN);
+    rc = make_tensor_map_3d(&mB, w_split, K, (uint64_t)Cout, (uint64_t)2 * wsets, K * 2, K * Cout * 2, (uint32_t)BN);
     if (rc) return rc;
 
     ConvParams p;

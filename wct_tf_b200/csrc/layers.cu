@@ -577,7 +577,12 @@ int launch_conv_head(const float* img, int N, int H, int W, const float* w, cons
     return 0;
 }
 int g_conv_tail_impl = 2;      // 1 = per-pixel kernel, 2 = shared-memory tiles (default for images >= 32x32)
+int launch_conv_tail_tc(const __half* in, ActGeom gi, const float* w, const float* b, int flags, float* img, cudaStream_t st);
 int launch_conv_tail(const __half* in, ActGeom gi, const float* w, const float* b, int flags, float* img, cudaStream_t st) {
+    {
+        const int rc = launch_conv_tail_tc(in, gi, w, b, flags, img, st);     // 64-channel tail on the tensor cores (conv_tail_tc.cu)
+        if (rc <= 0) return rc;
+    }
     if (g_conv_tail_impl == 2 && gi.C % TT_CH == 0 && gi.H >= TT_H && gi.W >= TT_W && gi.C <= 128) {
         const size_t tsmem = ((size_t)TT_ACT_F4 + TT_STAGE_F4 + (size_t)9 * (gi.C / 4) * 3) * sizeof(float4);
         constexpr size_t tsmem_max = ((size_t)TT_ACT_F4 + TT_STAGE_F4 + (size_t)9 * (128 / 4) * 3) * sizeof(float4);   // C = 128

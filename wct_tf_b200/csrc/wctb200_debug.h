@@ -22,6 +22,8 @@ WCTB200_API int wctb200_debug_set_cov_stages(int n);
  * a_lo b_hi (default, fp32-class), 2 = without a_lo b_hi (activations effectively fp16), 1 = a_hi b_hi only.  Returns the
  * value now selected.  With the fused MMA (N = 2*tile) 2 and 1 cost the same: a_hi [b_hi|b_lo] is one instruction. */
 WCTB200_API int wctb200_debug_set_conv_products(int n);
+/* decoder tail (64 -> 3): 1 = transposed tensor-core product (conv_tail_tc.cu, default), 0 = SIMT kernels of layers.cu */
+WCTB200_API int wctb200_debug_set_conv_tail_tc(int on);
 #ifdef __cplusplus
 }
 #endif
