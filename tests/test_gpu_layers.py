@@ -60,8 +60,20 @@ def test_act_roundtrip_and_reflect_halo(shape):
     assert np.array_equal(padded, ref)
 
 
-@pytest.mark.parametrize("shape", [(1, 6, 5), (2, 16, 12), (1, 33, 20)])
-def test_conv_head_matches_preprocess_plus_conv1_1(shape):
+@pytest.mark.parametrize("impl", ["tensor-core", "simt"])
+@pytest.mark.parametrize("shape", [(1, 6, 5), (2, 16, 12), (1, 33, 20), (3, 37, 53), (1, 128, 130), (2, 2, 2)])
+def test_conv_head_matches_preprocess_plus_conv1_1(shape, impl):
+    """the head runs on the tensor cores with an operand built in shared memory (conv_head_tc.cu); the SIMT kernel stays
+    covered through the debug knob"""
+    if impl == "simt":
+        U.lib().wctb200_debug_set_conv_head_tc(0)
+    try:
+        _conv_head_case(shape)
+    finally:
+        U.lib().wctb200_debug_set_conv_head_tc(1)
+
+
+def _conv_head_case(shape):
     from wct_tf_b200.weights import make_synthetic_weights
     n, h, w = shape
     wts = make_synthetic_weights(3)

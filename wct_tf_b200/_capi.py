@@ -61,6 +61,7 @@ DEBUG_SIGNATURES = {
     "wctb200_debug_set_jacobi_tolq": (_i, [_f]),
     "wctb200_debug_set_conv_products": (_i, [_i]),
     "wctb200_debug_set_conv_tail_tc": (_i, [_i]),
+    "wctb200_debug_set_conv_head_tc": (_i, [_i]),
     "wctb200_debug_set_cov_stages": (_i, [_i]),
 }
 

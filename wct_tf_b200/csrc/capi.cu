@@ -117,6 +117,7 @@ extern int g_conv_oversub;
 extern int g_conv_fuse;
 extern int g_conv_products;
 extern int g_conv_tail_tc;
+extern int g_conv_head_tc;
 extern int g_cov_max_stages;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
@@ -356,6 +357,10 @@ int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
 int wctb200_debug_set_cov_stages(int n) {
     if (n >= 1 && n <= 12) g_cov_max_stages = n;
     return g_cov_max_stages;
+}
+int wctb200_debug_set_conv_head_tc(int on) {
+    if (on == 0 || on == 1) g_conv_head_tc = on;
+    return g_conv_head_tc;
 }
 int wctb200_debug_set_conv_tail_tc(int on) {
     if (on == 0 || on == 1) g_conv_tail_tc = on;

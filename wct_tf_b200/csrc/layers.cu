@@ -571,7 +571,12 @@ int launch_conv3x3_ref(const __half* in, ActGeom gi, const float* w, const float
     WCTB_CHECK_LAUNCH("k_conv3x3_ref");
     return 0;
 }
+int launch_conv_head_tc(const float* img, int N, int H, int W, const float* w, const float* b, __half* out, cudaStream_t st);
 int launch_conv_head(const float* img, int N, int H, int W, const float* w, const float* b, __half* out, cudaStream_t st) {
+    {
+        const int rc = launch_conv_head_tc(img, N, H, W, w, b, out, st);      // tensor-core head (conv_head_tc.cu)
+        if (rc <= 0) return rc;
+    }
     k_conv_head<<<grid_for((long long)N * H * ((W + 3) / 4) * 8, 256), 256, 0, st>>>(img, N, H, W, w, b, out);
     WCTB_CHECK_LAUNCH("k_conv_head");
     return 0;

@@ -24,6 +24,8 @@ WCTB200_API int wctb200_debug_set_cov_stages(int n);
 WCTB200_API int wctb200_debug_set_conv_products(int n);
 /* decoder tail (64 -> 3): 1 = transposed tensor-core product (conv_tail_tc.cu, default), 0 = SIMT kernels of layers.cu */
 WCTB200_API int wctb200_debug_set_conv_tail_tc(int on);
+/* encoder head (3 -> 64): 1 = tensor cores with an operand built in shared memory (conv_head_tc.cu, default), 0 = SIMT */
+WCTB200_API int wctb200_debug_set_conv_head_tc(int on);
 #ifdef __cplusplus
 }
 #endif
