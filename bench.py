@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--groups", type=int, default=2, help="sub-batches per step run as independent stream pairs")
     ap.add_argument("--no-prio", action="store_true", help="tuning: all streams at the same priority")
     ap.add_argument("--no-fuse-upsample", action="store_true", help="tuning: separate upsample2 kernels + 9-tap convs")
+    ap.add_argument("--no-fuse-pool", action="store_true", help="tuning: separate maxpool2 kernels after conv1_2/2_2/3_4/4_4")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel profiling steps")
     ap.add_argument("--jacobi-tolq", type=float, default=0.0, help="tuning: eigensolver predicted-convergence level (0 = library default)")
     args = ap.parse_args()
@@ -242,8 +243,9 @@ def main():
     B = hi - lo                                          # frames this rank processes per step
     weights = make_synthetic_weights(42)
     wct = WCT(relu_targets=TARGETS, device="cuda:%d" % local, weights=weights, semantics=SEMANTICS)
-    if args.no_fuse_upsample:
-        wct.engine = Engine(weights, TARGETS, device="cuda:%d" % local, semantics=SEMANTICS, fuse_upsample=False)
+    if args.no_fuse_upsample or args.no_fuse_pool:
+        wct.engine = Engine(weights, TARGETS, device="cuda:%d" % local, semantics=SEMANTICS, fuse_upsample=not args.no_fuse_upsample,
+                            fuse_pool=not args.no_fuse_pool)
     eng = wct.engine
     if args.oversub:
         eng.lib.wctb200_debug_set_conv_oversub(args.oversub)

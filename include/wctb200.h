@@ -55,6 +55,10 @@ extern "C" {
 #define WCTB200_HALO_EDGE 4  /* conv3x3: write an EDGE-replicated halo instead of the reflect halo -- for an output
                                 that is consumed by wctb200_conv3x3_up2 only (UpSampling2D follows, model.py:293) */
 
+#define WCTB200_POOL2    8   /* conv3x3: MaxPooling2D 2x2/2 'same' (vgg_normalised.py:41-42) folded into the epilogue: the
+                                output is [N, ceil(H/2), ceil(W/2), Cout] (>= 2x2) and the full-resolution tensor is never
+                                written -- for conv1_2 / 2_2 / 3_4 / 4_4, whose only consumer is the pool */
+
 WCTB200_API int         wctb200_abi_version(void);
 WCTB200_API const char* wctb200_last_error(void);
 /* Synchronises `stream` and returns WCTB200_EDEVICE if any kernel since the last
@@ -110,7 +114,8 @@ WCTB200_API int wctb200_prep_conv_weights_up2(const float* w_hwio, int Cin, int 
 
 /* Conv2DReflect 3x3 (+bias, optional ReLU) on tensor cores (tcgen05, split-fp16 x3):
  * replaces `Lambda(pad_reflect) -> Conv2D(valid)` of vgg_normalised.py:28-40 and
- * model.py:291.  Cin, Cout multiples of 64.  in/out: SPF16 [N,H,W,Cin] -> [N,H,W,Cout]. */
+ * model.py:291.  Cin, Cout multiples of 64.  in/out: SPF16 [N,H,W,Cin] -> [N,H,W,Cout]
+ * ([N,ceil(H/2),ceil(W/2),Cout] with WCTB200_POOL2). */
 WCTB200_API int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin,
                     const void* w_split, const float* bias, int Cout, int flags,
                     void* act_out, void* stream);

@@ -300,3 +300,79 @@ def _conv_tail_case(n, h, w, c, clip):
     if clip:
         ref = np.clip(ref, 0, 1)
     assert_close(img.cpu().numpy(), ref, name="conv_tail")
+
+
+POOL_CASES = [
+    # N, H, W, Cin, Cout
+    (1, 8, 8, 64, 64),
+    (2, 6, 10, 64, 64),
+    (1, 7, 9, 64, 64),          # odd sizes: 'same' pooling keeps the ragged last row / column (ceil)
+    (1, 4, 4, 128, 128),
+    (2, 9, 70, 128, 128),       # two column segments, the second ragged
+    (1, 33, 130, 64, 64),       # three segments, odd height
+    (1, 16, 16, 256, 256),
+    (1, 12, 20, 512, 512),
+    (3, 5, 5, 64, 128),
+]
+
+
+@pytest.mark.parametrize("bn", [0, 64])
+@pytest.mark.parametrize("case", POOL_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_pool2_equals_conv_then_maxpool(case, bn):
+    """WCTB200_POOL2 (MaxPooling2D 2x2/2 'same' of vgg_normalised.py:41-42 folded into the conv epilogue) gives the SAME bits as
+    wctb200_conv3x3 -> wctb200_maxpool2 (max commutes with the monotone scale/bias/ReLU/split), reflect halo of the pooled map
+    included, and matches the float64 reference."""
+    n, h, w, cin, cout = case
+    if bn and cout % bn:
+        pytest.skip("tile does not divide Cout")
+    x, k, b = _conv_inputs((n, h, w, cin, cout, True), 21)
+    lib = U.lib()
+    xin = U.act_from_numpy(x)
+    wsp = torch.empty(lib.wctb200_conv_weight_bytes(9, cin, cout), dtype=torch.uint8, device="cuda")
+    d_k, d_b = U.dev(k), U.dev(b)
+    _capi.check(lib.wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsp.data_ptr(), U.stream()))
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    full = U.act_alloc(n, h, w, cout)
+    two_step = U.act_alloc(n, ho, wo, cout)
+    fused = U.act_alloc(n, ho, wo, cout)
+    lib.wctb200_debug_set_conv_bn(bn)
+    try:
+        _capi.check(lib.wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsp.data_ptr(), d_b.data_ptr(), cout, _capi.RELU,
+                                        full.data_ptr(), U.stream()))
+        _capi.check(lib.wctb200_maxpool2(full.data_ptr(), n, h, w, cout, two_step.data_ptr(), U.stream()))
+        _capi.check(lib.wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsp.data_ptr(), d_b.data_ptr(), cout,
+                                        _capi.RELU | _capi.POOL2, fused.data_ptr(), U.stream()))
+        U.check_device()
+    finally:
+        lib.wctb200_debug_set_conv_bn(0)
+    a = U.act_raw_padded(fused, n, ho, wo, cout)
+    assert np.isfinite(a).all(), "pooled cells left unwritten"
+    assert np.array_equal(a, U.act_raw_padded(two_step, n, ho, wo, cout))
+    assert np.array_equal(a, np.pad(a[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
+    ref = conv_ref64(U.split_repr(x), k, b, True)
+    t = torch.from_numpy(ref).permute(0, 3, 1, 2)
+    ref = F.max_pool2d(t, 2, 2, ceil_mode=True).permute(0, 2, 3, 1).numpy()
+    assert_close(a[:, 1:-1, 1:-1], ref, tol=1e-5, name="conv_pool_%d_%d" % (cin, cout))
+
+
+@pytest.mark.parametrize("case", [(4, 200, 300, 64, 64), (2, 130, 262, 128, 128), (1, 96, 96, 512, 512)], ids=lambda c: "x".join(map(str, c)))
+def test_conv3x3_pool2_many_tiles_per_cta(case):
+    """More tiles than CTAs (the persistent loop, the row-pair exchange buffer and the accumulator ring are reused back to back):
+    POOL2 == conv -> maxpool by value on every cell, halo included."""
+    n, h, w, cin, cout = case
+    x, k, b = _conv_inputs((n, h, w, cin, cout, True), 31)
+    lib = U.lib()
+    xin = U.act_from_numpy(x)
+    wsp = torch.empty(lib.wctb200_conv_weight_bytes(9, cin, cout), dtype=torch.uint8, device="cuda")
+    d_k, d_b = U.dev(k), U.dev(b)
+    _capi.check(lib.wctb200_prep_conv_weights(d_k.data_ptr(), 9, cin, cout, wsp.data_ptr(), U.stream()))
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    full, two_step, fused = U.act_alloc(n, h, w, cout), U.act_alloc(n, ho, wo, cout), U.act_alloc(n, ho, wo, cout)
+    _capi.check(lib.wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsp.data_ptr(), d_b.data_ptr(), cout, _capi.RELU, full.data_ptr(), U.stream()))
+    _capi.check(lib.wctb200_maxpool2(full.data_ptr(), n, h, w, cout, two_step.data_ptr(), U.stream()))
+    _capi.check(lib.wctb200_conv3x3(xin.data_ptr(), n, h, w, cin, wsp.data_ptr(), d_b.data_ptr(), cout, _capi.RELU | _capi.POOL2,
+                                    fused.data_ptr(), U.stream()))
+    U.check_device()
+    a = U.act_raw_padded(fused, n, ho, wo, cout)
+    assert np.isfinite(a).all()
+    assert np.array_equal(a, U.act_raw_padded(two_step, n, ho, wo, cout))

@@ -354,3 +354,24 @@ def test_passes_on_device_equal_host_round_trips(weights):
     assert np.array_equal(fused, twice)
     dev = wct.predict_batch(c, s, alpha=0.6, passes=2, return_device=True)
     assert dev.is_cuda and dev.dtype == torch.uint8 and np.array_equal(dev.cpu().numpy(), twice)
+
+
+def test_pool_fused_encoder_matches_separate_pool(weights):
+    """Engine(fuse_pool=True) (MaxPooling2D in the conv epilogue, WCTB200_POOL2) vs Engine(fuse_pool=False).  The pooled maps
+    are equal BY VALUE (tests/test_gpu_layers.py::test_conv3x3_pool2_equals_conv_then_maxpool), but a value that sits exactly
+    between two fp16 numbers can be stored as (hi, +half ulp) or (hi + ulp, -half ulp): the separate pool re-splits the merged
+    value (ties to even), the fused epilogue splits the fp32 accumulator, so the NEXT conv sees different operand bits and its
+    dropped lo*lo term differs at the 2^-22 level.  Encoder outputs must therefore agree to ~1e-6 relative, not bit for bit."""
+    targets = ["relu5_1", "relu4_1", "relu3_1", "relu2_1", "relu1_1"]
+    a = Engine(weights, targets, fuse_pool=True)
+    b = Engine(weights, targets, fuse_pool=False)
+    for (hw, seed) in [((64, 96), 5), ((51, 70), 6), ((130, 67), 7)]:
+        rng = np.random.default_rng(seed)
+        img = torch.from_numpy(rng.random((2,) + hw + (3,)).astype(np.float32)).cuda()
+        for t in targets:
+            fa, _ = a.encode(img, t)
+            fb, _ = b.encode(img, t)
+            xa, xb = a.act_to_f32(fa), b.act_to_f32(fb)
+            assert xa.shape == xb.shape
+            assert (xa - xb).abs().max().item() <= 2e-6 * (1.0 + xb.abs().max().item()), (hw, t)
+    a.check_device()

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libwctb200.so")
 RELU = 1
 CLIP01 = 2
 HALO_EDGE = 4
+POOL2 = 8
 EINVAL, ECUDA, EWS, EDEVICE = -1, -2, -3, -4       # include/wctb200.h
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t

@@ -229,7 +229,7 @@ int wctb200_prep_conv_weights_up2(const float* w_hwio, int Cin, int Cout, void* 
 int wctb200_conv3x3(const void* act_in, int N, int H, int W, int Cin, const void* w_split, const float* bias, int Cout,
                     int flags, void* act_out, void* stream) {
     WCTB_REQUIRE(act_in && w_split && act_out, "conv3x3: null pointer");
-    WCTB_REQUIRE((flags & ~(WCTB200_RELU | WCTB200_HALO_EDGE)) == 0, "conv3x3: unknown flag bits 0x%x", flags);
+    WCTB_REQUIRE((flags & ~(WCTB200_RELU | WCTB200_HALO_EDGE | WCTB200_POOL2)) == 0, "conv3x3: unknown flag bits 0x%x", flags);
     return launch_conv_tc(CONV_3X3, HCP(act_in), N, H, W, Cin, HCP(w_split), 1, weight_scale_ptr(HCP(w_split), 9, Cin, Cout),
                           bias, Cout, flags, HP(act_out), ST(stream));
 }

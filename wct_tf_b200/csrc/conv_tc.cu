@@ -51,6 +51,8 @@ struct ConvParams {
     int kw;               // CONV_TAPS: filter width (top-left anchored kw x kw correlation, style-swap patches)
     int products;         // 3 (default): a_hi b_hi + a_hi b_lo + a_lo b_hi; 2: without a_lo b_hi; 1: a_hi b_hi only (experiment knob)
     int per_image;        // tiles never straddle images; weight/bias set = image index (APPLY with nsets > 1)
+    int pool;             // CONV_3X3 + WCTB200_POOL2: M tile = 2 image rows x 64 columns, 2x2 max-pool in the epilogue
+    int pool_tx, pool_ho; // pool: column segments per row pair, row pairs per image
     int nsets;
     int tiles_per_image;
     int flags;
@@ -115,7 +117,17 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
     const long long HpWp = (long long)p.Hp * p.Wp;
     t.n0 = nt * BN;
     t.cls = 0;
-    if (p.mode == CONV_UP2) {
+    if (p.pool) {
+        // mt = (image * row pairs + pair i) * column segments + t; rows 2i, 2i+1, interior columns [64t, 64t + 64)
+        const int t_ = mt % p.pool_tx;
+        const int r_ = mt / p.pool_tx;
+        const int i_ = r_ % p.pool_ho;
+        const int img = r_ / p.pool_ho;
+        t.p0 = img * HpWp + (long long)(2 * i_ + 1) * p.Wp + 1 + 64 * t_;     // first position of the UPPER row segment
+        t.p_end = p.P;
+        t.set = 0;
+        t.cls = t_;                          // (reused: column segment; the row pair is recovered from p0)
+    } else if (p.mode == CONV_UP2) {
         // cout tile fastest, then the 4 parity classes: CTAs running together share one activation tile in L2
         t.cls = mt & 3;
         mt >>= 2;
@@ -138,8 +150,8 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile, i
 
 template <int BN, bool FUSE_>
 __global__ void __launch_bounds__(Conv2Cfg<BN, FUSE_>::THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvParams p,
-                const int total_tiles, const int n_tiles) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const __grid_constant__ CUtensorMap mapA64, const ConvParams p, const int total_tiles, const int n_tiles) {
     using Cfg = Conv2Cfg<BN, FUSE_>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -202,8 +214,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const int row = (int)(tc.p0 + off);
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
-                    tma_load_3d(st, &mapA, &full[s], ks * Cfg::BK, row, 0);
-                    tma_load_3d(st + Cfg::A_BYTES, &mapA, &full[s], ks * Cfg::BK, row, 1);
+                    if (p.pool) {
+                        // two 64-position boxes per plane: the segment of image row 2i and the one below it
+                        tma_load_3d(st, &mapA64, &full[s], ks * Cfg::BK, row, 0);
+                        tma_load_3d(st + Cfg::A_BYTES / 2, &mapA64, &full[s], ks * Cfg::BK, row + p.Wp, 0);
+                        tma_load_3d(st + Cfg::A_BYTES, &mapA64, &full[s], ks * Cfg::BK, row, 1);
+                        tma_load_3d(st + Cfg::A_BYTES + Cfg::A_BYTES / 2, &mapA64, &full[s], ks * Cfg::BK, row + p.Wp, 1);
+                    } else {
+                        tma_load_3d(st, &mapA, &full[s], ks * Cfg::BK, row, 0);
+                        tma_load_3d(st + Cfg::A_BYTES, &mapA, &full[s], ks * Cfg::BK, row, 1);
+                    }
                     tma_load_3d(st + 2 * Cfg::A_BYTES, &mapB, &full[s], tap * p.Cin + ks * Cfg::BK, tc.n0, tc.set * 2);
                     tma_load_3d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &mapB, &full[s], tap * p.Cin + ks * Cfg::BK,
                                 tc.n0, tc.set * 2 + 1);
@@ -263,7 +283,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int et = threadIdx.x - 64;                     // 0 .. 32*EPI_WARPS-1
         constexpr int ETHREADS = 32 * Cfg::EPI_WARPS;
         const bool up2 = p.mode == CONV_UP2;
-        ActGeom go(p.N, up2 ? 2 * p.H : p.H, up2 ? 2 * p.W : p.W, p.Cout);
+        ActGeom go(p.N, up2 ? 2 * p.H : (p.pool ? (p.H + 1) / 2 : p.H), up2 ? 2 * p.W : (p.pool ? (p.W + 1) / 2 : p.W), p.Cout);
         go.edge = (p.flags & WCTB200_HALO_EDGE) ? 1 : 0;
         const bool relu = (p.flags & WCTB200_RELU) != 0;
         const float wsc = p.wscale ? __ldg(p.wscale) : 1.f;
@@ -312,6 +332,52 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[b]);      // buffer may be overwritten
+            }
+            if (Cfg::STG_BYTES > 0 && p.pool) {
+                // ---- MaxPooling2D 2x2/2 'same' (vgg_normalised.py:41-42) on the raw accumulators: max commutes with the
+                // monotone  *scale + bias -> ReLU -> split  that follows.  Tile rows 0..63 = image row 2i, 64..127 = row 2i+1.
+                const int tpos = g * 32 + lane;
+                const int xloc = tpos & 63;
+                const unsigned int hpwp = (unsigned int)(p.Hp * p.Wp);
+                const unsigned int n = (unsigned int)tc.p0 / hpwp;
+                const int yy0 = (int)(((unsigned int)tc.p0 - n * hpwp) / (unsigned int)p.Wp);   // padded row of image row 2i
+                const int y = yy0 - 1 + (tpos >> 6);
+                const int x = 64 * tc.cls + xloc;
+                const bool valid = y < p.H && x < p.W;
+                const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+                for (int j = 0; j < Cfg::NACC; ++j) {
+                    const float v = valid ? acc[j] : ninf;
+                    acc[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));         // horizontal pair (x even, x+1)
+                }
+                uint8_t* stg_all = aux + Cfg::AUX_BYTES;
+                if (g >= 2) {                                                       // lower image row: hand over to warp g-2
+                    if (!(lane & 1)) {
+                        float* xb = reinterpret_cast<float*>(stg_all + e * 8192) + (lane >> 1);
+#pragma unroll
+                        for (int j = 0; j < Cfg::NACC; ++j) xb[j * 16] = acc[j];
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+                if (g < 2) {
+                    if (!(lane & 1)) {
+                        // epilogue warp with TMEM quadrant g+2 is warp index e' with (e' + 2) & 3 == g + 2
+                        const int ep = (g + 2 + 2) & 3;
+                        const float* xb = reinterpret_cast<const float*>(stg_all + ep * 8192) + (lane >> 1);
+#pragma unroll
+                        for (int j = 0; j < Cfg::NACC; ++j) acc[j] = fmaxf(acc[j], xb[j * 16]);
+                    }
+                    int flags = -1;
+                    unsigned int ppos = 0;
+                    const int yo = (yy0 - 1) >> 1, xo = x >> 1;
+                    if (!(lane & 1) && x < p.W && yy0 - 1 < p.H && !*abort_flag) {
+                        flags = halo_flags(go, yo, xo);
+                        ppos = (n * (unsigned int)go.Hp + (unsigned int)(yo + 1)) * (unsigned int)go.Wp + (unsigned int)(xo + 1);
+                    }
+                    uint8_t* stg = stg_all + e * 8192;
+                    store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, ppos, flags, p.out, go, tc.n0 + colbase);
+                }
+                continue;
             }
             // ---- store: interior pixel + the halo cells that mirror it ----
             // (32-bit position arithmetic: P < 2^31 is checked by the launcher; 64-bit divisions cost ~60 instructions each)
@@ -401,8 +467,8 @@ int make_tensor_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d
 int g_conv_oversub = 4;
 
 template <int BN, bool FUSE_>
-static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvParams& p, int total_tiles, int n_tiles,
-                      cudaStream_t st) {
+static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA64, const ConvParams& p, int total_tiles,
+                      int n_tiles, cudaStream_t st) {
     using Cfg = Conv2Cfg<BN, FUSE_>;
     WCTB_ENSURE_SMEM((conv_tc2_kernel<BN, FUSE_>), Cfg::SMEM_BYTES);
     // Over-subscribed persistent grid: with g_conv_oversub x #SMs CTAs (1 resident per SM) the
@@ -411,7 +477,7 @@ static int launch2_bn(const CUtensorMap& mA, const CUtensorMap& mB, const ConvPa
     // (a grid of exactly #SMs would run as two unbalanced waves).
     int grid = device_sm_count() * (g_conv_oversub > 0 ? g_conv_oversub : 1);
     if (grid > total_tiles) grid = total_tiles;
-    conv_tc2_kernel<BN, FUSE_><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p, total_tiles, n_tiles);
+    conv_tc2_kernel<BN, FUSE_><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, mA64, p, total_tiles, n_tiles);
     WCTB_CHECK_LAUNCH("conv_tc2_kernel");
     return 0;
 }
@@ -437,8 +503,11 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     const int taps = mode == CONV_3X3 ? 9 : (mode == CONV_UP2 ? 4 : (mode == CONV_TAPS ? kw * kw : 1));
     const int wsets = mode == CONV_UP2 ? 4 : nsets;
 
+    const bool pool = (flags & WCTB200_POOL2) != 0;
+    WCTB_REQUIRE(!pool || (mode == CONV_3X3 && (H + 1) / 2 >= 2 && (W + 1) / 2 >= 2), "conv: POOL2 needs the 3x3 mode and a pooled output >= 2x2");
     int BN = Cout % 128 == 0 ? 128 : 64;   // 256-wide tiles leave only 2 pipeline stages: measured slower
     if (g_conv_bn_override && Cout % g_conv_bn_override == 0) BN = g_conv_bn_override;
+    if (pool && BN > 128) BN = 128;        // the pooling epilogue works on the 4-warp layouts
 
     CUtensorMap mA, mB;
     int rc = make_tensor_map_3d(&mA, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 128);
@@ -446,6 +515,11 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     const uint64_t K = (uint64_t)taps * Cin;
     rc = make_tensor_map_3d(&mB, w_split, K, (uint64_t)Cout, (uint64_t)2 * wsets, K * 2, K * Cout * 2, (uint32_t)BN);
     if (rc) return rc;
+    CUtensorMap mA64 = mA;
+    if (pool) {
+        rc = make_tensor_map_3d(&mA64, in, (uint64_t)Cin, (uint64_t)gi.P, 2, (uint64_t)Cin * 2, (uint64_t)gi.plane * 2, 64);
+        if (rc) return rc;
+    }
 
     ConvParams p;
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.Hp = gi.Hp; p.Wp = gi.Wp; p.P = gi.P;
@@ -456,23 +530,26 @@ int launch_conv_tc(int mode, const __half* in, int N, int H, int W, int Cin, con
     p.nsets = nsets;
     p.per_image = nsets > 1 ? 1 : 0;
     p.tiles_per_image = cdiv((long long)gi.Hp * gi.Wp, 128);
+    p.pool = pool ? 1 : 0;
+    p.pool_tx = cdiv(W, 64);
+    p.pool_ho = (H + 1) / 2;
     p.flags = flags;
     p.bias = bias;
     p.wscale = wscale;
     p.out = out;
     p.err = device_error_word();
-    const int m_tiles = p.per_image ? N * p.tiles_per_image : cdiv(gi.P, 128);
+    const int m_tiles = pool ? N * p.pool_ho * p.pool_tx : (p.per_image ? N * p.tiles_per_image : cdiv(gi.P, 128));
     const int n_tiles = Cout / BN;
     const int total = m_tiles * n_tiles * (mode == CONV_UP2 ? 4 : 1);
     switch (BN) {
         // fused [b_hi|b_lo] MMAs (Conv2Cfg::FUSE): always at BN=64 (4 TMEM buffers stay); at BN=128 the ring shrinks to 2
         // buffers, which only pays for long K loops (measured: Cin=128 -9 %, Cin>=256 +3..5 %)
-        case 64: return g_conv_fuse == 0 ? launch2_bn<64, false>(mA, mB, p, total, n_tiles, st)
-                                         : launch2_bn<64, true>(mA, mB, p, total, n_tiles, st);
+        case 64: return g_conv_fuse == 0 ? launch2_bn<64, false>(mA, mB, mA64, p, total, n_tiles, st)
+                                         : launch2_bn<64, true>(mA, mB, mA64, p, total, n_tiles, st);
         case 128: return (g_conv_fuse == 1 || (g_conv_fuse < 0 && (long long)taps * Cin >= 9 * 256))
-                             ? launch2_bn<128, true>(mA, mB, p, total, n_tiles, st)
-                             : launch2_bn<128, false>(mA, mB, p, total, n_tiles, st);
-        default: return launch2_bn<256, false>(mA, mB, p, total, n_tiles, st);
+                             ? launch2_bn<128, true>(mA, mB, mA64, p, total, n_tiles, st)
+                             : launch2_bn<128, false>(mA, mB, mA64, p, total, n_tiles, st);
+        default: return launch2_bn<256, false>(mA, mB, mA64, p, total, n_tiles, st);
     }
 }
 

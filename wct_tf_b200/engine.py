@@ -32,7 +32,7 @@ class Act(object):
 
 
 class Engine(object):
-    def __init__(self, weights, relu_targets, device="cuda:0", semantics="tf", fuse_upsample=True):
+    def __init__(self, weights, relu_targets, device="cuda:0", semantics="tf", fuse_upsample=True, fuse_pool=True):
         if not torch.cuda.is_available():
             raise _capi.WctB200Error("no CUDA device: the WCT engine has no CPU fallback")
         self.lib = _capi.load()
@@ -49,6 +49,7 @@ class Engine(object):
         self._group = 0
         self._style_streams = {}
         self._group_streams = {}
+        self.fuse_pool = bool(fuse_pool)          # MaxPooling2D folded into the epilogue of the conv before it (WCTB200_POOL2)
         self.fuse_upsample = bool(fuse_upsample)  # UpSampling2D folded into the next conv (4 parity kernels, 4/9 of the MACs); fixed at construction
         self.launches = 0          # kernels launched through the C-ABI (bench.py "gpu_launches")
         self.profile = None        # optional dict: key -> [torch.cuda.Event pairs, flops, bytes]
@@ -170,17 +171,25 @@ class Engine(object):
         if "relu1_1" in taps:
             kept["relu1_1"] = x
         from .model import encoder_plan
-        for op in encoder_plan(target)[1:]:
+        plan = encoder_plan(target)[1:]
+        skip_pool = False
+        for i, op in enumerate(plan):
             if op.kind == "conv":
-                y = self._act(N, x.H, x.W, op.cout)
-                self._call("conv3x3_tc[%dx%d@%d]" % (op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr, N, x.H, x.W,
-                           op.cin, self.enc_w[op.name].data_ptr(), self.enc_b[op.name].data_ptr(), op.cout,
-                           _capi.RELU, y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
-                           bytes_=4.0 * N * x.H * x.W * (op.cin + op.cout))
-                x = y
                 relu_name = op.name.replace("conv", "relu")
+                # MaxPooling2D folded into the conv that feeds it (conv1_2 / 2_2 / 3_4 / 4_4: the pool is their only consumer)
+                pooled = (self.fuse_pool and i + 1 < len(plan) and plan[i + 1].kind != "conv" and relu_name not in taps
+                          and (x.H + 1) // 2 >= 2 and (x.W + 1) // 2 >= 2)
+                y = self._act(N, (x.H + 1) // 2, (x.W + 1) // 2, op.cout) if pooled else self._act(N, x.H, x.W, op.cout)
+                self._call("conv3x3_%s[%dx%d@%d]" % ("pool" if pooled else "tc", op.cin, op.cout, x.H), 1, lib.wctb200_conv3x3, x.ptr,
+                           N, x.H, x.W, op.cin, self.enc_w[op.name].data_ptr(), self.enc_b[op.name].data_ptr(), op.cout,
+                           _capi.RELU | (_capi.POOL2 if pooled else 0), y.ptr, st, flops=2.0 * 9 * op.cin * op.cout * N * x.H * x.W,
+                           bytes_=4.0 * N * (x.H * x.W * op.cin + y.H * y.W * op.cout))
+                x = y
+                skip_pool = pooled
                 if relu_name in taps:
                     kept[relu_name] = x
+            elif skip_pool:
+                skip_pool = False
             else:
                 y = self._act(N, (x.H + 1) // 2, (x.W + 1) // 2, x.C)
                 self._call("maxpool2", 1, lib.wctb200_maxpool2, x.ptr, N, x.H, x.W, x.C, y.ptr, st,
