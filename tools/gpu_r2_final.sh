@@ -13,4 +13,8 @@ timeout 300 python tools/conv_bench.py 16 > gpurun_out/r2z_conv_layer_bench.txt 
 timeout 300 python tools/jacobi_bench.py > gpurun_out/r2z_jacobi_bench.txt 2>&1
 timeout 300 python tools/cov_bench.py 16 > gpurun_out/r2z_cov_bench.txt 2>&1
 timeout 300 python tests/noise_split_gpu.py 128 > gpurun_out/r2z_noise_gpu.txt 2>&1
+timeout 300 python tools/tail_bench.py 16 > gpurun_out/r2z_tail_bench.txt 2>&1
+timeout 300 python tools/head_bench.py 16 > gpurun_out/r2z_head_bench.txt 2>&1
+timeout 300 python tools/image_ops_bench.py > gpurun_out/r2z_image_ops_bench.txt 2>&1
+timeout 300 python tools/timeline.py 30 2 1 > gpurun_out/r2z_timeline.txt 2>&1
 head -c 400 gpurun_out/r2z_bench_n1.json; echo; cat gpurun_out/r2z_other_configs.json | tail -12

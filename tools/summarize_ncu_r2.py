@@ -101,4 +101,9 @@ vp = os.path.join(src, "r2_cov.ncu-rep")
 if os.path.exists(vp):
     full(vp, os.path.join(dst, "r02_ncu_full_cov.txt"),
          "ncu --set full --clock-control none --import-source on -k regex:cov_tc_kernel python tools/cov_once.py 16   (16 frames: C64@512, C128@256, C256@128, C512@64)")
+tp = os.path.join(src, "r2_tail.ncu-rep")
+if os.path.exists(tp):
+    full(tp, os.path.join(dst, "r02_ncu_full_tail_head.txt"),
+         "ncu --set full --clock-control none -k regex:conv_(tail|head)_tc_kernel -s 2 -c 2 python tools/tail_head_once.py 16   (16 frames 512x512: decoder tail 64->3, encoder head 3->64)",
+         note="tail: compulsory traffic 16*514*514*256 B read + 16*512*512*12 B written = 1.13 GB; head: 16*512*512*12 B read + 16*514*514*256 B written = 1.13 GB.")
 print("wrote summaries to", dst)
