@@ -336,46 +336,73 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (Cfg::STG_BYTES > 0 && p.pool) {
                 // ---- MaxPooling2D 2x2/2 'same' (vgg_normalised.py:41-42) on the raw accumulators: max commutes with the
                 // monotone  *scale + bias -> ReLU -> split  that follows.  Tile rows 0..63 = image row 2i, 64..127 = row 2i+1.
+                // Work split: the two lanes of a horizontal pixel pair share the pooled pixel's channels (16-channel blocks:
+                // lane parity l owns channels 8l..8l+7 of each block), and the warps of the two image rows share them by halves
+                // (upper-row warps keep the lower half of the channel range, lower-row warps the upper half), so every lane of
+                // all four warps finishes and stores NACC/4 channels of one pooled pixel.
+                constexpr int NH = Cfg::NACC / 2;            // channels per half
+                constexpr int Q = Cfg::NACC / 4;             // channels a lane finishes
                 const int tpos = g * 32 + lane;
                 const int xloc = tpos & 63;
+                const int hv = tpos >> 6;                    // 0: image row 2i, 1: row 2i+1
+                const int lp = lane & 1;
                 const unsigned int hpwp = (unsigned int)(p.Hp * p.Wp);
                 const unsigned int n = (unsigned int)tc.p0 / hpwp;
                 const int yy0 = (int)(((unsigned int)tc.p0 - n * hpwp) / (unsigned int)p.Wp);   // padded row of image row 2i
-                const int y = yy0 - 1 + (tpos >> 6);
                 const int x = 64 * tc.cls + xloc;
-                const bool valid = y < p.H && x < p.W;
-                const float ninf = __int_as_float(0xff800000);
+                const bool valid = (yy0 - 1 + hv) < p.H && x < p.W;
+                if (__any_sync(0xffffffffu, !valid)) {       // ragged right / bottom edge only
+                    const float ninf = __int_as_float(0xff800000);
 #pragma unroll
-                for (int j = 0; j < Cfg::NACC; ++j) {
-                    const float v = valid ? acc[j] : ninf;
-                    acc[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));         // horizontal pair (x even, x+1)
+                    for (int j = 0; j < Cfg::NACC; ++j) acc[j] = valid ? acc[j] : ninf;
                 }
-                uint8_t* stg_all = aux + Cfg::AUX_BYTES;
-                if (g >= 2) {                                                       // lower image row: hand over to warp g-2
-                    if (!(lane & 1)) {
-                        float* xb = reinterpret_cast<float*>(stg_all + e * 8192) + (lane >> 1);
+                // horizontal: m[h][k] = max over the pixel pair of channel  h*NH + (k>>3)*16 + lp*8 + (k&7)
+                float keep[Q], send[Q];
 #pragma unroll
-                        for (int j = 0; j < Cfg::NACC; ++j) xb[j * 16] = acc[j];
+                for (int k = 0; k < Q; ++k) {
+                    const int c0 = (k >> 3) * 16 + (k & 7);
+                    float mh[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float a0 = acc[h * NH + c0], a1 = acc[h * NH + c0 + 8];
+                        const float mine = lp ? a1 : a0;
+                        const float other = lp ? a0 : a1;    // the neighbour lane's channel, this lane's pixel
+                        mh[h] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, other, 1));
                     }
+                    keep[k] = hv ? mh[1] : mh[0];
+                    send[k] = hv ? mh[0] : mh[1];
+                }
+                // vertical: hand the other half over to the warp of the other image row (same lane = same pixel column)
+                uint8_t* stg_all = aux + Cfg::AUX_BYTES;
+                {
+                    float* xb = reinterpret_cast<float*>(stg_all + e * 8192) + lane;
+#pragma unroll
+                    for (int k = 0; k < Q; ++k) xb[k * 32] = send[k];
                 }
                 asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
-                if (g < 2) {
-                    if (!(lane & 1)) {
-                        // epilogue warp with TMEM quadrant g+2 is warp index e' with (e' + 2) & 3 == g + 2
-                        const int ep = (g + 2 + 2) & 3;
-                        const float* xb = reinterpret_cast<const float*>(stg_all + ep * 8192) + (lane >> 1);
+                {
+                    const float* pb = reinterpret_cast<const float*>(stg_all + (e ^ 2) * 8192) + lane;   // TMEM quadrant g ^ 2
 #pragma unroll
-                        for (int j = 0; j < Cfg::NACC; ++j) acc[j] = fmaxf(acc[j], xb[j * 16]);
+                    for (int k = 0; k < Q; ++k) keep[k] = fmaxf(keep[k], pb[k * 32]);
+                }
+                const int xe = x & ~1;                       // the even column of the pair
+                if (xe < p.W && yy0 - 1 < p.H && !*abort_flag) {
+                    const int yo = (yy0 - 1) >> 1, xo = xe >> 1;
+                    const int flags = halo_flags(go, yo, xo);
+                    const unsigned int ppos = (n * (unsigned int)go.Hp + (unsigned int)(yo + 1)) * (unsigned int)go.Wp + (unsigned int)(xo + 1);
+                    const int cb = colbase + hv * NH + lp * 8;   // first channel this lane stores
+#pragma unroll
+                    for (int q = 0; q < Q / 8; ++q) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float t = fmaf(keep[q * 8 + j], wsc, sbias[cb + q * 16 + j]);
+                            v[j] = relu ? fmaxf(t, 0.f) : t;
+                        }
+                        Half8 hi, lo;
+                        split8(v, hi, lo);
+                        store8_at(p.out, go, ppos, flags, tc.n0 + cb + q * 16, hi, lo);
                     }
-                    int flags = -1;
-                    unsigned int ppos = 0;
-                    const int yo = (yy0 - 1) >> 1, xo = x >> 1;
-                    if (!(lane & 1) && x < p.W && yy0 - 1 < p.H && !*abort_flag) {
-                        flags = halo_flags(go, yo, xo);
-                        ppos = (n * (unsigned int)go.Hp + (unsigned int)(yo + 1)) * (unsigned int)go.Wp + (unsigned int)(xo + 1);
-                    }
-                    uint8_t* stg = stg_all + e * 8192;
-                    store_tile_rows<Cfg::NACC>(acc, wsc, sbias + colbase, relu, stg, lane, ppos, flags, p.out, go, tc.n0 + colbase);
                 }
                 continue;
             }
