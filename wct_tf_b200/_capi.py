@@ -63,6 +63,8 @@ DEBUG_SIGNATURES = {
     "wctb200_debug_set_conv_products": (_i, [_i]),
     "wctb200_debug_set_conv_tail_tc": (_i, [_i]),
     "wctb200_debug_set_conv_head_tc": (_i, [_i]),
+    "wctb200_debug_set_matfun": (_i, [_i, _i]),
+    "wctb200_debug_matfun": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
     "wctb200_debug_set_cov_stages": (_i, [_i]),
 }
 

@@ -110,14 +110,18 @@ int launch_wct_style_prepare(const __half*, int, int, int, int, float, float, fl
 int launch_wct_apply(const __half*, int, int, int, int, const void*, int, float, float, float, float, int, __half*, int32_t*,
                      void*, size_t, cudaStream_t);
 int launch_covariance(const __half*, int, int, int, int, float, float*, float*, cudaStream_t);
-int launch_jacobi(float*, int, int, float*, int*, cudaStream_t);
-int launch_eig_post(const float*, const float*, float*, int, int, float, float, int, float*, float*, int*, cudaStream_t);
+int launch_jacobi(float*, int, int, float*, int*, cudaStream_t, const int* skip);
+int launch_eig_post(const float*, const float*, float*, int, int, float, float, int, float*, float*, int*, cudaStream_t, const int* skip);
 extern int g_conv_bn_override;
 extern int g_conv_oversub;
 extern int g_conv_fuse;
 extern int g_conv_products;
 extern int g_conv_tail_tc;
 extern int g_conv_head_tc;
+int launch_matfun_ns(const float* A, int C, int count, int n_first, float thresh, float eps_eig, float* out, int* ok, int* kcount,
+                     cudaStream_t st, float* info);
+extern int g_matfun;
+extern int g_matfun_max_it;
 extern int g_cov_max_stages;
 int set_jacobi_tolq(float v);
 extern int g_jacobi_lg;
@@ -321,8 +325,8 @@ int wctb200_jacobi_eigh(float* a, int C, int count, float* sigma, int32_t* sweep
     float* a0 = scratch + (size_t)count * 16;
     float* lam = a0 + nmat;
     cudaError_t ce = cudaMemcpyAsync(a0, a, nmat * sizeof(float), cudaMemcpyDeviceToDevice, ST(stream));
-    int rc = ce == cudaSuccess ? launch_jacobi(a, C, count, conv, sweeps, ST(stream)) : cuda_fail(ce, "cudaMemcpyAsync");
-    if (!rc) rc = launch_eig_post(a, a0, lam, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream));
+    int rc = ce == cudaSuccess ? launch_jacobi(a, C, count, conv, sweeps, ST(stream), nullptr) : cuda_fail(ce, "cudaMemcpyAsync");
+    if (!rc) rc = launch_eig_post(a, a0, lam, C, count, 0.f, 0.f, count, sigma, nullptr, nullptr, ST(stream), nullptr);
     return rc;
 }
 
@@ -357,6 +361,17 @@ int wctb200_debug_set_jacobi_tolq(float tolq) { return set_jacobi_tolq(tolq); }
 int wctb200_debug_set_cov_stages(int n) {
     if (n >= 1 && n <= 12) g_cov_max_stages = n;
     return g_cov_max_stages;
+}
+int wctb200_debug_matfun(const float* A, int C, int count, int n_first, float thresh, float eps_eig, float* out, int* ok,
+                         float* info, void* stream) {
+    WCTB_REQUIRE(A && out && ok && count >= 1 && n_first >= 0 && n_first <= count, "debug_matfun: bad arguments");
+    const int rc = launch_matfun_ns(A, C, count, n_first, thresh, eps_eig, out, ok, nullptr, ST(stream), info);
+    return rc < 0 ? rc : 0;
+}
+int wctb200_debug_set_matfun(int mode, int max_it) {
+    if (mode == 0 || mode == 1) g_matfun = mode;
+    if (max_it >= 1 && max_it <= 64) g_matfun_max_it = max_it;
+    return g_matfun;
 }
 int wctb200_debug_set_conv_head_tc(int on) {
     if (on == 0 || on == 1) g_conv_head_tc = on;

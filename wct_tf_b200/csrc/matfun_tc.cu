@@ -1,0 +1,433 @@
+// Whitening / colouring matrices WITHOUT an eigendecomposition when every eigenvalue is kept.
+//
+//   reference: ops.py:53-77 (wct_tf) / ops.py:110-128 (wct_np):  U S V^T = svd(cov);  k = #{S > 1e-5};
+//              W_c = E_k S_k^-1/2 E_k^T   (content),   C_s = E_k S_k^+1/2 E_k^T   (style).
+//
+// When k = C (no eigenvalue at or below the threshold) these are the matrix functions  A^-1/2  and  A^+1/2  of
+// A = cov (+ eps_eig I), and both come out of ONE coupled Newton-Schulz iteration (Denman-Beavers in Higham's stable
+// product form) that consists of nothing but C x C x C products -- tensor-core work instead of ~1.7 M plane rotations:
+//       Y_0 = A / s,  Z_0 = I                  (s = ||A||_F >= lambda_max)
+//       T   = (3 I - Z Y) / 2 ;   Y <- Y T ;   Z <- T Z          ->   Y -> (A/s)^1/2 ,  Z -> (A/s)^-1/2
+// The products are TRUE products (A operand K-major, B operand MN-major through the tcgen05 descriptors): although every
+// iterate is symmetric in exact arithmetic, using rows for columns destabilises the iteration.  All operands live in HBM/L2 as split-fp16 planes [matrix][hi|lo][C][C]; a product is one launch of
+// `ns_gemm_kernel` (the TMA / tcgen05 / TMEM pipeline of conv_tc.cu: a_hi [b_hi|b_lo] + a_lo b_hi, chunked drain into fp32
+// registers), batched over the matrices of a level.  The residual max|I - Z Y| falls out of the first product of an
+// iteration; a matrix that reaches `tol` is skipped by every later launch (`conv_iter`), so the launch count is fixed and
+// nothing synchronises with the host.
+//
+// Guard (all on the device, per matrix).  The fast path is taken only if (i) the iteration converged within the budget
+// (cond(A) up to ~1e4) and (ii) the threshold provably keeps every eigenvalue:  1 / lambda_min <= sum_i 1 / lambda_i =
+// ||A^-1/2||_F^2 = ||Z||_F^2 / s, so  s / ||Z||_F^2 - eps_eig > thresh * 1.01  implies  lambda_min(cov) > thresh, i.e. k = C.
+// Everything else -- rank-deficient or ill-conditioned covariances, eigenvalues near the threshold -- is left to the Jacobi
+// eigensolver, whose kernels skip the matrices flagged here (`ok`).  Measured accuracy of the products (split-fp16 x3):
+// the transformed features move by ~4e-5 (values up to 5) against the eigendecomposition in float64
+// (profiles/r02_matfun_accuracy.txt); the parity gate is 1e-3.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace wctb {
+
+int make_tensor_map_3d(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                       uint64_t stride2_bytes, uint32_t box1);
+
+struct NsCfg {
+    static constexpr int BM = 128, BN = 128, BK = 64;
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;      // 64 KB
+    static constexpr int STAGES = 3;
+    static constexpr int ACC_COLS = 2 * BN;                            // [a_hi b_hi + a_lo b_hi | a_hi b_lo]
+    static constexpr int NBUF = 2;
+    static constexpr int TMEM_COLS = NBUF * ACC_COLS;                  // 512
+    static constexpr int CH = 4;                                       // k-iterations per accumulation chunk
+    static constexpr int THREADS = 192;
+    static constexpr int AUX_BYTES = 512;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+};
+
+struct NsState {                 // per matrix
+    float s;                     // ||A||_F
+    float f32_scale;             // factor of the fp32 output: s^-1/2 (whitening) or s^+1/2 (colouring)
+    int conv_iter;               // iteration whose residual was below tol (INT_MAX: not yet)
+    unsigned int resid_bits;     // max |I - Z Y| of the running iteration (float bits, >= 0)
+    int tiles_done;
+    int ok;                      // set by k_ns_finish
+    float last_resid;
+    int pad;
+};
+
+struct NsGemmParams {
+    int n, batch, tiles_m, it, mode;          // mode 1: T = 1.5 I - 0.5 A B (+ residual); mode 2: A B
+    int f32_rule;                             // 0: no fp32 output; 1: matrices b < n_first; 2: matrices b >= n_first
+    int n_first;
+    int want_zz;                              // per-tile sums of squares of the output (the guard's ||Z||_F^2)
+    float tol;
+    NsState* state;
+    __half* out_split;                        // [batch][2][n][n]
+    float* out_f32;                           // [batch][n][n]
+    float* zz_slots;                          // [batch][tiles_m * tiles_m]
+    unsigned int* err;
+};
+
+__global__ void __launch_bounds__(NsCfg::THREADS, 1)
+ns_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const NsGemmParams p) {
+    using Cfg = NsCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* aux = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tfull = empty + Cfg::STAGES;
+    uint64_t* tempty = tfull + Cfg::NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + Cfg::NBUF);
+    volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    float* red = reinterpret_cast<float*>(aux + 256);          // [4] epilogue partials
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    {
+        __shared__ unsigned int s_prev_err;
+        if (threadIdx.x == 0) s_prev_err = *reinterpret_cast<volatile unsigned int*>(p.err);
+        __syncthreads();
+        if (s_prev_err != 0u) return;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < Cfg::NBUF; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        *abort_flag = 0;
+        fence_barrier_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kiters = p.n / Cfg::BK;
+    const int nchunks = (kiters + Cfg::CH - 1) / Cfg::CH;
+    const int tpm = p.tiles_m * p.tiles_m;
+    const int total_tiles = p.batch * tpm;
+    // a matrix that has converged is skipped from the NEXT iteration on (conv_iter is written by the last tile of the
+    // mode-1 product of iteration `it` itself: `it > conv_iter` is false for every reader of this launch either way)
+    auto skipped = [&](int b) { return p.it > *reinterpret_cast<volatile int*>(&p.state[b].conv_iter); };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t itg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = tile / tpm, r = tile - b * tpm;
+                if (skipped(b)) continue;
+                const int mi = r / p.tiles_m, ni = r - mi * p.tiles_m;
+                const int rowA = (b * 2) * p.n + mi * Cfg::BM;           // plane 0; plane 1 is n rows further
+                const int rowB = (b * 2) * p.n;                          // B: k-rows of plane 0 start here
+                const int colB = ni * Cfg::BN;
+                for (int ki = 0; ki < kiters; ++ki, ++itg) {
+                    const int s = itg % Cfg::STAGES;
+                    mbar_wait(&empty[s], ((itg / Cfg::STAGES) & 1) ^ 1u, abort_flag, p.err, 0x150u + s);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                    tma_load_3d(st, &mapA, &full[s], ki * Cfg::BK, rowA, 0);
+                    tma_load_3d(st + Cfg::A_BYTES, &mapA, &full[s], ki * Cfg::BK, rowA + p.n, 0);
+                    // B is read as it stands -- rows k, columns j -- i.e. MN-major: four [64 k][64 j] boxes (hi j-groups, lo j-groups)
+                    uint8_t* sb = st + 2 * Cfg::A_BYTES;
+                    tma_load_3d(sb, &mapB, &full[s], colB, rowB + ki * Cfg::BK, 0);
+                    tma_load_3d(sb + 8192, &mapB, &full[s], colB + 64, rowB + ki * Cfg::BK, 0);
+                    tma_load_3d(sb + 16384, &mapB, &full[s], colB, rowB + p.n + ki * Cfg::BK, 0);
+                    tma_load_3d(sb + 24576, &mapB, &full[s], colB + 64, rowB + p.n + ki * Cfg::BK, 0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // A K-major (rows of A), B MN-major (rows of B are the contraction index): TRUE products A B.  (Using B's rows as
+            // columns -- legitimate for exactly symmetric B -- makes the iteration unstable: the iterates only commute up to
+            // rounding, and the transposed products diverge after reaching ~1e-4; tools/ns_emulation.py.)
+            constexpr uint32_t idesc = umma_idesc_f16(Cfg::BM, Cfg::BN) | (1u << 16);
+            constexpr uint32_t idesc2 = umma_idesc_f16(Cfg::BM, 2 * Cfg::BN) | (1u << 16);
+            uint32_t itg = 0, cg_ = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                if (skipped(tile / tpm)) continue;
+                for (int c = 0; c < nchunks; ++c, ++cg_) {
+                    const int bb = cg_ % Cfg::NBUF;
+                    mbar_wait(&tempty[bb], ((cg_ / Cfg::NBUF) & 1) ^ 1u, abort_flag, p.err, 0x450u + bb);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(bb * Cfg::ACC_COLS);
+                    const int it_end = min(kiters, (c + 1) * Cfg::CH);
+                    for (int ki = c * Cfg::CH; ki < it_end; ++ki, ++itg) {
+                        const int s = itg % Cfg::STAGES;
+                        mbar_wait(&full[s], (itg / Cfg::STAGES) & 1, abort_flag, p.err, 0x250u + s);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                        const uint64_t a_hi = umma_desc_sw128(st);
+                        const uint64_t a_lo = umma_desc_sw128(st + Cfg::A_BYTES);
+                        const bool first = (ki == c * Cfg::CH);
+#pragma unroll
+                        for (int k = 0; k < Cfg::BK / 16; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+                            const uint64_t b_hi = umma_desc_mn_sw128(st + 2 * Cfg::A_BYTES + k * 2048);   // 16 k-rows of 128 B per step
+                            umma_f16(tacc, a_hi + ko, b_hi, idesc2, (first && k == 0) ? 0u : 1u);        // N = 256: [b_hi | b_lo]
+                            umma_f16(tacc, a_lo + ko, b_hi, idesc, 1u);
+                        }
+                        umma_commit(&empty[s]);
+                    }
+                    umma_commit(&tfull[bb]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int e = warp - 2;
+        const int g = warp & 3;
+        uint32_t cg_ = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int b = tile / tpm, r = tile - b * tpm;
+            if (skipped(b)) continue;
+            const int mi = r / p.tiles_m, ni = r - mi * p.tiles_m;
+            float acc[Cfg::BN];
+#pragma unroll
+            for (int i = 0; i < Cfg::BN; ++i) acc[i] = 0.f;
+            for (int c = 0; c < nchunks; ++c, ++cg_) {
+                const int bb = cg_ % Cfg::NBUF;
+                mbar_wait(&tfull[bb], (cg_ / Cfg::NBUF) & 1, abort_flag, p.err, 0x350u + bb);
+                tc_fence_after();
+                const uint32_t tsrc = tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(bb * Cfg::ACC_COLS);
+#pragma unroll
+                for (int c0 = 0; c0 < Cfg::BN; c0 += 32) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tsrc + c0, r0);
+                    tmem_ld32(tsrc + Cfg::BN + c0, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[bb]);
+            }
+            // ---- epilogue: this thread owns row `row`, columns [col0, col0 + 128) ----
+            const int row = mi * Cfg::BM + g * 32 + lane;
+            const int col0 = ni * Cfg::BN;
+            const int dj = row - col0;                               // diagonal element sits at acc[dj] when 0 <= dj < 128
+            float rmax = 0.f, zz = 0.f;
+            if (p.mode == 1) {
+#pragma unroll
+                for (int j = 0; j < Cfg::BN; ++j) {
+                    const float d = (j == dj) ? 1.f : 0.f;
+                    rmax = fmaxf(rmax, fabsf(acc[j] - d));           // |I - Z Y|
+                    acc[j] = fmaf(-0.5f, acc[j], 1.5f * d);          // T = (3 I - Z Y) / 2
+                }
+            }
+            const bool f32 = p.f32_rule != 0 && ((p.f32_rule == 1) == (b < p.n_first)) && !*abort_flag;
+            const float fs = f32 ? p.state[b].f32_scale : 0.f;
+            __half* o_hi = p.out_split + ((long long)(b * 2) * p.n + row) * p.n + col0;
+            __half* o_lo = o_hi + (long long)p.n * p.n;
+            float* o_f = p.out_f32 + ((long long)b * p.n + row) * p.n + col0;
+            if (!*abort_flag) {
+#pragma unroll
+                for (int q = 0; q < Cfg::BN / 8; ++q) {
+                    Half8 hi, lo;
+                    split8(acc + q * 8, hi, lo);
+                    *reinterpret_cast<Half8*>(o_hi + q * 8) = hi;
+                    *reinterpret_cast<Half8*>(o_lo + q * 8) = lo;
+                    if (f32) {
+                        *reinterpret_cast<float4*>(o_f + q * 8) = make_float4(acc[q * 8] * fs, acc[q * 8 + 1] * fs, acc[q * 8 + 2] * fs, acc[q * 8 + 3] * fs);
+                        *reinterpret_cast<float4*>(o_f + q * 8 + 4) = make_float4(acc[q * 8 + 4] * fs, acc[q * 8 + 5] * fs, acc[q * 8 + 6] * fs, acc[q * 8 + 7] * fs);
+                    }
+                }
+            }
+            if (p.want_zz) {
+#pragma unroll
+                for (int j = 0; j < Cfg::BN; ++j) zz = fmaf(acc[j], acc[j], zz);
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) zz += __shfl_xor_sync(0xffffffffu, zz, o);
+                if (lane == 0) red[e] = zz;
+            }
+            if (p.mode == 1) {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+                if (lane == 0) atomicMax(&p.state[b].resid_bits, __float_as_uint(rmax));     // order independent
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0 && lane == 0) {
+                if (p.want_zz) p.zz_slots[(long long)b * tpm + r] = (red[0] + red[1]) + (red[2] + red[3]);   // fixed order
+                if (p.mode == 1) {
+                    const int done = atomicAdd(&p.state[b].tiles_done, 1);
+                    if (done == tpm - 1) {                           // last tile of this matrix in this launch
+                        __threadfence();
+                        const float res = __uint_as_float(atomicAdd(&p.state[b].resid_bits, 0u));
+                        p.state[b].last_resid = res;
+                        p.state[b].resid_bits = 0u;
+                        p.state[b].tiles_done = 0;
+                        if (res < p.tol) p.state[b].conv_iter = p.it;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // red[] is reused by the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// one block per matrix: s = ||A + eps I||_F, Y0 = (A + eps I)/s and Z0 = I as split planes, state reset
+__global__ void __launch_bounds__(1024)
+k_ns_init(const float* __restrict__ A, int n, float eps_eig, int n_first, __half* __restrict__ Y, __half* __restrict__ Z,
+          NsState* __restrict__ state) {
+    const int b = blockIdx.x;
+    const float* a = A + (long long)b * n * n;
+    __shared__ float red[32];
+    __shared__ float s_s;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+        float v = a[i];
+        if (i / n == i % n) v += eps_eig;
+        ss = fmaf(v, v, ss);
+    }
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        const float s = sqrtf(t);
+        const bool good = isfinite(s) && s > 0.f;
+        s_s = good ? s : 1.f;
+        NsState st;
+        st.s = s_s;
+        st.f32_scale = (b < n_first) ? rsqrtf(s_s) : sqrtf(s_s);
+        st.conv_iter = good ? 0x7fffffff : -1;          // a degenerate matrix never enters the iteration
+        st.resid_bits = 0u;
+        st.tiles_done = 0;
+        st.ok = 0;
+        st.last_resid = good ? 1.f : 1e30f;
+        st.pad = 0;
+        state[b] = st;
+    }
+    __syncthreads();
+    const float inv = 1.f / s_s;
+    __half* y_hi = Y + (long long)(b * 2) * n * n;
+    __half* y_lo = y_hi + (long long)n * n;
+    __half* z_hi = Z + (long long)(b * 2) * n * n;
+    __half* z_lo = z_hi + (long long)n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+        const bool diag = (i / n == i % n);
+        float v = a[i];
+        if (diag) v += eps_eig;
+        __half hi, lo;
+        split_f32(v * inv, hi, lo);
+        y_hi[i] = hi;
+        y_lo[i] = lo;
+        z_hi[i] = __float2half(diag ? 1.f : 0.f);
+        z_lo[i] = __float2half(0.f);
+    }
+}
+
+// the guard: converged within the budget AND the threshold provably keeps every eigenvalue
+__global__ void k_ns_finish(NsState* __restrict__ state, const float* __restrict__ zz_slots, int tpm, int batch, int max_it,
+                            float thresh, float eps_eig, int* __restrict__ ok, int* __restrict__ kcount, int C, float* __restrict__ info) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    NsState st = state[b];
+    float zz = 0.f;
+    for (int i = 0; i < tpm; ++i) zz += zz_slots[(long long)b * tpm + i];
+    // sum_i 1/lambda_i(A) = ||Z||_F^2 / s  >=  1 / lambda_min(A);  lambda_min(cov) = lambda_min(A) - eps_eig
+    const float lmin_bound = st.s / zz - eps_eig;
+    const bool good = st.conv_iter >= 0 && st.conv_iter < max_it && isfinite(zz) && zz > 0.f && lmin_bound > thresh * 1.01f;
+    ok[b] = good ? 1 : 0;
+    state[b].ok = good ? 1 : 0;
+    if (good && kcount) kcount[b] = C;                  // every eigenvalue kept (ops.py:57-64)
+    if (info) {                                         // probe: iteration of convergence, last residual, eigenvalue bound
+        info[4 * b] = (float)(st.conv_iter == 0x7fffffff ? -1 : st.conv_iter);
+        info[4 * b + 1] = st.last_resid;
+        info[4 * b + 2] = lmin_bound;
+        info[4 * b + 3] = st.s;
+    }
+}
+
+int g_matfun = 1;                 // 0: never (always the Jacobi eigensolver), 1: auto  (wctb200_debug_set_matfun)
+int g_matfun_max_it = 16;          // matrices that need more (cond > ~5e3) fail the eigenvalue guard anyway
+
+static int ns_gemm(const __half* A, const __half* B, int n, int batch, int it, int mode, int f32_rule, int n_first, int want_zz,
+                   float tol, NsState* state, __half* out_split, float* out_f32, float* zz_slots, cudaStream_t st) {
+    using Cfg = NsCfg;
+    CUtensorMap mA, mB;
+    const uint64_t rows = (uint64_t)batch * 2 * n;
+    int rc = make_tensor_map_3d(&mA, A, (uint64_t)n, rows, 1, (uint64_t)n * 2, rows * n * 2, Cfg::BM);
+    if (rc) return rc;
+    rc = make_tensor_map_3d(&mB, B, (uint64_t)n, rows, 1, (uint64_t)n * 2, rows * n * 2, 64);
+    if (rc) return rc;
+    NsGemmParams p;
+    p.n = n; p.batch = batch; p.tiles_m = n / Cfg::BM; p.it = it; p.mode = mode;
+    p.f32_rule = out_f32 ? f32_rule : 0;
+    p.n_first = n_first;
+    p.want_zz = want_zz;
+    p.tol = tol;
+    p.state = state;
+    p.out_split = out_split;
+    p.out_f32 = out_f32;
+    p.zz_slots = zz_slots;
+    p.err = device_error_word();
+    WCTB_ENSURE_SMEM(ns_gemm_kernel, Cfg::SMEM_BYTES);
+    int grid = device_sm_count();
+    const int total = batch * p.tiles_m * p.tiles_m;
+    if (grid > total) grid = total;
+    ns_gemm_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(mA, mB, p);
+    WCTB_CHECK_LAUNCH("ns_gemm_kernel");
+    return 0;
+}
+
+size_t matfun_scratch_bytes(int C, int count) {
+    const size_t plane2 = (size_t)2 * C * C * 2;                     // one split matrix
+    return (size_t)count * (5 * plane2 + 64 * 4) + (size_t)count * sizeof(NsState) + 4096;
+}
+
+// A: `count` covariances (fp32, [count][C][C]); the first n_first want A^-1/2 (whitening), the rest A^+1/2 (colouring).
+// out: [count][C][C] fp32, written for every matrix the iteration touches; ok[b] = 1 where `out` is valid (guard passed),
+// kcount[b] = C there.  Returns 1 when the fast path is not attempted at all (ok[] is zeroed then).
+int launch_matfun_ns(const float* A, int C, int count, int n_first, float thresh, float eps_eig, float* out, int* ok, int* kcount,
+                     cudaStream_t st, float* info) {
+    WCTB_CUDA(cudaMemsetAsync(ok, 0, (size_t)count * sizeof(int), st));
+    if (!g_matfun || C < 128 || C % 128 != 0 || count < 1) return 1;
+    uint8_t* scratch = nullptr;
+    { int rc0 = scratch_alloc(reinterpret_cast<void**>(&scratch), matfun_scratch_bytes(C, count), st, 4); if (rc0) return rc0; }
+    const size_t msz = (size_t)count * 2 * C * C;                    // halves per operand buffer
+    __half* Y[2] = {reinterpret_cast<__half*>(scratch), reinterpret_cast<__half*>(scratch) + msz};
+    __half* Z[2] = {Y[1] + msz, Y[1] + 2 * msz};
+    __half* T = Z[1] + msz;
+    float* zz = reinterpret_cast<float*>(T + msz);
+    NsState* state = reinterpret_cast<NsState*>(zz + (size_t)count * 64);
+    const int tpm = (C / 128) * (C / 128);
+    WCTB_CUDA(cudaMemsetAsync(zz, 0, (size_t)count * 64 * 4, st));
+    k_ns_init<<<count, 1024, 0, st>>>(A, C, eps_eig, n_first, Y[0], Z[0], state);
+    WCTB_CHECK_LAUNCH("k_ns_init");
+    // the tensor core adds into its fp32 accumulator with truncation (conv_tc.cu): (Z Y)_ii settles ~3e-6 below 1, which is the
+    // floor of the measured residual; tol sits above it and one more (quadratically convergent) iteration always follows
+    const float tol = 2e-5f;
+    int cur = 0;
+    for (int it = 0; it < g_matfun_max_it; ++it) {
+        int rc = ns_gemm(Z[cur], Y[cur], C, count, it, 1, 0, n_first, 0, tol, state, T, nullptr, nullptr, st);        // T = (3I - ZY)/2
+        if (rc) return rc;
+        rc = ns_gemm(Y[cur], T, C, count, it, 2, 2, n_first, 0, tol, state, Y[cur ^ 1], out, nullptr, st);            // Y' = Y T  (fp32: colouring)
+        if (rc) return rc;
+        rc = ns_gemm(T, Z[cur], C, count, it, 2, 1, n_first, 1, tol, state, Z[cur ^ 1], out, zz, st);                 // Z' = T Z  (fp32: whitening; ||Z||_F^2)
+        if (rc) return rc;
+        cur ^= 1;
+    }
+    k_ns_finish<<<cdiv(count, 128), 128, 0, st>>>(state, zz, tpm, count, g_matfun_max_it, thresh, eps_eig, ok, kcount, C, info);
+    WCTB_CHECK_LAUNCH("k_ns_finish");
+    return 0;
+}
+
+}  // namespace wctb

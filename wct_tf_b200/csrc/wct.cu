@@ -219,7 +219,11 @@ __device__ float g_jacobi_tolq = 1e-4f;   // predicted-convergence level (see k_
 template <int NN>
 __global__ void __launch_bounds__(512, 1)
 k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict__ sweeps_out, int max_sweeps, float tol,
-         int lg, int stagger) {
+         int lg, int stagger, const int* __restrict__ skip) {
+    if (skip && skip[blockIdx.y]) {          // matrix handled by the matrix-function fast path (matfun_tc.cu): whole cluster leaves
+        if (blockIdx.x == 0 && threadIdx.x == 0 && sweeps_out) sweeps_out[blockIdx.y] = 0;
+        return;
+    }
     using Cfg = JacobiCfg<NN>;
     constexpr int P = Cfg::P;
     constexpr int NB = 2 * P;
@@ -379,7 +383,9 @@ k_jacobi(float* __restrict__ Gall, float* __restrict__ conv_ws, int* __restrict_
 // the 1e-5 cut for lambda_max > 25; LAPACK: 4e-8*lambda_max).  The Rayleigh quotient is second order in
 // that noise: the same null columns give ~1e-8.   grid (C/16, problems), C threads.
 __global__ void __launch_bounds__(512)
-k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int C, float* __restrict__ lam) {
+k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int C, float* __restrict__ lam,
+           const int* __restrict__ skip) {
+    if (skip && skip[blockIdx.y]) return;
     __shared__ __align__(16) float gs[512 * 16];
     __shared__ float red_q[16][17], red_s[16][17];     // [warp][column]: fixed-order (deterministic) reduction
     const int prob = blockIdx.y, j0 = blockIdx.x * 16, r = threadIdx.x;
@@ -439,8 +445,10 @@ k_rayleigh(const float* __restrict__ A0all, const float* __restrict__ Gall, int 
 //   mode 1 (style, colouring)  : d = (sigma+eps_eig)^+1/2 / sigma^2
 //   so that  E_k f(S_k) E_k^T = G diag(d) G^T  with G's columns = sigma_i u_i.
 __global__ void k_eig_post(const float* __restrict__ Gall, const float* __restrict__ lam, int C, float thresh, float eps_eig,
-                           int n_content, float* __restrict__ sigma, float* __restrict__ dvec, int* __restrict__ kcount) {
+                           int n_content, float* __restrict__ sigma, float* __restrict__ dvec, int* __restrict__ kcount,
+                           const int* __restrict__ skip) {
     const int prob = blockIdx.y;
+    if (skip && skip[prob]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int col = blockIdx.x * (blockDim.x >> 5) + warp;
     if (col >= C) return;
@@ -468,7 +476,9 @@ __global__ void k_eig_post(const float* __restrict__ Gall, const float* __restri
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_outer_gemm(const float* __restrict__ A, long long sa, const float* __restrict__ B, long long sb,
-             const float* __restrict__ d, long long sd, float* __restrict__ Cm, long long sc, int n) {
+             const float* __restrict__ d, long long sd, float* __restrict__ Cm, long long sc, int n,
+             const int* __restrict__ skip = nullptr) {
+    if (skip && skip[blockIdx.z]) return;      // this output was produced by the matrix-function fast path
     __shared__ __align__(16) float As[16][64];
     __shared__ __align__(16) float Bs[16][64];
     const int z = blockIdx.z;
@@ -585,7 +595,7 @@ __global__ void k_affine_apply(const __half* __restrict__ in, ActGeom g, const f
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WctWs {
-    size_t sum, sumsq, dsum, mean, var, G, A0, lam, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, scale, shift, total;
+    size_t sum, sumsq, dsum, mean, var, G, A0, lam, sigma, dvec, Wc, Cs, T, Msplit, bias, conv, kcount, ok, scale, shift, total;
 };
 static WctWs wct_layout(int C, int Nc, int Ns) {
     WctWs w;
@@ -609,6 +619,7 @@ static WctWs wct_layout(int C, int Nc, int Ns) {
     w.bias = take((size_t)Nc * C * 4);
     w.conv = take(np * 16 * 4);
     w.kcount = take(np * 2 * 4);
+    w.ok = take(np * 4);               // matrices whose W / C_s came from the matrix-function fast path (matfun_tc.cu)
     w.scale = take((size_t)Nc * C * 4);
     w.shift = take((size_t)Nc * C * 4);
     w.total = o;
@@ -640,7 +651,7 @@ int set_jacobi_tolq(float v) {
     return cudaMemcpyToSymbol(g_jacobi_tolq, &v, sizeof(float)) == cudaSuccess ? 0 : -1;
 }
 
-int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st) {
+int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaStream_t st, const int* skip) {
     const float tol = 2.f * sqrtf((float)C) * 5.96e-8f;
     const int max_sweeps = 40;
     const int lg = g_jacobi_lg >= 0 ? g_jacobi_lg : (C >= 512 ? 2 : 1);
@@ -660,7 +671,7 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
     case NN: {                                                                                                       \
         WCTB_ENSURE_SMEM(k_jacobi<NN>, JacobiCfg<NN>::SMEM_BYTES);                                                   \
         cfg.dynamicSmemBytes = JacobiCfg<NN>::SMEM_BYTES;                                                            \
-        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, lg, stagger));         \
+        WCTB_CUDA(cudaLaunchKernelEx(&cfg, k_jacobi<NN>, G, conv_ws, sweeps, max_sweeps, tol, lg, stagger, skip));         \
         break;                                                                                                       \
     }
     switch (C) {
@@ -677,20 +688,23 @@ int launch_jacobi(float* G, int C, int count, float* conv_ws, int* sweeps, cudaS
 }
 
 int launch_eig_post(const float* G, const float* A0, float* lam, int C, int count, float thresh, float eps_eig,
-                    int n_content, float* sigma, float* dvec, int* kcount, cudaStream_t st) {
+                    int n_content, float* sigma, float* dvec, int* kcount, cudaStream_t st, const int* skip = nullptr) {
     if (A0 && lam) {
         dim3 gr((unsigned)(C / 16), (unsigned)count);
-        k_rayleigh<<<gr, C, 0, st>>>(A0, G, C, lam);
+        k_rayleigh<<<gr, C, 0, st>>>(A0, G, C, lam, skip);
         WCTB_CHECK_LAUNCH("k_rayleigh");
     } else {
         lam = nullptr;
     }
     dim3 grid((unsigned)cdiv(C, 8), (unsigned)count);
-    k_eig_post<<<grid, 256, 0, st>>>(G, lam, C, thresh, eps_eig, n_content, sigma, dvec, kcount);
+    k_eig_post<<<grid, 256, 0, st>>>(G, lam, C, thresh, eps_eig, n_content, sigma, dvec, kcount, skip);
     WCTB_CHECK_LAUNCH("k_eig_post");
     return 0;
 }
 
+// matfun_tc.cu: A^-1/2 / A^+1/2 by coupled Newton-Schulz on the tensor cores where every eigenvalue is kept; ok[b] = 1 there
+int launch_matfun_ns(const float* A, int C, int count, int n_first, float thresh, float eps_eig, float* out, int* ok, int* kcount,
+                     cudaStream_t st, float* info = nullptr);
 // cov_tc.cu: per-channel means and covariance (+ eps_cov I) in one pass over the features
 int launch_mean_cov(const __half* act, ActGeom g, float eps_cov, float* mean, float* G, float* A0, double* dsum, cudaStream_t st);
 
@@ -729,13 +743,17 @@ int launch_wct_level(const __half* content, int Nc, int Hc, int Wc, const __half
     if (rc) return rc;
     rc = launch_mean_cov(style, gs, eps_cov, mean + (long long)Nc * C, G + Nc * CC, A0 + Nc * CC, dsum + (long long)Nc * C, st);
     if (rc) return rc;
-    rc = launch_jacobi(G, C, np, conv, kc + np, st);
+    // fast path first: W_c = A^-1/2, C_s = A^+1/2 straight from the covariances where the threshold keeps every eigenvalue
+    int* ok = reinterpret_cast<int*>(w + L.ok);
+    rc = launch_matfun_ns(A0, C, np, Nc, thresh, eps_eig, Wcm, ok, kc, st);        // Wc and Cs are contiguous in ws (Wc then Cs)
+    if (rc < 0) return rc;
+    rc = launch_jacobi(G, C, np, conv, kc + np, st, ok);
     if (rc) return rc;
-    rc = launch_eig_post(G, A0, lam, C, np, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, np, thresh, eps_eig, Nc, sigma, dvec, kc, st, ok);
     if (rc) return rc;
     // W_c (whitening) per content frame, C_s (colouring) per style
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)np);
-    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C);   // Wc and Cs are contiguous in ws (Wc then Cs)
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C, ok);
     WCTB_CHECK_LAUNCH("k_outer_gemm(W)");
     dim3 gt((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Nc);
     k_outer_gemm<<<gt, 256, 0, st>>>(Csm, Ns == 1 ? 0 : CC, Wcm, CC, nullptr, 0, T, CC, C);   // T = C_s W_c (C_s symmetric)
@@ -795,12 +813,15 @@ int launch_wct_style_prepare(const __half* style, int Ns, int Hs, int Ws, int C,
     float* lam = reinterpret_cast<float*>(w + L.lam);
     int rc = launch_mean_cov(style, ActGeom(Ns, Hs, Ws, C), eps_cov, mean_s, G, A0, dsum, st);
     if (rc) return rc;
-    rc = launch_jacobi(G, C, Ns, conv, kc + Ns, st);
+    int* ok = reinterpret_cast<int*>(w + L.ok);
+    rc = launch_matfun_ns(A0, C, Ns, /*n_first=*/0, thresh, eps_eig, Cs, ok, kc, st);     // C_s = A^+1/2 where every eigenvalue is kept
+    if (rc < 0) return rc;
+    rc = launch_jacobi(G, C, Ns, conv, kc + Ns, st, ok);
     if (rc) return rc;
-    rc = launch_eig_post(G, A0, lam, C, Ns, thresh, eps_eig, /*n_content=*/0, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, Ns, thresh, eps_eig, /*n_content=*/0, sigma, dvec, kc, st, ok);
     if (rc) return rc;
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Ns);
-    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Cs, CC, C);
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Cs, CC, C, ok);
     WCTB_CHECK_LAUNCH("k_outer_gemm(Cs)");
     return 0;
 }
@@ -839,12 +860,15 @@ int launch_wct_apply(const __half* content, int Nc, int Hc, int Wc, int C, const
     float* lam = reinterpret_cast<float*>(w + L.lam);
     int rc = launch_mean_cov(content, ActGeom(Nc, Hc, Wc, C), eps_cov, mean, G, A0, dsum, st);
     if (rc) return rc;
-    rc = launch_jacobi(G, C, Nc, conv, kc + Nc, st);
+    int* ok = reinterpret_cast<int*>(w + L.ok);
+    rc = launch_matfun_ns(A0, C, Nc, /*n_first=*/Nc, thresh, eps_eig, Wcm, ok, kc, st);   // W_c = A^-1/2 where every eigenvalue is kept
+    if (rc < 0) return rc;
+    rc = launch_jacobi(G, C, Nc, conv, kc + Nc, st, ok);
     if (rc) return rc;
-    rc = launch_eig_post(G, A0, lam, C, Nc, thresh, eps_eig, Nc, sigma, dvec, kc, st);
+    rc = launch_eig_post(G, A0, lam, C, Nc, thresh, eps_eig, Nc, sigma, dvec, kc, st, ok);
     if (rc) return rc;
     dim3 gg((unsigned)(C / 64), (unsigned)(C / 64), (unsigned)Nc);
-    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C);
+    k_outer_gemm<<<gg, 256, 0, st>>>(G, CC, G, CC, dvec, C, Wcm, CC, C, ok);
     WCTB_CHECK_LAUNCH("k_outer_gemm(Wc)");
     k_outer_gemm<<<gg, 256, 0, st>>>(Cs, Ns == 1 ? 0 : CC, Wcm, CC, nullptr, 0, T, CC, C);   // T = C_s W_c
     WCTB_CHECK_LAUNCH("k_outer_gemm(T)");
@@ -1133,11 +1157,11 @@ int launch_style_swap_level(const __half* content, int Hc, int Wc, const __half*
     if (rc) return rc;
     rc = launch_mean_cov(style, gs, eps_cov, mean + C, G + CC, A0 + CC, dsum + C, st);
     if (rc) return rc;
-    rc = launch_jacobi(G, C, 2, conv, kc + 2, st);
+    rc = launch_jacobi(G, C, 2, conv, kc + 2, st, nullptr);
     if (rc) return rc;
     rc = launch_eig_post(G, A0, lam, C, 2, thresh, 0.f, 2, sigma, dvec, kc, st);          // S^-1/2 for BOTH (ops.py:187,193)
     if (rc) return rc;
-    k_eig_post<<<dim3((unsigned)cdiv(C, 8), 1), 256, 0, st>>>(G + CC, lam + C, C, thresh, 0.f, 0, sigma2, dvec2, nullptr);   // S^+1/2 (ops.py:203)
+    k_eig_post<<<dim3((unsigned)cdiv(C, 8), 1), 256, 0, st>>>(G + CC, lam + C, C, thresh, 0.f, 0, sigma2, dvec2, nullptr, nullptr);   // S^+1/2 (ops.py:203)
     WCTB_CHECK_LAUNCH("k_eig_post(colour)");
     dim3 g2((unsigned)(C / 64), (unsigned)(C / 64), 2), g1((unsigned)(C / 64), (unsigned)(C / 64), 1);
     k_outer_gemm<<<g2, 256, 0, st>>>(G, CC, G, CC, dvec, C, mats, CC, C);                   // W_c, W_s

@@ -24,6 +24,15 @@ WCTB200_API int wctb200_debug_set_cov_stages(int n);
 WCTB200_API int wctb200_debug_set_conv_products(int n);
 /* decoder tail (64 -> 3): 1 = transposed tensor-core product (conv_tail_tc.cu, default), 0 = SIMT kernels of layers.cu */
 WCTB200_API int wctb200_debug_set_conv_tail_tc(int on);
+/* whitening / colouring matrices: mode 1 (default) = coupled Newton-Schulz on the tensor cores where the threshold keeps
+ * every eigenvalue (matfun_tc.cu), Jacobi eigensolver otherwise; mode 0 = always the eigensolver.  max_it: iteration budget
+ * (0 = leave unchanged).  Returns the mode. */
+WCTB200_API int wctb200_debug_set_matfun(int mode, int max_it);
+/* the fast path alone: A [count][C][C] fp32 (device) -> out = A^-1/2 for the first n_first matrices, A^+1/2 for the rest;
+ * ok[b] = 1 where the guard accepted the result (device int[count]); info (device float[count][4], may be null) receives
+ * (iteration of convergence or -1, last residual max|I - ZY|, lower bound of lambda_min, ||A||_F) */
+WCTB200_API int wctb200_debug_matfun(const float* A, int C, int count, int n_first, float thresh, float eps_eig, float* out, int* ok,
+                                     float* info, void* stream);
 /* encoder head (3 -> 64): 1 = tensor cores with an operand built in shared memory (conv_head_tc.cu, default), 0 = SIMT */
 WCTB200_API int wctb200_debug_set_conv_head_tc(int on);
 #ifdef __cplusplus
