@@ -43,7 +43,8 @@ struct NsCfg {
     static constexpr int CH = 4;                                       // k-iterations per accumulation chunk
     static constexpr int THREADS = 192;
     static constexpr int AUX_BYTES = 512;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;
+    static constexpr int STG_BYTES = 4 * 8192;                         // per-epilogue-warp transposition buffer (coalesced row stores)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + STG_BYTES + 1024;
 };
 
 struct NsState {                 // per matrix
@@ -227,25 +228,59 @@ ns_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     acc[j] = fmaf(-0.5f, acc[j], 1.5f * d);          // T = (3 I - Z Y) / 2
                 }
             }
-            const bool f32 = p.f32_rule != 0 && ((p.f32_rule == 1) == (b < p.n_first)) && !*abort_flag;
+            // the fp32 result and ||Z||_F^2 are only needed from the FINAL iterate: the mode-1 product of this very iteration
+            // (earlier in stream order) has set conv_iter = it for a matrix whose residual passed
+            const bool final_it = *reinterpret_cast<volatile int*>(&p.state[b].conv_iter) == p.it;
+            const bool f32 = final_it && p.f32_rule != 0 && ((p.f32_rule == 1) == (b < p.n_first));
             const float fs = f32 ? p.state[b].f32_scale : 0.f;
-            __half* o_hi = p.out_split + ((long long)(b * 2) * p.n + row) * p.n + col0;
-            __half* o_lo = o_hi + (long long)p.n * p.n;
-            float* o_f = p.out_f32 + ((long long)b * p.n + row) * p.n + col0;
+            // Row-major stores through a per-warp transposition buffer: a thread owns a ROW of the tile, so direct stores
+            // would put 32 lanes on 32 different rows (ncu: 32 half-filled sectors per request, lg_throttle).  64 columns at a
+            // time go through 8 KB of shared memory (XOR-swizzled 16-byte chunks) and leave as full 128 / 256-byte row segments.
+            uint8_t* stg = aux + Cfg::AUX_BYTES + e * 8192;
+            const int rowbase = mi * Cfg::BM + g * 32;
             if (!*abort_flag) {
 #pragma unroll
-                for (int q = 0; q < Cfg::BN / 8; ++q) {
-                    Half8 hi, lo;
-                    split8(acc + q * 8, hi, lo);
-                    *reinterpret_cast<Half8*>(o_hi + q * 8) = hi;
-                    *reinterpret_cast<Half8*>(o_lo + q * 8) = lo;
-                    if (f32) {
-                        *reinterpret_cast<float4*>(o_f + q * 8) = make_float4(acc[q * 8] * fs, acc[q * 8 + 1] * fs, acc[q * 8 + 2] * fs, acc[q * 8 + 3] * fs);
-                        *reinterpret_cast<float4*>(o_f + q * 8 + 4) = make_float4(acc[q * 8 + 4] * fs, acc[q * 8 + 5] * fs, acc[q * 8 + 6] * fs, acc[q * 8 + 7] * fs);
+                for (int h = 0; h < Cfg::BN / 64; ++h) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        Half8 hi, lo;
+                        split8(acc + h * 64 + q * 8, hi, lo);
+                        const int slot = q ^ (lane & 7);
+                        *reinterpret_cast<Half8*>(stg + (lane * 8 + slot) * 16) = hi;
+                        *reinterpret_cast<Half8*>(stg + 4096 + (lane * 8 + slot) * 16) = lo;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = j * 4 + (lane >> 3), c = lane & 7;
+                        const int slot = c ^ (rr & 7);
+                        const Half8 hi = *reinterpret_cast<const Half8*>(stg + (rr * 8 + slot) * 16);
+                        const Half8 lo = *reinterpret_cast<const Half8*>(stg + 4096 + (rr * 8 + slot) * 16);
+                        __half* o = p.out_split + ((long long)(b * 2) * p.n + rowbase + rr) * p.n + col0 + h * 64 + c * 8;
+                        *reinterpret_cast<Half8*>(o) = hi;
+                        *reinterpret_cast<Half8*>(o + (long long)p.n * p.n) = lo;
+                    }
+                    __syncwarp();
+                    if (f32) {                                   // warp-uniform (one matrix per tile)
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const float* a4 = acc + h * 64 + q * 4;
+                            const int slot = q ^ (lane & 15);
+                            *reinterpret_cast<float4*>(stg + (lane * 16 + slot) * 16) = make_float4(a4[0] * fs, a4[1] * fs, a4[2] * fs, a4[3] * fs);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int rr = j * 2 + (lane >> 4), c = lane & 15;
+                            const int slot = c ^ (rr & 15);
+                            const float4 v = *reinterpret_cast<const float4*>(stg + (rr * 16 + slot) * 16);
+                            *reinterpret_cast<float4*>(p.out_f32 + ((long long)b * p.n + rowbase + rr) * p.n + col0 + h * 64 + c * 4) = v;
+                        }
+                        __syncwarp();
                     }
                 }
             }
-            if (p.want_zz) {
+            if (p.want_zz && final_it) {
 #pragma unroll
                 for (int j = 0; j < Cfg::BN; ++j) zz = fmaf(acc[j], acc[j], zz);
 #pragma unroll
@@ -260,7 +295,7 @@ ns_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (e == 0 && lane == 0) {
-                if (p.want_zz) p.zz_slots[(long long)b * tpm + r] = (red[0] + red[1]) + (red[2] + red[3]);   // fixed order
+                if (p.want_zz && final_it) p.zz_slots[(long long)b * tpm + r] = (red[0] + red[1]) + (red[2] + red[3]);   // fixed order
                 if (p.mode == 1) {
                     const int done = atomicAdd(&p.state[b].tiles_done, 1);
                     if (done == tpm - 1) {                           // last tile of this matrix in this launch
