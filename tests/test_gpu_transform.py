@@ -243,3 +243,88 @@ def test_style_swap_level_matches_oracle(case):
     assert err <= 1e-3
     padded = U.act_raw_padded(out, 1, hwc[0], hwc[1], C)
     assert np.array_equal(padded, np.pad(padded[:, 1:-1, 1:-1], ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect"))
+
+
+# ---------------------------------------------------------------------------
+# matrix-function fast path (matfun_tc.cu): W_c = A^-1/2, C_s = A^+1/2 by coupled Newton-Schulz where k = C
+# ---------------------------------------------------------------------------
+def _cov_batch(C, HW, count, decay, seed, dead=0):
+    out = []
+    for i in range(count):
+        r = np.random.default_rng(seed + i)
+        X = np.maximum(r.standard_normal((C, C)) / np.sqrt(C) @ r.standard_normal((C, HW)) + 0.3, 0)
+        X *= np.exp(-decay * np.arange(C) / C)[:, None]
+        if dead:
+            X[r.choice(C, dead, replace=False)] = 0.0
+        X -= X.mean(1, keepdims=True)
+        out.append((X @ X.T / (HW - 1) + 1e-8 * np.eye(C)).astype(np.float32))
+    return np.stack(out)
+
+
+def _matfun(A, n_first, thresh=1e-5, eps_eig=0.0):
+    count, C = A.shape[0], A.shape[1]
+    dA = U.dev(A)
+    out = torch.full_like(dA, float("nan"))
+    ok = torch.zeros(count, dtype=torch.int32, device="cuda")
+    info = torch.zeros(count * 4, dtype=torch.float32, device="cuda")
+    _capi.check(U.lib().wctb200_debug_matfun(dA.data_ptr(), C, count, n_first, thresh, eps_eig, out.data_ptr(), ok.data_ptr(),
+                                             info.data_ptr(), U.stream()))
+    U.check_device()
+    return out.cpu().numpy(), ok.cpu().numpy(), info.cpu().numpy().reshape(count, 4)
+
+
+@pytest.mark.parametrize("C,HW", [(128, 4096), (256, 2048), (512, 1024), (512, 4096)])
+def test_matfun_fast_path_matches_float64_eigh(C, HW):
+    """Well-conditioned covariances (every eigenvalue far above 1e-5): the guard accepts all of them, A^-1/2 (first half of the
+    batch) and A^+1/2 (second half) agree with the float64 eigendecomposition to 2e-4 of their largest entry (measured
+    3e-5 .. 6e-5), eps_eig included (wct_np semantics)."""
+    for eps_eig in (0.0, 1e-5):
+        A = _cov_batch(C, HW, 6, 0.0, 7 * C + HW)
+        out, ok, info = _matfun(A, 3, eps_eig=eps_eig)
+        assert ok.tolist() == [1] * 6, (ok, info)
+        for b in range(6):
+            w, v = np.linalg.eigh(A[b].astype(np.float64))
+            ref = (v * (w + eps_eig) ** (-0.5 if b < 3 else 0.5)) @ v.T
+            err = np.abs(out[b] - ref).max() / np.abs(ref).max()
+            assert err <= 2e-4, (C, b, err)
+            assert info[b, 2] > 1e-5 and info[b, 2] <= w[0] * 1.001 + eps_eig          # the bound really is a lower bound of lambda_min
+
+
+@pytest.mark.parametrize("C", [128, 512])
+def test_matfun_guard_leaves_hard_matrices_to_the_eigensolver(C):
+    """Rank-deficient covariances (dead channels: eigenvalues at the 1e-8 regulariser), eigenvalues straddling the 1e-5 threshold and
+    a degenerate all-zero matrix must NOT take the fast path; a mixed batch flags exactly the good ones."""
+    good = _cov_batch(C, 4096, 2, 0.0, 11)
+    dead = _cov_batch(C, 4096, 2, 0.0, 12, dead=5)
+    w, v = np.linalg.eigh(good[0].astype(np.float64))
+    w2 = w.copy(); w2[:3] = [4e-6, 9e-6, 2e-5]                                  # two eigenvalues below, one just above the threshold
+    near = ((v * w2) @ v.T).astype(np.float32)[None]
+    zero = np.zeros((1, C, C), np.float32)
+    A = np.concatenate([good[:1], dead[:1], near, zero, good[1:], dead[1:]])
+    out, ok, info = _matfun(A, 3)
+    assert ok.tolist() == [1, 0, 0, 0, 1, 0], (ok, info)
+
+
+def test_wct_level_fast_path_equals_eigensolver_path():
+    """The same WCT level through the matrix-function fast path (default) and with it switched off (Jacobi eigensolver): k = C on both,
+    zero sweeps reported by the fast path, stylised features within 3e-4 of each other and each within the gate of the oracle."""
+    rng = np.random.default_rng(5)
+    C = 256
+    mix = rng.standard_normal((C, C)) / np.sqrt(C)
+    content = np.maximum(rng.standard_normal((2, 24, 40, C)) @ mix + 0.3, 0).astype(np.float32)
+    style = np.maximum(rng.standard_normal((2, 30, 28, C)) @ mix.T + 0.3, 0).astype(np.float32)
+    lib = U.lib()
+    res = {}
+    for mode in (1, 0):
+        lib.wctb200_debug_set_matfun(mode, 0)
+        try:
+            res[mode] = _run_wct(content, style, 0.7, "tf")
+        finally:
+            lib.wctb200_debug_set_matfun(1, 0)
+    (fast, kf), (slow, ks) = res[1], res[0]
+    assert kf[:4].tolist() == [C] * 4 and ks[:4].tolist() == [C] * 4
+    assert kf[4:].tolist() == [0] * 4 and min(ks[4:]) > 0                         # sweeps: none on the fast path
+    assert np.abs(fast - slow).max() <= 3e-4, np.abs(fast - slow).max()
+    for i in range(2):
+        ref = ref_ops.wct_tf(content[i:i + 1].astype(np.float64), style[i:i + 1].astype(np.float64), 0.7)
+        assert np.abs(fast[i:i + 1] - ref).max() <= 1e-3 and np.abs(slow[i:i + 1] - ref).max() <= 1e-3

@@ -141,6 +141,12 @@ class Engine(object):
         rec["bytes"] += bytes_
         rec["launches"] += nkernels
 
+    @staticmethod
+    def _matfun_launches(C):
+        """kernels the matrix-function fast path adds to a WCT call (matfun_tc.cu: init + 3 products x 16 iterations + guard;
+        launches of converged matrices return at once but are launches all the same)"""
+        return 2 + 3 * 16 if C >= 128 else 0
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -258,7 +264,7 @@ class Engine(object):
         kbuf = torch.empty(2 * (content.N + style.N), dtype=torch.int32, device=self.device) if want_info else None
         C = content.C
         hwc, hws = content.H * content.W, style.H * style.W
-        self._call("wct_level[C%d]" % C, 14, self.lib.wctb200_wct_level, content.ptr, content.N, content.H, content.W,
+        self._call("wct_level[C%d]" % C, 14 + self._matfun_launches(C), self.lib.wctb200_wct_level, content.ptr, content.N, content.H, content.W,
                    style.ptr, style.N, style.H, style.W, C, float(alpha), sem["eps_cov"], sem["eps_eig"],
                    sem["thresh"], sem["readd"], out.ptr, kbuf.data_ptr() if want_info else None, ws.data_ptr(),
                    ws.numel(), st, flops=2.0 * C * C * (2 * content.N * hwc + style.N * hws),
@@ -293,7 +299,7 @@ class Engine(object):
         state = torch.empty(self.lib.wctb200_wct_style_state_bytes(C, style.N), dtype=torch.uint8, device=self.device)
         ws = self._workspace(C, 0, style.N)
         hws = style.H * style.W
-        self._call("wct_style[C%d]" % C, 7, self.lib.wctb200_wct_style_prepare, style.ptr, style.N, style.H, style.W, C,
+        self._call("wct_style[C%d]" % C, 7 + self._matfun_launches(C), self.lib.wctb200_wct_style_prepare, style.ptr, style.N, style.H, style.W, C,
                    sem["eps_cov"], sem["eps_eig"], sem["thresh"], state.data_ptr(), ws.data_ptr(), ws.numel(), st,
                    flops=2.0 * C * C * style.N * hws, bytes_=4.0 * C * style.N * hws)
         return state
@@ -306,7 +312,7 @@ class Engine(object):
         ws = self._workspace(C, content.N, 0)
         kbuf = torch.empty(2 * (content.N + n_style), dtype=torch.int32, device=self.device) if want_info else None
         hwc = content.H * content.W
-        self._call("wct_level[C%d]" % C, 9, self.lib.wctb200_wct_apply, content.ptr, content.N, content.H, content.W, C,
+        self._call("wct_level[C%d]" % C, 9 + self._matfun_launches(C), self.lib.wctb200_wct_apply, content.ptr, content.N, content.H, content.W, C,
                    state.data_ptr(), n_style, float(alpha), sem["eps_cov"], sem["eps_eig"], sem["thresh"], sem["readd"],
                    out.ptr, kbuf.data_ptr() if want_info else None, ws.data_ptr(), ws.numel(), st,
                    flops=2.0 * C * C * 2 * content.N * hwc, bytes_=4.0 * C * 2 * content.N * hwc)
