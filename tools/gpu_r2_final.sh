@@ -17,4 +17,6 @@ timeout 300 python tools/tail_bench.py 16 > gpurun_out/r2z_tail_bench.txt 2>&1
 timeout 300 python tools/head_bench.py 16 > gpurun_out/r2z_head_bench.txt 2>&1
 timeout 300 python tools/image_ops_bench.py > gpurun_out/r2z_image_ops_bench.txt 2>&1
 timeout 300 python tools/timeline.py 30 2 1 > gpurun_out/r2z_timeline.txt 2>&1
+timeout 300 python tools/matfun_bench.py > gpurun_out/r2z_matfun_bench.txt 2>&1
+timeout 300 python tools/k_probe.py > gpurun_out/r2z_k_probe.txt 2>&1
 head -c 400 gpurun_out/r2z_bench_n1.json; echo; cat gpurun_out/r2z_other_configs.json | tail -12

@@ -7,4 +7,5 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:cov_tc_kernel -o gpurun_out/r2_cov -f python tools/cov_once.py 16 > gpurun_out/r2_ncu_cov.log 2>&1
 ls -la gpurun_out/r2_*
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_(tail|head)_tc_kernel" -s 2 -c 2 -o gpurun_out/r2_tail -f python tools/tail_head_once.py 16 > gpurun_out/r2_ncu_tail.log 2>&1
-ls -la gpurun_out/r2_tail*
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ns_gemm -s 55 -c 1 -o gpurun_out/r2_nsgemm -f python tools/matfun_once.py > gpurun_out/r2_ncu_nsgemm.log 2>&1
+ls -la gpurun_out/r2_tail* gpurun_out/r2_nsgemm*

@@ -106,4 +106,8 @@ if os.path.exists(tp):
     full(tp, os.path.join(dst, "r02_ncu_full_tail_head.txt"),
          "ncu --set full --clock-control none -k regex:conv_(tail|head)_tc_kernel -s 2 -c 2 python tools/tail_head_once.py 16   (16 frames 512x512: decoder tail 64->3, encoder head 3->64)",
          note="tail: compulsory traffic 16*514*514*256 B read + 16*512*512*12 B written = 1.13 GB; head: 16*512*512*12 B read + 16*514*514*256 B written = 1.13 GB.")
+np_ = os.path.join(src, "r2_nsgemm.ncu-rep")
+if os.path.exists(np_):
+    full(np_, os.path.join(dst, "r02_ncu_full_ns_gemm.txt"),
+         "ncu --set full --clock-control none -k regex:ns_gemm -s 55 -c 1 python tools/matfun_once.py   (one batched 512x512x512 product of the Newton-Schulz iteration, 15 matrices = 240 tiles of 128x128)")
 print("wrote summaries to", dst)
