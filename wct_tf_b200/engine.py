@@ -143,9 +143,9 @@ class Engine(object):
 
     @staticmethod
     def _matfun_launches(C):
-        """kernels the matrix-function fast path adds to a WCT call (matfun_tc.cu: init + 3 products x 16 iterations + guard;
+        """kernels the matrix-function fast path adds to a WCT call (matfun_tc.cu: norm + init + 3 products x 16 iterations + guard;
         launches of converged matrices return at once but are launches all the same)"""
-        return 2 + 3 * 16 if C >= 128 else 0
+        return 3 + 3 * 16 if C >= 128 else 0
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
