@@ -260,3 +260,36 @@ def test_tf_checkpoint_snappy_block_decoder():
     # copy with a 1-byte offset (tag type 1: len 4..11, offset < 2048): "xyxyxyxyxy"
     comp = bytes([10, (2 - 1) << 2]) + b"xy" + bytes([((8 - 4) << 2) | 1, 2])
     assert _snappy_decompress(comp) == b"xy" * 5
+
+
+def test_device_image_geometry_matches_the_oracle_helpers(monkeypatch):
+    """wct_tf_b200.device_image computes sizes and crop windows on the host and hands them to ONE device resample call; the
+    arithmetic (utils.py:29-67: short-side rule with Python-3 rounding, upscale-when-too-small, centred windows) is checked here
+    against the oracle's shapes without a GPU by intercepting the resample call."""
+    import torch
+    from oracle import image_ops as O
+    from wct_tf_b200 import device_image as D
+
+    calls = []
+
+    def fake_imresize(img, hw, window=None):
+        h, w = (img.shape[0], img.shape[1])
+        calls.append((h, w, tuple(int(v) for v in hw), None if window is None else tuple(int(v) for v in window)))
+        oh, ow = (hw if window is None else window[2:])
+        return torch.zeros((int(oh), int(ow), 3), dtype=torch.uint8)
+
+    monkeypatch.setattr(D, "imresize", fake_imresize)
+    rng = np.random.default_rng(0)
+    for (h, w) in [(40, 64), (64, 40), (37, 37), (300, 451), (5, 9), (501, 333)]:
+        img_np = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        img = torch.from_numpy(img_np)
+        for size in (16, 25, 96, 512):
+            assert tuple(D.resize_to(img, size).shape) == O.resize_to(img_np, size).shape
+            assert tuple(D.center_crop(img, size).shape) == O.center_crop(img_np, size).shape
+            hh, ww, hw, win = calls[-1]
+            assert win[2:] == (size, size) and win[0] == (hw[0] - size) // 2 and win[1] == (hw[1] - size) // 2
+            assert win[0] >= 0 and win[1] >= 0 and win[0] + size <= hw[0] and win[1] + size <= hw[1]
+        for (ht, wt) in [(32, 32), (h, w), (h + 9, w), (h, 2 * w), (96, 112)]:
+            assert tuple(D.center_crop_to(img, ht, wt).shape) == O.center_crop_to(img_np, ht, wt).shape
+            hh, ww, hw, win = calls[-1]
+            assert win[0] + ht <= hw[0] and win[1] + wt <= hw[1]
