@@ -136,6 +136,9 @@ def make_config(world, B, adain, groups, scaling, global_batch):
            "l2": "two input sets alternate; per-step activation working set (>5 GB) >> 126 MB L2",
            "precision": "fp32-class: split-fp16 pairs (22-23 bits, power-of-two scaled weights) x3 products on tcgen05, "
                         "fp32 accumulate (TMEM chunks of 4 k-iterations summed in registers)",
+           "transform": "whitening / colouring matrices per frame and level from the frame's own covariances: coupled Newton-Schulz "
+                        "on tcgen05 where the 1e-5 threshold provably keeps every eigenvalue (all matrices of this synthetic "
+                        "workload: k = C), Jacobi eigendecomposition otherwise",
            "streams": "%d sub-batch group(s) per step, each a (content, style) stream pair" % groups}
     if scaling == "strong":
         cfg["workload"] = ("configs[2]: batch of %d 512x512 frames, ONE shared 512x512 style, 5 levels, alpha=0.8, wct_tf "
