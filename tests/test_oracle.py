@@ -178,3 +178,19 @@ def test_image_oracle_helpers_follow_the_reference_rules():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "coral_keep_colors.npz"))
     assert np.abs(image_ops.coral(g["style"] / 255., g["content"] / 255.) - g["coraled"]).max() < 1e-9   # reference's coral.py output
     assert np.array_equal(image_ops.preserve_colors(g["style"], g["content"]), g["out"])
+
+
+def test_resample_oracle_random_sizes_against_pillow():
+    """40 random (size, target) pairs incl. extreme aspect ratios and 1-4 channels: the oracle stays bit-identical to Pillow."""
+    from PIL import Image
+    from oracle import image_ops
+    rng = np.random.default_rng(2024)
+    for _ in range(40):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        oh, ow = int(rng.integers(1, 120)), int(rng.integers(1, 120))
+        c = int(rng.choice([1, 3, 4]))
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        mode = {1: "L", 3: "RGB", 4: "RGBX"}[c]
+        pil = Image.fromarray(img[:, :, 0] if c == 1 else img, mode)
+        want = np.asarray(pil.resize((ow, oh), Image.BILINEAR)).reshape(oh, ow, c)
+        assert np.array_equal(image_ops.resample_bilinear_u8(img, oh, ow), want), (h, w, c, oh, ow)
